@@ -1,0 +1,151 @@
+// Element-level quadrature of the nonlinear terms, shared by all stencil kernels.
+//
+// The reference integrates every form with FIAT's degree-3 "default" rules because every
+// driver sets parameters["form_compiler"]["quadrature_degree"] = 3 (dolfin/bench1.py:14-16):
+//   triangle    : Strang-Fix 6 points, weights 1/12, barycentric = permutations of (A, B, C)
+//   tetrahedron : Zienkiewicz-Taylor 5 points: centroid (weight -0.8/6) and four points with
+//                 one barycentric 1/2 and three 1/6 (weight 0.45/6 each)
+// Both are inexact for the quartic/.. free energies, and parity with FEniCS depends on using
+// exactly these rules.  A "cell patch" is what one structured cell holds:
+// the 6 Kuhn tetrahedra of a cube (DOLFIN BoxMesh) or the 4 triangles of a crossed square.
+#pragma once
+#include "pfh_problems.cuh"
+
+#define PFH_DEV PFH_HD
+
+namespace elem {
+
+constexpr double SF_A = 0.659027622374092, SF_B = 0.231933368553031, SF_C = 0.109039009072877;
+constexpr double TET_W0 = -0.8 / 6.0, TET_W1 = 0.45 / 6.0;
+
+// local vertices of the six tetrahedra of a cube; local index = lx + 2 ly + 4 lz
+PFH_HD constexpr int kuhn(int t, int a) {
+  constexpr int K[6][4] = {{0, 1, 3, 7}, {0, 1, 7, 5}, {0, 5, 7, 4}, {0, 3, 2, 7}, {0, 6, 4, 7}, {0, 2, 6, 7}};
+  return K[t][a];
+}
+// local vertices of the four triangles of a crossed square: 0..3 corners v0..v3, 4 centre
+PFH_HD constexpr int tri(int t, int a) {
+  constexpr int T[4][3] = {{0, 1, 4}, {0, 2, 4}, {1, 3, 4}, {2, 3, 4}};
+  return T[t][a];
+}
+// barycentric coordinates of the 6 Strang-Fix points
+PFH_HD constexpr double sf(int q, int a) {
+  constexpr double L[6][3] = {{SF_C, SF_A, SF_B}, {SF_B, SF_A, SF_C}, {SF_C, SF_B, SF_A},
+                              {SF_A, SF_B, SF_C}, {SF_B, SF_C, SF_A}, {SF_A, SF_C, SF_B}};
+  return L[q][a];
+}
+
+// Nonlinear load of one cube: out[o][k] += int_{cube} phi_k g_o(u_h)   (JAC: g -> dg(u_h; x_h))
+template <class P, bool JAC>
+PFH_DEV void cube_load(const P& prob, const double (&u)[P::NIN][8], const double (&x)[P::NIN][8], double detJ,
+                       double (&out)[P::NOUT][8]) {
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    double s[P::NIN], sx[P::NIN];
+#pragma unroll
+    for (int f = 0; f < P::NIN; ++f) {
+      s[f] = u[f][kuhn(t, 0)] + u[f][kuhn(t, 1)] + u[f][kuhn(t, 2)] + u[f][kuhn(t, 3)];
+      sx[f] = JAC ? x[f][kuhn(t, 0)] + x[f][kuhn(t, 1)] + x[f][kuhn(t, 2)] + x[f][kuhn(t, 3)] : 0.0;
+    }
+    double uq[P::NIN], xq[P::NIN], g0[P::NOUT], gj[4][P::NOUT];
+#pragma unroll
+    for (int f = 0; f < P::NIN; ++f) {
+      uq[f] = 0.25 * s[f];
+      xq[f] = 0.25 * sx[f];
+    }
+    if (JAC) prob.dg(uq, xq, g0); else prob.g(uq, g0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int f = 0; f < P::NIN; ++f) {
+        uq[f] = s[f] * (1.0 / 6.0) + u[f][kuhn(t, j)] * (1.0 / 3.0);
+        xq[f] = JAC ? sx[f] * (1.0 / 6.0) + x[f][kuhn(t, j)] * (1.0 / 3.0) : 0.0;
+      }
+      if (JAC) prob.dg(uq, xq, gj[j]); else prob.g(uq, gj[j]);
+    }
+#pragma unroll
+    for (int o = 0; o < P::NOUT; ++o) {
+      const double S = gj[0][o] + gj[1][o] + gj[2][o] + gj[3][o];
+      const double base = detJ * (TET_W0 * 0.25 * g0[o] + (TET_W1 / 6.0) * S);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[o][kuhn(t, j)] += base + detJ * (TET_W1 / 3.0) * gj[j][o];
+    }
+  }
+}
+
+// Nonlinear load of one crossed square: out[o][k] += int_{square} phi_k g_o(u_h), k = 0..4
+template <class P, bool JAC>
+PFH_DEV void square_load(const P& prob, const double (&u)[P::NIN][5], const double (&x)[P::NIN][5], double detJ,
+                         double (&out)[P::NOUT][5]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    double acc[P::NOUT][3];
+#pragma unroll
+    for (int o = 0; o < P::NOUT; ++o) acc[o][0] = acc[o][1] = acc[o][2] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      double uq[P::NIN], xq[P::NIN], g[P::NOUT];
+#pragma unroll
+      for (int f = 0; f < P::NIN; ++f) {
+        uq[f] = sf(q, 0) * u[f][tri(t, 0)] + sf(q, 1) * u[f][tri(t, 1)] + sf(q, 2) * u[f][tri(t, 2)];
+        xq[f] = JAC ? sf(q, 0) * x[f][tri(t, 0)] + sf(q, 1) * x[f][tri(t, 1)] + sf(q, 2) * x[f][tri(t, 2)] : 0.0;
+      }
+      if (JAC) prob.dg(uq, xq, g); else prob.g(uq, g);
+#pragma unroll
+      for (int o = 0; o < P::NOUT; ++o) {
+        acc[o][0] += sf(q, 0) * g[o];
+        acc[o][1] += sf(q, 1) * g[o];
+        acc[o][2] += sf(q, 2) * g[o];
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < P::NOUT; ++o)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) out[o][tri(t, a)] += (detJ / 12.0) * acc[o][a];
+  }
+}
+
+// int_{cube} e(u_h), int_{cube} m(u_h)  (all NF fields)
+template <class P>
+PFH_DEV void cube_energy(const P& prob, const double (&u)[P::NF][8], double detJ, double& E, double& Mm) {
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    double s[P::NF], uq[P::NF];
+#pragma unroll
+    for (int f = 0; f < P::NF; ++f) {
+      s[f] = u[f][kuhn(t, 0)] + u[f][kuhn(t, 1)] + u[f][kuhn(t, 2)] + u[f][kuhn(t, 3)];
+      uq[f] = 0.25 * s[f];
+    }
+    double e = TET_W0 * prob.e(uq), m = TET_W0 * prob.m(uq);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int f = 0; f < P::NF; ++f) uq[f] = s[f] * (1.0 / 6.0) + u[f][kuhn(t, j)] * (1.0 / 3.0);
+      e += TET_W1 * prob.e(uq);
+      m += TET_W1 * prob.m(uq);
+    }
+    E += detJ * e;
+    Mm += detJ * m;
+  }
+}
+
+template <class P>
+PFH_DEV void square_energy(const P& prob, const double (&u)[P::NF][5], double detJ, double& E, double& Mm) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    double e = 0.0, m = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      double uq[P::NF];
+#pragma unroll
+      for (int f = 0; f < P::NF; ++f)
+        uq[f] = sf(q, 0) * u[f][tri(t, 0)] + sf(q, 1) * u[f][tri(t, 1)] + sf(q, 2) * u[f][tri(t, 2)];
+      e += prob.e(uq);
+      m += prob.m(uq);
+    }
+    E += (detJ / 12.0) * e;
+    Mm += (detJ / 12.0) * m;
+  }
+}
+
+}  // namespace elem

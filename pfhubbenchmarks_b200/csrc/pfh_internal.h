@@ -1,0 +1,239 @@
+// Internal declarations shared by the translation units of libpfh_b200.so.
+// Host-side C++; device-side descriptors are PODs passed to kernels by value.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pfh_b200.h"
+
+#define PFH_MAX_FIELDS 6
+
+struct PfhError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+void pfh_set_error(const std::string& msg);
+
+#define PFH_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      char b__[512];                                                                           \
+      snprintf(b__, sizeof b__, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, \
+               __LINE__, cudaGetErrorString(e__));                                             \
+      throw PfhError(b__);                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define PFH_CHECK(cond, msg)                  \
+  do {                                        \
+    if (!(cond)) throw PfhError(std::string(msg)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Mesh descriptors (device PODs).  Stencil coefficient tables are built on the host by
+// assembling the P1 element matrices of the reference's meshes (pfh_tables.cpp).
+// ------------------------------------------------------------------------------------------
+
+// 3-D Kuhn mesh = df.BoxMesh (dolfin/b13d.py:24-26).  Offsets of the 15-point P1 stencil:
+//  0 self | 1 +x 2 -x 3 +y 4 -y 5 +z 6 -z | 7 +x+y 8 -x-y 9 +y+z 10 -y-z 11 +x+z 12 -x-z 13 +xyz 14 -xyz
+// The stiffness matrix only populates offsets 0..6 (checked when the tables are built).
+#define PFH_NOFF3 15
+#define PFH_NKOFF3 7
+struct Mesh3 {
+  int nxv, nyv, nzv;   // global vertex counts per direction
+  int z0, nzl;         // first owned global plane, number of owned planes
+  long long nxy;       // nxv*nyv
+  long long n_owned;   // nxy*nzl
+  double hx, hy, hz, detJ;  // detJ = hx*hy*hz = 6|T|
+  double mI[PFH_NOFF3];     // interior mass row
+  double kI[PFH_NKOFF3];    // interior stiffness row
+  const double* mT;         // [27][15] rows by boundary type (tz*9+ty*3+tx; 0 lo, 1 interior, 2 hi)
+  const double* kT;         // [27][7]
+};
+
+// 2-D crossed mesh = df.RectangleMesh(..., 'crossed') (dolfin/bench1.py:21-23).
+// Corner row offsets: 0 self | 1 +x 2 -x 3 +y 4 -y | centres: 5 NE(ix,iy) 6 NW(ix-1,iy) 7 SE(ix,iy-1) 8 SW(ix-1,iy-1)
+// Centre row offsets: 0 self | corners 1 v0(ix,iy) 2 v1(ix+1,iy) 3 v2(ix,iy+1) 4 v3(ix+1,iy+1)
+#define PFH_NOFF2 9
+struct Mesh2 {
+  int nx, ny;          // cells
+  int nxv, nyv;        // corner counts
+  long long ncorner, ncentre, n_owned;
+  double hx, hy, detJ; // detJ = hx*hy/2 = 2|T|
+  double mC[5], kC[5]; // centre rows
+  double mI[PFH_NOFF2], kI[PFH_NOFF2];  // interior corner rows
+  const double* mT;    // [9][9] corner rows by type (ty*3+tx)
+  const double* kT;    // [9][9]
+};
+
+void pfh_build_tables3(Mesh3& m, std::vector<double>& mT, std::vector<double>& kT);
+void pfh_build_tables2(Mesh2& m, std::vector<double>& mT, std::vector<double>& kT);
+
+// Scalar field operand of a stencil kernel: owned planes + (3-D slabs) one ghost plane per side.
+struct FieldRef {
+  const double* p;
+  const double* glo;
+  const double* ghi;
+};
+
+// Linear part of the residual / Jacobian:
+//   R_a = sum_b (Mc[a][b] M + Kc[a][b] K) u_b - Mp[a] M u0_a + N[g_a](u)
+struct LinCoefs {
+  double Mc[PFH_MAX_FIELDS][PFH_MAX_FIELDS];
+  double Kc[PFH_MAX_FIELDS][PFH_MAX_FIELDS];
+  double Mp[PFH_MAX_FIELDS];
+};
+
+struct ProblemParams {
+  int id;
+  int nf;
+  double p[PFH_MAX_PARAMS];
+};
+
+// ------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------
+enum TimerId {
+  T_RESIDUAL = 0, T_JAC_APPLY, T_CHEB_SWEEP, T_CHEB_FIRST, T_LIN_APPLY, T_MULTIDOT, T_MULTIAXPY,
+  T_VEC, T_REDUCE, T_ENERGY, T_HALO, T_ALLREDUCE, T_IC, T_JACOBI, T_COPY, T_OTHER
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int id;
+};
+
+struct Comm;  // pfh_comm.cpp
+
+struct pfh_ctx {
+  pfh_config cfg;
+  int dim = 0;
+  int nf = 0;
+  ProblemParams prob;
+  Mesh2 m2;
+  Mesh3 m3;
+  long long n_owned = 0, n_global = 0;
+  long long nplane = 0;  // ghost plane size (3-D) or 0
+  double dt = 0.1;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  double* d_tables = nullptr;
+
+  // workspaces (device)
+  std::vector<double*> allocs;
+  double *U = nullptr, *U0 = nullptr, *R = nullptr, *DX = nullptr;  // nf*n_owned each
+  double* V = nullptr;                                               // (basis+1) * nf*n_owned
+  double *W1 = nullptr, *W2 = nullptr;                               // nf*n_owned Krylov temporaries
+  double* S[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // scalar temporaries (n_owned)
+  double* zero_field = nullptr;                                      // n_owned zeros
+  // ghost planes: [nf][nplane] each
+  double *gU_lo = nullptr, *gU_hi = nullptr;    // linearisation point / current iterate
+  double *gU0_lo = nullptr, *gU0_hi = nullptr;  // previous step
+  double *gX_lo = nullptr, *gX_hi = nullptr;    // operand of an operator apply
+  double *gS_lo = nullptr, *gS_hi = nullptr;    // scalar operand (preconditioner sweeps)
+  const double* jac_point = nullptr;            // device pointer to linearisation point (nf*n_owned)
+  bool jac_ghost_valid = false;
+
+  // reductions
+  double* d_partial = nullptr;  // [PFH_RED_MAXBLOCKS][PFH_RED_MAXVALS]
+  double* d_red = nullptr;      // final values (device)
+  double* h_red = nullptr;      // pinned host mirror
+  unsigned int* d_counter = nullptr;
+
+  // preconditioner state
+  pfh_solver_opts pc_opts;
+  bool pc_ready = false;
+  double pc_alpha = 0.0;
+  double lmax = 2.5, lmin_m = 0.5, lmin_a = 0.1;
+
+  Comm* comm = nullptr;
+
+  // instrumentation
+  long long launches = 0;
+  bool profiling = false;
+  std::vector<EventPair> ev_pending;
+  std::vector<EventPair> ev_free;
+  double t_ms[PFH_N_TIMERS] = {0};
+  long long t_n[PFH_N_TIMERS] = {0};
+  int variant_nl3 = 0;  // 0 = gather (v1), 1 = cube-centric shared-memory kernel
+};
+
+#define PFH_RED_MAXBLOCKS 1184  // 8 CTAs per SM * 148 SMs
+#define PFH_RED_MAXVALS 36
+
+double* pfh_alloc(pfh_ctx* c, size_t n_doubles);
+void pfh_prof_begin(pfh_ctx* c, int id);
+void pfh_prof_end(pfh_ctx* c, int id);
+void pfh_prof_resolve(pfh_ctx* c);
+
+struct ProfScope {
+  pfh_ctx* c;
+  int id;
+  ProfScope(pfh_ctx* c_, int id_) : c(c_), id(id_) {
+    c->launches++;
+    if (c->profiling) pfh_prof_begin(c, id);
+  }
+  ~ProfScope() {
+    if (c->profiling) pfh_prof_end(c, id);
+  }
+};
+
+// ---- stencil launchers (pfh_stencil.cu); operands are device pointers, ghosts must be current ----
+LinCoefs pfh_lin_coefs(const pfh_ctx* c, double dt);
+void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R);
+void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y);
+// out = s * add + (am M + ak K) in   (add may be null when s == 0)
+void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out);
+// z = b * Dinv r,  D = diag(am M + ak K)
+void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z);
+// zprev <- z + a (z - zprev) + b Dinv (r - (am M + ak K) z)
+void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z,
+                  double* zprev);
+// point-Jacobi on the Jacobian diagonal blocks: z_a = r_a / diag_a
+void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z);
+void k_energy(pfh_ctx* c, const double* u, double out[4]);  // includes final reduction + allreduce + D2H
+void k_initial_condition(pfh_ctx* c, const double* icp, int n, double* w);
+void k_dirichlet_fix(pfh_ctx* c, double* w);  // impose Dirichlet values on the iterate (bench6)
+
+// ---- vector kernels (pfh_vec.cu) ----
+void v_copy(pfh_ctx* c, double* dst, const double* src, long long n);
+void v_zero(pfh_ctx* c, double* dst, long long n);
+void v_axpy(pfh_ctx* c, double a, const double* x, double* y, long long n);               // y += a x
+void v_axpby(pfh_ctx* c, double a, const double* x, double b, const double* y, double* out, long long n);
+void v_scale(pfh_ctx* c, double a, const double* x, double* out, long long n);            // out = a x
+// dots[k] = V_k . w (k < nv), dots[nv] = w . w ; global (allreduced) values returned on the host
+void v_multidot(pfh_ctx* c, const double* V, long long stride, int nv, const double* w, long long n,
+                double* host_out);
+// out = scale * (w - sum_k h[k] V_k)
+void v_multiaxpy(pfh_ctx* c, const double* V, long long stride, int nv, const double* h,
+                 const double* w, double scale, double* out, long long n);
+// out = sum_k y[k] V_k
+void v_combine(pfh_ctx* c, const double* V, long long stride, int nv, const double* y, double* out,
+               long long n);
+double v_norm2(pfh_ctx* c, const double* x, long long n);  // global ||x||_2^2 on the host
+// finish a two-stage reduction: sums d_partial[nblocks][nvals] -> allreduce -> host; returns h_red
+const double* pfh_reduce_finish(pfh_ctx* c, int nblocks, int nvals);
+
+// ---- communication (pfh_comm.cpp) ----
+Comm* comm_create(const pfh_config& cfg, cudaStream_t s);
+void comm_destroy(Comm*);
+void comm_allreduce_sum(pfh_ctx* c, double* d_buf, int n);
+// exchange boundary planes of nfields fields stored field-major with stride fstride
+void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, double* glo, double* ghi);
+int comm_unique_id(void* out);
+
+// ---- solver (pfh_solver.cpp) ----
+void s_exchange_state(pfh_ctx* c, const double* u, double* glo, double* ghi);
+void s_residual(pfh_ctx* c, const double* u, const double* u0, double* R, bool u0_ghost_current);
+void s_jac_setup(pfh_ctx* c, const double* u);
+void s_jac_apply(pfh_ctx* c, const double* x, double* y);
+void s_precond_setup(pfh_ctx* c, const pfh_solver_opts* o);
+void s_precond_apply(pfh_ctx* c, const double* r, double* z);
+void s_newton(pfh_ctx* c, double* w, const double* w0, const pfh_solver_opts* o, pfh_solve_report* rep);

@@ -1,0 +1,53 @@
+"""Test-only CPU build of the product's per-vertex operator code (see emul.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = os.path.join(_HERE, "libpfh_emul.so")
+_SRC = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_tables.cpp")]
+_DEPS = _SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", f)
+                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h")]
+
+
+def build():
+    if os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in _DEPS):
+        return _LIB
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-I" + cuda_inc, "-o", _LIB] + _SRC)
+    return _LIB
+
+
+_P = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(_P) if a is not None else None
+
+
+def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=None, icp=None, nf=2,
+        z0=0, nzl=-1, glo=None, ghi=None):
+    """mode: 0 residual, 1 jac_apply, 2 energy -> [E, M], 3 scalar op -> [Av, diag], 4 initial condition."""
+    lib = ctypes.CDLL(build())
+    nc = (ctypes.c_int * 3)(*(list(ncell) + [1] * (3 - len(ncell))))
+    ln = (ctypes.c_double * 3)(*(list(length) + [1.0] * (3 - len(length))))
+    pr = np.ascontiguousarray(params, dtype=np.float64)
+    if mesh_kind == 3:
+        nzv = ncell[2] + 1
+        n = (ncell[0] + 1) * (ncell[1] + 1) * (nzv if nzl < 0 else nzl)
+    else:
+        n = (ncell[0] + 1) * (ncell[1] + 1) + ncell[0] * ncell[1]
+    arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (U, X, U0, glo, ghi)]
+    out = np.zeros({0: nf * n, 1: nf * n, 2: 2, 3: 2 * n, 4: nf * n}[mode])
+    icp = np.ascontiguousarray(icp if icp is not None else [0.0], dtype=np.float64)
+    rc = lib.emul_run(mesh_kind, problem, nc, ln, _p(pr), len(pr), ctypes.c_double(dt), mode, z0, nzl,
+                      _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(out), _p(icp))
+    assert rc == 0, rc
+    if mode in (0, 1, 4):
+        return out.reshape(nf, n)
+    if mode == 3:
+        return out.reshape(2, n)
+    return out

@@ -1,0 +1,140 @@
+// TEST INFRASTRUCTURE: compiles the product's __host__ __device__ per-vertex operator code
+// (pfh_vertex.cuh / pfh_elem.cuh / pfh_problems.cuh / pfh_tables.cpp) for the CPU so the
+// index arithmetic, stencil tables, quadrature and hand-written f', f'' can be checked against
+// the oracle without a GPU.  Never loaded by the product.
+#include <cmath>
+#include <vector>
+
+#include "../../pfhubbenchmarks_b200/csrc/pfh_vertex.cuh"
+
+void pfh_set_error(const std::string&) {}
+
+namespace {
+struct Setup {
+  Mesh2 m2;
+  Mesh3 m3;
+  std::vector<double> mT, kT;
+  int dim;
+};
+
+void setup(Setup& S, int mesh_kind, const int* nc, const double* len, int z0, int nzl) {
+  if (mesh_kind == PFH_MESH_KUHN3D) {
+    S.dim = 3;
+    Mesh3& m = S.m3;
+    m.nxv = nc[0] + 1; m.nyv = nc[1] + 1; m.nzv = nc[2] + 1;
+    m.z0 = z0; m.nzl = nzl < 0 ? m.nzv : nzl;
+    m.nxy = (long long)m.nxv * m.nyv; m.n_owned = m.nxy * m.nzl;
+    m.hx = len[0] / nc[0]; m.hy = len[1] / nc[1]; m.hz = len[2] / nc[2];
+    m.detJ = m.hx * m.hy * m.hz;
+    pfh_build_tables3(m, S.mT, S.kT);
+    m.mT = S.mT.data(); m.kT = S.kT.data();
+  } else {
+    S.dim = 2;
+    Mesh2& m = S.m2;
+    m.nx = nc[0]; m.ny = nc[1]; m.nxv = nc[0] + 1; m.nyv = nc[1] + 1;
+    m.ncorner = (long long)m.nxv * m.nyv; m.ncentre = (long long)m.nx * m.ny; m.n_owned = m.ncorner + m.ncentre;
+    m.hx = len[0] / nc[0]; m.hy = len[1] / nc[1]; m.detJ = 0.5 * m.hx * m.hy;
+    pfh_build_tables2(m, S.mT, S.kT);
+    m.mT = S.mT.data(); m.kT = S.kT.data();
+  }
+}
+
+template <class P>
+int run(const Setup& S, const ProblemParams& pp, double dt, int mode, const double* U, const double* X, const double* U0,
+        const double* glo, const double* ghi, double* out, const double* icp) {
+  P prob(pp);
+  LinCoefs L;
+  memset(&L, 0, sizeof L);
+  prob.lin(dt, L);
+  if (S.dim == 3) {
+    const Mesh3& m = S.m3;
+    const long long n = m.n_owned;
+    FieldRef u[P::NF], x[P::NF], u0[P::NF];
+    // ghost layout (slab tests): glo/ghi hold [3 vectors (U, X, U0)][NF][nxy]
+    for (int f = 0; f < P::NF; ++f) {
+      u[f] = {U + f * n, glo ? glo + (0 * P::NF + f) * m.nxy : nullptr, ghi ? ghi + (0 * P::NF + f) * m.nxy : nullptr};
+      x[f] = {X ? X + f * n : nullptr, glo ? glo + (1 * P::NF + f) * m.nxy : nullptr, ghi ? ghi + (1 * P::NF + f) * m.nxy : nullptr};
+      u0[f] = {U0 ? U0 + f * n : nullptr, glo ? glo + (2 * P::NF + f) * m.nxy : nullptr, ghi ? ghi + (2 * P::NF + f) * m.nxy : nullptr};
+    }
+    double E = 0, Mm = 0;
+#pragma omp parallel for reduction(+ : E, Mm) collapse(2)
+    for (int zl = 0; zl < m.nzl; ++zl)
+      for (int iy = 0; iy < m.nyv; ++iy)
+        for (int ix = 0; ix < m.nxv; ++ix) {
+          const long long i = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
+          if (mode == 0 || mode == 1) {
+            double o[P::NF];
+            if (mode == 0) vtx::vertex_op3<P, false>(prob, m, L, u, x, u0, ix, iy, zl, o);
+            else vtx::vertex_op3<P, true>(prob, m, L, u, x, u0, ix, iy, zl, o);
+            for (int a = 0; a < P::NF; ++a) out[a * n + i] = o[a];
+          } else if (mode == 2) {
+            double e, mm;
+            vtx::vertex_energy3<P>(prob, m, u, ix, iy, zl, e, mm);
+            E += e; Mm += mm;
+          } else if (mode == 3) {  // scalar op: out = (am M + ak K) U[0], am = icp[0], ak = icp[1]
+            double Av, d, s;
+            vtx::scalar_op3(m, icp[0], icp[1], u[0], ix, iy, zl, Av, d, s);
+            out[i] = Av; out[n + i] = d;
+          } else if (mode == 4) {
+            double o[P::NF];
+            prob.ic(icp, ix * m.hx, iy * m.hy, o);
+            for (int a = 0; a < P::NF; ++a) out[a * n + i] = o[a];
+          }
+        }
+    if (mode == 2) { out[0] = E; out[1] = Mm; }
+  } else {
+    const Mesh2& m = S.m2;
+    const long long n = m.n_owned;
+    double E = 0, Mm = 0;
+#pragma omp parallel for reduction(+ : E, Mm)
+    for (long long i = 0; i < n; ++i) {
+      if (mode == 0 || mode == 1) {
+        double o[P::NF];
+        if (mode == 0) vtx::vertex_op2<P, false>(prob, m, L, U, X, U0, i, o);
+        else vtx::vertex_op2<P, true>(prob, m, L, U, X, U0, i, o);
+        for (int a = 0; a < P::NF; ++a) out[a * n + i] = o[a];
+      } else if (mode == 2) {
+        double e, mm;
+        vtx::vertex_energy2<P>(prob, m, U, i, e, mm);
+        E += e; Mm += mm;
+      } else if (mode == 3) {
+        double Av, d, s;
+        vtx::scalar_op2(m, icp[0], icp[1], U, i, Av, d, s);
+        out[i] = Av; out[n + i] = d;
+      } else if (mode == 4) {
+        double x, y;
+        if (i < m.ncorner) { x = (i % m.nxv) * m.hx; y = (i / m.nxv) * m.hy; }
+        else { const long long ci = i - m.ncorner; x = (ci % m.nx + 0.5) * m.hx; y = (ci / m.nx + 0.5) * m.hy; }
+        double o[P::NF];
+        prob.ic(icp, x, y, o);
+        for (int a = 0; a < P::NF; ++a) out[a * n + i] = o[a];
+      }
+    }
+    if (mode == 2) { out[0] = E; out[1] = Mm; }
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int emul_run(int mesh_kind, int problem, const int* ncell, const double* length, const double* params, int nparams,
+                        double dt, int mode, int z0, int nzl, const double* U, const double* X, const double* U0,
+                        const double* glo, const double* ghi, double* out, const double* icp) {
+  try {
+    Setup S;
+    setup(S, mesh_kind, ncell, length, z0, nzl);
+    ProblemParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.id = problem;
+    for (int i = 0; i < nparams; ++i) pp.p[i] = params[i];
+    switch (problem) {
+      case PFH_PROBLEM_CH: return run<ProbCH>(S, pp, dt, mode, U, X, U0, glo, ghi, out, icp);
+      case PFH_PROBLEM_BENCH2: return run<ProbBench2>(S, pp, dt, mode, U, X, U0, glo, ghi, out, icp);
+      case PFH_PROBLEM_BENCH3: return run<ProbBench3>(S, pp, dt, mode, U, X, U0, glo, ghi, out, icp);
+      case PFH_PROBLEM_BENCH6: return run<ProbBench6>(S, pp, dt, mode, U, X, U0, glo, ghi, out, icp);
+    }
+    return -2;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "emul: %s\n", e.what());
+    return -1;
+  }
+}
