@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -128,7 +129,8 @@ struct pfh_ctx {
 
   // workspaces (device)
   std::vector<double*> allocs;
-  double *U = nullptr, *U0 = nullptr, *R = nullptr, *DX = nullptr;  // nf*n_owned each
+  double *U = nullptr, *U0 = nullptr;  // device staging of caller host buffers (host entry points)
+  double *R = nullptr, *B = nullptr, *DX = nullptr, *DX2 = nullptr;  // nf*n_owned each
   double* V = nullptr;                                               // (basis+1) * nf*n_owned
   double *W1 = nullptr, *W2 = nullptr;                               // nf*n_owned Krylov temporaries
   double* S[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // scalar temporaries (n_owned)
@@ -177,7 +179,7 @@ struct ProfScope {
   pfh_ctx* c;
   int id;
   ProfScope(pfh_ctx* c_, int id_) : c(c_), id(id_) {
-    c->launches++;
+    if (id != T_COPY && id != T_HALO && id != T_ALLREDUCE) c->launches++;  // our own kernels only
     if (c->profiling) pfh_prof_begin(c, id);
   }
   ~ProfScope() {

@@ -1,0 +1,364 @@
+// Matrix-free stencil kernels (sm_100a, fp64): residual, Jacobian-vector product, the scalar
+// SPD operators of the preconditioner (Jacobi-Chebyshev sweeps on am M + ak K), the energy /
+// solute reductions and the initial conditions.  These replace FFC's generated tabulate_tensor
+// kernels + DOLFIN's assembler + PETSc MatMult on the reference's hot path
+// (dolfin/bench1.py:162 -> SNESSolve; SURVEY.md section 3.3, hot loops A-D).
+//
+// Thread mapping: 3-D kernels use (BX x BY) tiles of an x-y plane and march along z so the three
+// planes a vertex reads stay in L1; 2-D kernels are flat over the DOLFIN vertex order.
+#include "pfh_vertex.cuh"
+
+namespace {
+
+constexpr int BX = 64, BY = 4, ZCHUNK = 16;
+constexpr int TPB = 256;
+
+template <int NF>
+struct Fields {
+  FieldRef f[NF];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum of NV values; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV]) {
+  __shared__ double sh[NV][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    v[k] = warp_sum(v[k]);
+    if (lane == 0) sh[k][wid] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = lane < nw ? sh[k][lane] : 0.0;
+      v[k] = warp_sum(t);
+    }
+  }
+}
+
+// ------------------------------- 3-D kernels -------------------------------
+template <class P, bool JAC>
+__global__ void __launch_bounds__(BX* BY) k3_op(P prob, Mesh3 m, LinCoefs L, Fields<P::NF> U, Fields<P::NF> X,
+                                                 Fields<P::NF> U0, double* __restrict__ out) {
+  const int ix = blockIdx.x * BX + threadIdx.x, iy = blockIdx.y * BY + threadIdx.y;
+  if (ix >= m.nxv || iy >= m.nyv) return;
+  const int z_end = min(m.nzl, (int)(blockIdx.z + 1) * ZCHUNK);
+  for (int zl = blockIdx.z * ZCHUNK; zl < z_end; ++zl) {
+    double o[P::NF];
+    vtx::vertex_op3<P, JAC>(prob, m, L, U.f, X.f, U0.f, ix, iy, zl, o);
+    const long long i = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
+#pragma unroll
+    for (int a = 0; a < P::NF; ++a) out[a * m.n_owned + i] = o[a];
+  }
+}
+
+// MODE 0: out = s*add + A in ; MODE 1: z = b Dinv r ; MODE 2: zprev <- z + a (z - zprev) + b Dinv (r - A z)
+template <int MODE>
+__global__ void __launch_bounds__(BX* BY) k3_scalar(Mesh3 m, double am, double ak, double a, double b, FieldRef in,
+                                                    const double* __restrict__ r, double* __restrict__ out) {
+  const int ix = blockIdx.x * BX + threadIdx.x, iy = blockIdx.y * BY + threadIdx.y;
+  if (ix >= m.nxv || iy >= m.nyv) return;
+  const int z_end = min(m.nzl, (int)(blockIdx.z + 1) * ZCHUNK);
+  for (int zl = blockIdx.z * ZCHUNK; zl < z_end; ++zl) {
+    const long long i = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
+    if (MODE == 1) {
+      out[i] = b / vtx::scalar_diag3(m, am, ak, ix, iy, zl) * r[i];
+    } else {
+      double Av, d, self;
+      vtx::scalar_op3(m, am, ak, in, ix, iy, zl, Av, d, self);
+      if (MODE == 0) out[i] = (a != 0.0 ? a * r[i] : 0.0) + Av;
+      else out[i] = self + a * (self - out[i]) + (b / d) * (r[i] - Av);
+    }
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(TPB) k3_energy(P prob, Mesh3 m, Fields<P::NF> U, double* __restrict__ partial) {
+  double acc[2] = {0.0, 0.0};
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < m.n_owned; i += (long long)gridDim.x * TPB) {
+    const int zl = (int)(i / m.nxy);
+    const int rem = (int)(i - (long long)zl * m.nxy);
+    double e, mm;
+    vtx::vertex_energy3<P>(prob, m, U.f, rem % m.nxv, rem / m.nxv, zl, e, mm);
+    acc[0] += e;
+    acc[1] += mm;
+  }
+  block_sum<2>(acc);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x * PFH_RED_MAXVALS + 0] = acc[0];
+    partial[blockIdx.x * PFH_RED_MAXVALS + 1] = acc[1];
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(TPB) k3_ic(P prob, Mesh3 m, Fields<1> /*unused*/, const double* __restrict__ q, double* __restrict__ w) {
+  double qq[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) qq[k] = q[k];
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < m.n_owned; i += (long long)gridDim.x * TPB) {
+    const int rem = (int)(i % m.nxy);
+    double u[P::NF];
+    prob.ic(qq, (rem % m.nxv) * m.hx, (rem / m.nxv) * m.hy, u);
+#pragma unroll
+    for (int a = 0; a < P::NF; ++a) w[a * m.n_owned + i] = u[a];
+  }
+}
+
+// ------------------------------- 2-D kernels -------------------------------
+template <class P, bool JAC>
+__global__ void __launch_bounds__(TPB) k2_op(P prob, Mesh2 m, LinCoefs L, const double* __restrict__ U,
+                                             const double* __restrict__ X, const double* __restrict__ U0,
+                                             double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= m.n_owned) return;
+  double o[P::NF];
+  vtx::vertex_op2<P, JAC>(prob, m, L, U, X, U0, i, o);
+#pragma unroll
+  for (int a = 0; a < P::NF; ++a) out[a * m.n_owned + i] = o[a];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k2_scalar(Mesh2 m, double am, double ak, double a, double b,
+                                                 const double* __restrict__ in, const double* __restrict__ r,
+                                                 double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= m.n_owned) return;
+  if (MODE == 1) {
+    out[i] = b / vtx::scalar_diag2(m, am, ak, i) * r[i];
+  } else {
+    double Av, d, self;
+    vtx::scalar_op2(m, am, ak, in, i, Av, d, self);
+    if (MODE == 0) out[i] = (a != 0.0 ? a * r[i] : 0.0) + Av;
+    else out[i] = self + a * (self - out[i]) + (b / d) * (r[i] - Av);
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(TPB) k2_energy(P prob, Mesh2 m, const double* __restrict__ U, double* __restrict__ partial) {
+  double acc[2] = {0.0, 0.0};
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < m.n_owned; i += (long long)gridDim.x * TPB) {
+    double e, mm;
+    vtx::vertex_energy2<P>(prob, m, U, i, e, mm);
+    acc[0] += e;
+    acc[1] += mm;
+  }
+  block_sum<2>(acc);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x * PFH_RED_MAXVALS + 0] = acc[0];
+    partial[blockIdx.x * PFH_RED_MAXVALS + 1] = acc[1];
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(TPB) k2_ic(P prob, Mesh2 m, const double* __restrict__ q, double* __restrict__ w) {
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= m.n_owned) return;
+  double qq[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) qq[k] = q[k];
+  double x, y;
+  if (i < m.ncorner) {
+    x = (i % m.nxv) * m.hx;
+    y = (i / m.nxv) * m.hy;
+  } else {
+    const long long ci = i - m.ncorner;
+    x = (ci % m.nx + 0.5) * m.hx;
+    y = (ci / m.nx + 0.5) * m.hy;
+  }
+  double u[P::NF];
+  prob.ic(qq, x, y, u);
+#pragma unroll
+  for (int a = 0; a < P::NF; ++a) w[a * m.n_owned + i] = u[a];
+}
+
+// z_a = r_a / (Mc_aa M_ii + Kc_aa K_ii): point Jacobi on the linear part of the diagonal blocks
+template <int DIM>
+__global__ void __launch_bounds__(TPB) k_jacobi_kernel(Mesh2 m2, Mesh3 m3, LinCoefs L, int nf, const double* __restrict__ r,
+                                                       double* __restrict__ z) {
+  const long long n = DIM == 2 ? m2.n_owned : m3.n_owned;
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= n) return;
+  for (int a = 0; a < nf; ++a) {
+    double d;
+    if (DIM == 2) {
+      d = vtx::scalar_diag2(m2, L.Mc[a][a], L.Kc[a][a], i);
+    } else {
+      const int zl = (int)(i / m3.nxy);
+      const int rem = (int)(i - (long long)zl * m3.nxy);
+      d = vtx::scalar_diag3(m3, L.Mc[a][a], L.Kc[a][a], rem % m3.nxv, rem / m3.nxv, zl);
+    }
+    z[a * n + i] = r[a * n + i] / (d != 0.0 ? d : 1.0);
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(TPB) k2_dirichlet(P prob, Mesh2 m, double* __restrict__ w) {
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= m.ncorner) return;
+  const int ix = (int)(i % m.nxv), iy = (int)(i / m.nxv);
+#pragma unroll
+  for (int a = 0; a < P::NF; ++a) {
+    double val;
+    if (prob.dirichlet(a, ix, iy, m.nx, iy * m.hy, val)) w[a * m.n_owned + i] = val;
+  }
+}
+
+// -------- launch helpers --------
+dim3 grid3(const Mesh3& m) { return dim3((m.nxv + BX - 1) / BX, (m.nyv + BY - 1) / BY, (m.nzl + ZCHUNK - 1) / ZCHUNK); }
+int grid1(long long n) { return (int)((n + TPB - 1) / TPB); }
+int grid_red(long long n) {
+  long long g = (n + TPB - 1) / TPB;
+  return (int)(g < PFH_RED_MAXBLOCKS ? g : PFH_RED_MAXBLOCKS);
+}
+
+template <class P>
+Fields<P::NF> state_fields(const pfh_ctx* c, const double* u, const double* glo, const double* ghi) {
+  Fields<P::NF> F;
+  for (int f = 0; f < P::NF; ++f) {
+    F.f[f].p = u ? u + f * c->n_owned : nullptr;
+    F.f[f].glo = (glo && c->nplane) ? glo + f * c->nplane : nullptr;
+    F.f[f].ghi = (ghi && c->nplane) ? ghi + f * c->nplane : nullptr;
+  }
+  return F;
+}
+
+#define PFH_DISPATCH2(c, BODY)                                            \
+  switch ((c)->prob.id) {                                                 \
+    case PFH_PROBLEM_CH: { using P = ProbCH; BODY; } break;               \
+    case PFH_PROBLEM_BENCH2: { using P = ProbBench2; BODY; } break;       \
+    case PFH_PROBLEM_BENCH3: { using P = ProbBench3; BODY; } break;       \
+    case PFH_PROBLEM_BENCH6: { using P = ProbBench6; BODY; } break;       \
+    default: throw PfhError("unknown problem id");                        \
+  }
+#define PFH_DISPATCH3(c, BODY)                                                     \
+  switch ((c)->prob.id) {                                                          \
+    case PFH_PROBLEM_CH: { using P = ProbCH; BODY; } break;                        \
+    default: throw PfhError("3-D meshes support PFH_PROBLEM_CH only (b13d)");      \
+  }
+
+template <class P>
+LinCoefs lin_of(const pfh_ctx* c, double dt) {
+  LinCoefs L;
+  memset(&L, 0, sizeof L);
+  P(c->prob).lin(dt, L);
+  return L;
+}
+
+}  // namespace
+
+LinCoefs pfh_lin_coefs(const pfh_ctx* c, double dt) {
+  LinCoefs L;
+  PFH_DISPATCH2(c, L = lin_of<P>(c, dt));
+  return L;
+}
+
+void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
+  ProfScope ps(c, T_RESIDUAL);
+  const LinCoefs L = pfh_lin_coefs(c, c->dt);
+  if (c->dim == 3) {
+    PFH_DISPATCH3(c, (k3_op<P, false><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(
+                         P(c->prob), c->m3, L, state_fields<P>(c, u, c->gU_lo, c->gU_hi), state_fields<P>(c, nullptr, nullptr, nullptr),
+                         state_fields<P>(c, u0, c->gU0_lo, c->gU0_hi), R)));
+  } else {
+    PFH_DISPATCH2(c, (k2_op<P, false><<<grid1(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, u, nullptr, u0, R)));
+  }
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
+  ProfScope ps(c, T_JAC_APPLY);
+  const LinCoefs L = pfh_lin_coefs(c, c->dt);
+  if (c->dim == 3) {
+    PFH_DISPATCH3(c, (k3_op<P, true><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(
+                         P(c->prob), c->m3, L, state_fields<P>(c, ulin, c->gU_lo, c->gU_hi), state_fields<P>(c, x, c->gX_lo, c->gX_hi),
+                         state_fields<P>(c, nullptr, nullptr, nullptr), y)));
+  } else {
+    PFH_DISPATCH2(c, (k2_op<P, true><<<grid1(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, ulin, x, nullptr, y)));
+  }
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out) {
+  ProfScope ps(c, T_LIN_APPLY);
+  PFH_CHECK(s == 0.0 || add != nullptr, "k_lin_apply: add operand missing");
+  if (c->dim == 3)
+    k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out);
+  else
+    k2_scalar<0><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, s, 0.0, in.p, add, out);
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z) {
+  ProfScope ps(c, T_CHEB_FIRST);
+  if (c->dim == 3)
+    k3_scalar<1><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z);
+  else
+    k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z);
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev) {
+  ProfScope ps(c, T_CHEB_SWEEP);
+  if (c->dim == 3)
+    k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev);
+  else
+    k2_scalar<2><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, a, b, z.p, r, zprev);
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k_jacobi(pfh_ctx* c, const double* /*ulin*/, const double* r, double* z) {
+  ProfScope ps(c, T_JACOBI);
+  const LinCoefs L = pfh_lin_coefs(c, c->dt);
+  if (c->dim == 3)
+    k_jacobi_kernel<3><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, c->m3, L, c->nf, r, z);
+  else
+    k_jacobi_kernel<2><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, c->m3, L, c->nf, r, z);
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k_energy(pfh_ctx* c, const double* u, double out[4]) {
+  const int nb = grid_red(c->n_owned);
+  {
+    ProfScope ps(c, T_ENERGY);
+    if (c->dim == 3) {
+      PFH_DISPATCH3(c, (k3_energy<P><<<nb, TPB, 0, c->stream>>>(P(c->prob), c->m3, state_fields<P>(c, u, c->gU_lo, c->gU_hi), c->d_partial)));
+    } else {
+      PFH_DISPATCH2(c, (k2_energy<P><<<nb, TPB, 0, c->stream>>>(P(c->prob), c->m2, u, c->d_partial)));
+    }
+    PFH_CUDA(cudaGetLastError());
+  }
+  const double* h = pfh_reduce_finish(c, nb, 2);
+  out[0] = h[0];
+  out[1] = h[1];
+  out[2] = out[3] = 0.0;
+}
+
+void k_initial_condition(pfh_ctx* c, const double* icp, int n, double* w) {
+  PFH_CHECK(n <= 8, "too many initial-condition parameters");
+  double q[8] = {0};
+  for (int i = 0; i < n; ++i) q[i] = icp[i];
+  // small parameter block travels through the reduction scratch buffer
+  PFH_CUDA(cudaMemcpyAsync(c->d_red, q, sizeof q, cudaMemcpyHostToDevice, c->stream));
+  ProfScope ps(c, T_IC);
+  if (c->dim == 3) {
+    PFH_DISPATCH3(c, (k3_ic<P><<<grid_red(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m3, Fields<1>(), c->d_red, w)));
+  } else {
+    PFH_DISPATCH2(c, (k2_ic<P><<<grid1(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m2, c->d_red, w)));
+  }
+  PFH_CUDA(cudaGetLastError());
+  PFH_CUDA(cudaStreamSynchronize(c->stream));  // q is a stack buffer
+}
+
+void k_dirichlet_fix(pfh_ctx* c, double* w) {
+  if (c->dim != 2 || c->prob.id != PFH_PROBLEM_BENCH6) return;
+  ProfScope ps(c, T_OTHER);
+  k2_dirichlet<ProbBench6><<<grid1(c->m2.ncorner), TPB, 0, c->stream>>>(ProbBench6(c->prob), c->m2, w);
+  PFH_CUDA(cudaGetLastError());
+}

@@ -1,0 +1,241 @@
+// Krylov vector kernels (fp64, HBM-streaming): fused multi-dot and multi-axpy for classical
+// Gram-Schmidt GMRES, norms, axpy-type updates and the deterministic two-stage reductions.
+// These replace PETSc's VecMDot / VecMAXPY / VecNorm / VecAXPY (+ MPI_Allreduce) on the
+// reference's hot path (hot loop E).
+#include "pfh_internal.h"
+
+namespace {
+constexpr int TPB = 256;
+constexpr int MD = 8;  // basis vectors handled per multi-dot / multi-axpy pass
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+int grid_stream(long long n) {  // enough CTAs to fill 148 SMs x 8, grid-stride beyond that
+  long long g = (n + TPB * 2 - 1) / (TPB * 2);
+  if (g < 1) g = 1;
+  return (int)(g < PFH_RED_MAXBLOCKS ? g : PFH_RED_MAXBLOCKS);
+}
+
+struct Coef {
+  double v[MD];
+};
+
+// partial[block][k0 + k] = sum_i V_{k0+k}[i] w[i] (k < nb); if WW also partial[block][ww_slot] = sum w^2
+template <bool WW>
+__global__ void __launch_bounds__(TPB) k_multidot(const double* __restrict__ V, long long stride, int nb, int k0, int ww_slot,
+                                                  const double* __restrict__ w, long long n, double* __restrict__ partial) {
+  double acc[MD + 1];
+#pragma unroll
+  for (int k = 0; k <= MD; ++k) acc[k] = 0.0;
+  const long long n2 = n >> 1;
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n2; i += (long long)gridDim.x * TPB) {
+    const double2 wi = w2[i];
+#pragma unroll
+    for (int k = 0; k < MD; ++k)
+      if (k < nb) {
+        const double2 vi = reinterpret_cast<const double2*>(V + (long long)k * stride)[i];
+        acc[k] += vi.x * wi.x + vi.y * wi.y;
+      }
+    if (WW) acc[MD] += wi.x * wi.x + wi.y * wi.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double wi = w[n - 1];
+#pragma unroll
+    for (int k = 0; k < MD; ++k)
+      if (k < nb) acc[k] += V[(long long)k * stride + n - 1] * wi;
+    if (WW) acc[MD] += wi * wi;
+  }
+  __shared__ double sh[MD + 1][TPB / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k <= MD; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (lane == 0) sh[k][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x <= MD) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < TPB / 32; ++q) s += sh[threadIdx.x][q];
+    if (threadIdx.x < nb) partial[blockIdx.x * PFH_RED_MAXVALS + k0 + threadIdx.x] = s;
+    if (WW && threadIdx.x == MD) partial[blockIdx.x * PFH_RED_MAXVALS + ww_slot] = s;
+  }
+}
+
+// out = wscale * w - sum_k h[k] V_k   (HAS_W false: out = - sum_k h[k] V_k)
+template <bool HAS_W>
+__global__ void __launch_bounds__(TPB) k_multiaxpy(const double* __restrict__ V, long long stride, int nb, Coef h,
+                                                   const double* w, double wscale, double* out, long long n) {
+  const long long n2 = n >> 1;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n2; i += (long long)gridDim.x * TPB) {
+    double2 r = make_double2(0.0, 0.0);
+    if (HAS_W) {
+      r = reinterpret_cast<const double2*>(w)[i];
+      r.x *= wscale;
+      r.y *= wscale;
+    }
+#pragma unroll
+    for (int k = 0; k < MD; ++k)
+      if (k < nb) {
+        const double2 vi = reinterpret_cast<const double2*>(V + (long long)k * stride)[i];
+        r.x -= h.v[k] * vi.x;
+        r.y -= h.v[k] * vi.y;
+      }
+    reinterpret_cast<double2*>(out)[i] = r;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double r = HAS_W ? w[n - 1] * wscale : 0.0;
+#pragma unroll
+    for (int k = 0; k < MD; ++k)
+      if (k < nb) r -= h.v[k] * V[(long long)k * stride + n - 1];
+    out[n - 1] = r;
+  }
+}
+
+// out = a x + b y  (y may be null when b == 0)
+__global__ void __launch_bounds__(TPB) k_axpby(double a, const double* __restrict__ x, double b, const double* y,
+                                               double* out, long long n) {
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB)
+    out[i] = a * x[i] + (b != 0.0 ? b * y[i] : 0.0);
+}
+
+__global__ void __launch_bounds__(TPB) k_norm2(const double* __restrict__ x, long long n, double* __restrict__ partial) {
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) acc += x[i] * x[i];
+  __shared__ double sh[TPB / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  acc = warp_sum(acc);
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < TPB / 32; ++q) s += sh[q];
+    partial[blockIdx.x * PFH_RED_MAXVALS] = s;
+  }
+}
+
+// second stage: red[v] = sum_b partial[b][v], fixed order => deterministic
+__global__ void __launch_bounds__(TPB) k_reduce_final(const double* __restrict__ partial, int nblocks, int nvals,
+                                                      double* __restrict__ red) {
+  __shared__ double sh[TPB / 32];
+  for (int v = 0; v < nvals; ++v) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += TPB) acc += partial[b * PFH_RED_MAXVALS + v];
+    acc = warp_sum(acc);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < TPB / 32; ++q) s += sh[q];
+      red[v] = s;
+    }
+    __syncthreads();
+  }
+}
+}  // namespace
+
+const double* pfh_reduce_finish(pfh_ctx* c, int nblocks, int nvals) {
+  PFH_CHECK(nvals <= PFH_RED_MAXVALS && nblocks <= PFH_RED_MAXBLOCKS, "reduction scratch too small");
+  {
+    ProfScope ps(c, T_REDUCE);
+    k_reduce_final<<<1, TPB, 0, c->stream>>>(c->d_partial, nblocks, nvals, c->d_red);
+    PFH_CUDA(cudaGetLastError());
+  }
+  if (c->cfg.nranks > 1) comm_allreduce_sum(c, c->d_red, nvals);
+  PFH_CUDA(cudaMemcpyAsync(c->h_red, c->d_red, nvals * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PFH_CUDA(cudaStreamSynchronize(c->stream));
+  return c->h_red;
+}
+
+void v_copy(pfh_ctx* c, double* dst, const double* src, long long n) {
+  ProfScope ps(c, T_COPY);
+  PFH_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+}
+void v_zero(pfh_ctx* c, double* dst, long long n) {
+  ProfScope ps(c, T_COPY);
+  PFH_CUDA(cudaMemsetAsync(dst, 0, n * sizeof(double), c->stream));
+}
+void v_axpby(pfh_ctx* c, double a, const double* x, double b, const double* y, double* out, long long n) {
+  ProfScope ps(c, T_VEC);
+  k_axpby<<<grid_stream(n), TPB, 0, c->stream>>>(a, x, b, y, out, n);
+  PFH_CUDA(cudaGetLastError());
+}
+void v_axpy(pfh_ctx* c, double a, const double* x, double* y, long long n) { v_axpby(c, a, x, 1.0, y, y, n); }
+void v_scale(pfh_ctx* c, double a, const double* x, double* out, long long n) { v_axpby(c, a, x, 0.0, nullptr, out, n); }
+
+void v_multidot(pfh_ctx* c, const double* V, long long stride, int nv, const double* w, long long n, double* host_out) {
+  PFH_CHECK(nv + 1 <= PFH_RED_MAXVALS, "too many basis vectors for the reduction scratch");
+  PFH_CHECK((stride & 1) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+            "multidot operands must be 16-byte aligned");
+  const int nb = grid_stream(n);
+  int k0 = 0;
+  do {
+    const int cnt = nv - k0 < MD ? nv - k0 : MD;
+    const bool last = k0 + cnt >= nv;
+    ProfScope ps(c, T_MULTIDOT);
+    if (last)
+      k_multidot<true><<<nb, TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, k0, nv, w, n, c->d_partial);
+    else
+      k_multidot<false><<<nb, TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, k0, nv, w, n, c->d_partial);
+    PFH_CUDA(cudaGetLastError());
+    k0 += cnt;
+  } while (k0 < nv);
+  const double* h = pfh_reduce_finish(c, nb, nv + 1);
+  for (int k = 0; k <= nv; ++k) host_out[k] = h[k];
+}
+
+// out = wscale * w - sum_k coef_k V_k, MD basis vectors per pass (w == nullptr: no w term)
+static void multiaxpy_raw(pfh_ctx* c, const double* V, long long stride, int nv, const double* coef, const double* w,
+                          double wscale, double* out, long long n) {
+  PFH_CHECK((stride & 1) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+            "multiaxpy operands must be 16-byte aligned");
+  int k0 = 0;
+  bool first = true;
+  do {
+    const int cnt = nv - k0 < MD ? nv - k0 : MD;
+    Coef cf;
+    for (int k = 0; k < MD; ++k) cf.v[k] = k < cnt ? coef[k0 + k] : 0.0;
+    ProfScope ps(c, T_MULTIAXPY);
+    const double* win = first ? w : out;
+    if (win)
+      k_multiaxpy<true><<<grid_stream(n), TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, cf, win,
+                                                              first ? wscale : 1.0, out, n);
+    else
+      k_multiaxpy<false><<<grid_stream(n), TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, cf, nullptr, 0.0, out, n);
+    PFH_CUDA(cudaGetLastError());
+    first = false;
+    k0 += cnt;
+  } while (k0 < nv);
+}
+
+void v_multiaxpy(pfh_ctx* c, const double* V, long long stride, int nv, const double* h, const double* w, double scale,
+                 double* out, long long n) {
+  std::vector<double> cf(nv);
+  for (int k = 0; k < nv; ++k) cf[k] = scale * h[k];
+  multiaxpy_raw(c, V, stride, nv, cf.data(), w, scale, out, n);
+}
+
+void v_combine(pfh_ctx* c, const double* V, long long stride, int nv, const double* y, double* out, long long n) {
+  std::vector<double> cf(nv);
+  for (int k = 0; k < nv; ++k) cf[k] = -y[k];
+  multiaxpy_raw(c, V, stride, nv, cf.data(), nullptr, 0.0, out, n);
+}
+
+double v_norm2(pfh_ctx* c, const double* x, long long n) {
+  const int nb = grid_stream(n);
+  {
+    ProfScope ps(c, T_VEC);
+    k_norm2<<<nb, TPB, 0, c->stream>>>(x, n, c->d_partial);
+    PFH_CUDA(cudaGetLastError());
+  }
+  return pfh_reduce_finish(c, nb, 1)[0];
+}

@@ -1,0 +1,85 @@
+"""The product's per-vertex operator code (csrc/pfh_vertex.cuh etc.), compiled for the CPU by
+tests/emul, against the oracle's assembled operators.  CPU only; exercises stencil tables,
+quadrature, hand-written f'/f'', Dirichlet rows and slab ghost planes."""
+import numpy as np
+import pytest
+
+import emul
+from helpers import discretization, rel_max
+from oracle import mesh as omesh, problems, stepper
+
+CASES = [
+    ("bench1", 2, 1, (7, 5), (14.0, 10.0), [0.3, 0.7, 5.0, 2.0, 5.0], [0.5, 0.05]),
+    ("bench1", 2, 1, (6, 4), (9.0, 10.0), [0.3, 0.7, 5.0, 2.0, 5.0], [0.5, 0.05]),       # hx != hy
+    ("b13d", 3, 1, (5, 4, 3), (10.0, 8.0, 6.0), [0.3, 0.7, 5.0, 2.0, 5.0], [0.5, 0.05]),
+    ("b13d", 3, 1, (3, 4, 5), (4.0, 8.0, 7.0), [0.3, 0.7, 5.0, 2.0, 5.0], [0.5, 0.05]),   # anisotropic cells
+    ("bench2", 2, 2, (6, 5), (12.0, 10.0), [0.3, 0.7, 2.0, 3.0, 3.0, 5.0, 1.0, 5.0, 5.0], [0.5, 0.05, 0.1, 1.5]),
+    ("bench3", 2, 3, (6, 5), (12.0, 10.0), [1.0, 1.0, 10.0, 10.0 / 0.6267, 120.0], [-0.3, 8.0, 1.0, 1.0, -1.0]),
+    ("bench6", 2, 6, (6, 5), (12.0, 10.0), [0.3, 0.7, 5.0, 2.0, 5.0, 0.09, 90.0], [0.5, 0.04]),
+]
+
+
+@pytest.mark.parametrize("name,mk,pid,ncell,length,params,icp", CASES)
+def test_operators_match_oracle(name, mk, pid, ncell, length, params, icp):
+    rng = np.random.default_rng(1)
+    D = discretization(name, ncell, length)
+    P, m, nf = D.prob, D.mesh, D.nf
+    U = P.ic(m) + 0.1 * rng.standard_normal((nf, m.nv))
+    U0 = P.ic(m) + 0.1 * rng.standard_normal((nf, m.nv))
+    X = rng.standard_normal((nf, m.nv))
+    dt = 0.37
+    args = (mk, pid, list(ncell), list(length), params, dt)
+    assert rel_max(emul.run(*args, 0, U=U, U0=U0, nf=nf), D.residual(U, U0, dt)) < 1e-13
+    assert rel_max(emul.run(*args, 1, U=U, X=X, nf=nf), (D.jacobian(U, dt) @ X.ravel()).reshape(nf, -1)) < 1e-13
+    EM = emul.run(*args, 2, U=U, nf=nf)
+    assert abs(EM[0] / D.energy(U) - 1) < 1e-13 and abs(EM[1] / D.mass(U) - 1) < 1e-13
+    assert rel_max(emul.run(*args, 4, icp=icp, nf=nf), P.ic(m)) < 1e-14
+    A = 1.3 * D.V.M + 0.7 * D.V.K
+    got = emul.run(*args, 3, U=U, icp=[1.3, 0.7], nf=nf)
+    assert rel_max(got[0], A @ U[0]) < 1e-13 and rel_max(got[1], A.diagonal()) < 1e-14
+
+
+def test_jacobian_is_derivative_of_residual():
+    """J.v against a centred finite difference of R (SURVEY section 7 gate: <= 1e-6)."""
+    rng = np.random.default_rng(2)
+    for (name, mk, pid, ncell, length, params, _) in CASES:
+        D = discretization(name, ncell, length)
+        nf, nv = D.nf, D.nv
+        U = D.prob.ic(D.mesh) + 0.05 * rng.standard_normal((nf, nv))
+        X = rng.standard_normal((nf, nv))
+        args = (mk, pid, list(ncell), list(length), params, 0.2)
+        eps = 1e-6
+        fd = (emul.run(*args, 0, U=U + eps * X, U0=U, nf=nf) - emul.run(*args, 0, U=U - eps * X, U0=U, nf=nf)) / (2 * eps)
+        assert rel_max(emul.run(*args, 1, U=U, X=X, nf=nf), fd) < 1e-7
+
+
+def test_slab_with_ghost_planes_equals_global():
+    """z-slab ownership + one ghost plane per side reproduces the single-domain operator."""
+    rng = np.random.default_rng(3)
+    ncell, length = (4, 3, 7), (8.0, 6.0, 14.0)
+    params = [0.3, 0.7, 5.0, 2.0, 5.0]
+    D = discretization("b13d", ncell, length)
+    nf, nv = 2, D.nv
+    nxy = 5 * 4
+    U = D.prob.ic(D.mesh) + 0.1 * rng.standard_normal((nf, nv))
+    U0 = D.prob.ic(D.mesh) + 0.1 * rng.standard_normal((nf, nv))
+    X = rng.standard_normal((nf, nv))
+    Rg = D.residual(U, U0, 0.3)
+    Yg = (D.jacobian(U, 0.3) @ X.ravel()).reshape(nf, -1)
+    Etot = 0.0
+    for (z0, z1) in [(0, 3), (3, 5), (5, 8)]:
+        sl = slice(z0 * nxy, z1 * nxy)
+
+        def ghosts(zp):
+            g = np.zeros((3, nf, nxy))
+            if 0 <= zp < 8:
+                for i, A in enumerate((U, X, U0)):
+                    g[i] = A[:, zp * nxy:(zp + 1) * nxy]
+            return g
+        kw = dict(z0=z0, nzl=z1 - z0, glo=ghosts(z0 - 1), ghi=ghosts(z1), nf=nf)
+        R = emul.run(3, 1, list(ncell), list(length), params, 0.3, 0, U=U[:, sl], U0=U0[:, sl], **kw)
+        Y = emul.run(3, 1, list(ncell), list(length), params, 0.3, 1, U=U[:, sl], X=X[:, sl], **kw)
+        assert np.abs(R - Rg[:, sl]).max() < 1e-12 * np.abs(Rg).max()
+        assert np.abs(Y - Yg[:, sl]).max() < 1e-12 * np.abs(Yg).max()
+        Etot += emul.run(3, 1, list(ncell), list(length), params, 0.3, 2, U=U[:, sl], **kw)[0]
+    assert abs(Etot / D.energy(U) - 1) < 1e-13
