@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Headline benchmark: implicit Cahn-Hilliard time steps (b13d family) on a synthetic 3-D P1 grid.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--grid 512]
+
+* step      = one backward-Euler time step = `niters, converged = solver.solve()` plus the
+              free-energy / solute reductions (dolfin/b13d.py:149-186), reference solver settings
+              (atol 1e-6, 10 Newton its, Krylov rtol 1e-5), dt list 0.1,0.2,0.4,0.8,1.6,1.6,...
+* workload  = b13d on a Kuhn grid with `grid` vertices per edge (default 512^3 = 2.68e8 DOF), h = 2,
+              bench1 initial condition; for N > 1 the SAME grid is z-slab sharded (strong scaling).
+* value     = DOF x Newton iterations / s over the K timed steps, inputs resident in HBM,
+              CUDA events on the ctx stream, barrier + synchronize on both sides, max over ranks.
+* e2e       = the same steps through the host-buffer C-ABI call pfh_step_host (pinned host arrays,
+              H2D of w and w0 and D2H of w inside the timed region).
+* roofline  = the kernel family with the largest share of the timed region: algorithmic bytes
+               / mean launch duration (CUDA events inside the library).
+* cpu_baseline / --impl reference = the oracle port (numpy/scipy restatement of the FEniCS path;
+              FEniCS itself is not installable here) timed on the host on a bounded sample grid.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CH DOF*Newton-steps/s (b13d 3-D Cahn-Hilliard, implicit step)"
+UNIT = "DOF*Newton-steps/s"
+
+
+def dt_schedule(n):
+    """0.1, 0.2, 0.4, 0.8, 1.6, 1.6, ... (the doubling schedule capped at 1.6)."""
+    return [min(0.1 * 2 ** k, 1.6) for k in range(n)]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def oracle_steps(sample_grid, n_steps, skip=0):
+    """Run backward-Euler steps of the oracle (assemble + Newton + preconditioned GMRES, reference solver
+    tolerances) on a Kuhn grid with `sample_grid` vertices per edge. Returns (dof, newton_its list, seconds list)."""
+    import numpy as np
+    from oracle import krylov, mesh, problems, stepper
+    n = sample_grid - 1
+    m = mesh.kuhn3d(n, n, n, 2.0 * n, 2.0 * n, 2.0 * n)
+    P = problems.CahnHilliard()
+    D = stepper.Discretization(m, P)
+    u = P.ic(m)
+    its, secs = [], []
+    for k, dt in enumerate(dt_schedule(skip + n_steps)):
+        t0 = time.perf_counter()
+        u, nit, ok = D.solve_step(u, u, dt, atol=1e-6, rtol=1e-9, max_it=10,
+                                  linear=krylov.make_linear(rtol=1e-5, n_m=3, n_a=6))
+        E, C = D.energy(u), D.mass(u)
+        t1 = time.perf_counter()
+        assert ok and np.isfinite(E) and np.isfinite(C)
+        if k >= skip:
+            its.append(nit); secs.append(t1 - t0)
+    return 2 * m.nv, its, secs
+
+
+def cpu_baseline(sample_grid=40, n_steps=2):
+    dof, its, secs = oracle_steps(sample_grid, n_steps)
+    return {"value": dof * sum(its) / sum(secs), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle port (numpy/scipy: assembled P1 operators, Newton, Schur-Chebyshev GMRES), %d^3-vertex "
+                      "Kuhn grid, first %d steps of the dt list, single thread" % (sample_grid, n_steps)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dof, its, secs = oracle_steps(args.ref_grid, args.steps, skip=args.warmup)
+    total = sum(secs)
+    val = dof * sum(its) / total
+    sample = ("oracle port (numpy/scipy restatement; FEniCS/PETSc not installable here), %d^3-vertex Kuhn grid sample of the "
+              "b13d workload, steps %d..%d of the dt list, single thread" % (args.ref_grid, args.warmup, args.warmup + args.steps - 1))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "b13d_kuhn3d_%d" % args.grid, "sample_grid": args.ref_grid, "fields": "c,mu"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pfhubbenchmarks_b200 import _lib, engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.grid - 1
+    L = 2.0 * n
+    ctx = engine.Context("b13d", (n, n, n), (L, L, L), device=local, rank=rank, nranks=world, nccl_id=nccl_id,
+                         krylov_basis=args.restart)
+    dof = 2 * ctx.n_global
+    opts = _lib.default_opts(krylov_restart=args.restart, pc_variant=args.pc_variant, pc_sweeps_mass=args.sweeps_mass,
+                             pc_sweeps_shifted=args.sweeps_shifted, krylov_maximum_iterations=int(n ** 3 / 10) or 1000)
+    stream = torch.cuda.ExternalStream(ctx.lib.pfh_stream(ctx._h), device=torch.device("cuda", local))
+    dts = dt_schedule(args.warmup + args.steps)
+
+    w = ctx.initial_condition()
+    w0 = torch.empty_like(w)
+    reports = []
+
+    def one_step(dt):
+        w0.copy_(w)                      # w0.assign(w)       (b13d.py:146)
+        ctx.dt = dt                      # t = tprev + dt
+        rep = ctx.newton_solve(w, w0, opts=opts)    # niters, converged = solver.solve()
+        E, C = ctx.energy(w)             # total_free_energy, total_solute
+        rep["energy"], rep["solute"] = E, C
+        return rep
+
+    for k in range(args.warmup):
+        rep = one_step(dts[k])
+        assert rep["converged"], rep
+    # state at the start of the timed region, kept on the host for the e2e pass
+    start_host = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+    start_host.copy_(w)
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, inputs resident in HBM ----
+    ctx.timers(reset=True)
+    ctx.set_option("profiling", 1)
+    ctx.set_option("reset_launch_count", 0)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for k in range(args.steps):
+        rep = one_step(dts[args.warmup + k])
+        reports.append(rep)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.finish()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count()
+    timers = ctx.timers(reset=True)
+    ctx.set_option("profiling", 0)
+    assert all(r["converged"] for r in reports), reports
+    newton = sum(r["niters"] for r in reports)
+    krylov = sum(r["krylov_its"] for r in reports)
+
+    # ---- e2e: the same K steps through the host-buffer plugin call ----
+    h_w = start_host.numpy().copy() if False else start_host.numpy()
+    h_w0 = torch.empty(w.shape, dtype=w.dtype, pin_memory=True).numpy()
+    e2e_ms, e2e_newton = 0.0, 0
+    for k in range(args.steps):
+        np.copyto(h_w0, h_w)             # w0.assign(w) on the host, outside the timed call
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        rep = ctx.step_host(h_w, h_w0, dts[args.warmup + k], opts=opts)
+        b.record(stream)
+        barrier()
+        e2e_ms += a.elapsed_time(b)
+        e2e_newton += rep["niters"]
+        assert rep["converged"], rep
+    bytes_vec = 8 * 2 * ctx.n_owned
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms = allmax(ms)
+    e2e_ms = allmax(e2e_ms)
+    launches_all = int(allsum(launches))
+    value = dof * newton / (ms * 1e-3)
+    e2e_value = dof * e2e_newton / (e2e_ms * 1e-3)
+
+    peak, peak_src = measured_peak()
+    fam = {k: v for k, v in timers.items() if v["launches"] > 0}
+    total_fam_ms = sum(v["ms"] for v in fam.values())
+    ours = {k: v for k, v in fam.items() if k not in ("halo", "allreduce", "copy")}
+    dom = max(ours, key=lambda k: ours[k]["ms"])
+    d = ours[dom]
+    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": d["bytes"] / d["launches"],
+                "ms_per_launch": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms}
+    kernels = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                   "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                   "share": round(v["ms"] / ms, 4)} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+
+    line = None
+    if rank == 0:
+        cpu = cpu_baseline(args.cpu_grid, 2) if (world == 1 and not args.no_cpu) else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "b13d_kuhn3d_%d" % args.grid, "grid_vertices": [args.grid] * 3, "dof": dof,
+                           "fields": "c,mu", "h": 2.0, "dt_list": dts[args.warmup:], "parallelism": "z-slabs x%d" % world,
+                           "solver": "newton(atol 1e-6, max 10) + GMRES(%d, rtol 1e-5) + Schur/Chebyshev(%d,%d,%s)" % (
+                               args.restart, args.sweeps_mass, args.sweeps_shifted, "upper" if args.pc_variant else "full"),
+                           "l2_policy": "inputs_exceed_l2 (every vector is %.0f MB >> 126 MB L2)" % (bytes_vec / 1e6)},
+                "newton_its": newton, "krylov_its": krylov, "energy": reports[-1]["energy"], "solute": reports[-1]["solute"],
+                "gpu_launches": launches_all, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * bytes_vec * world,
+                        "d2h_bytes_per_step": bytes_vec * world + 32, "ms_per_step": e2e_ms / args.steps},
+                "roofline": roofline, "kernels": kernels, "kernel_time_coverage": total_fam_ms / ms}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=512, help="vertices per edge of the synthetic 3-D grid")
+    ap.add_argument("--restart", type=int, default=30)
+    ap.add_argument("--pc-variant", type=int, default=0)
+    ap.add_argument("--sweeps-mass", type=int, default=3)
+    ap.add_argument("--sweeps-shifted", type=int, default=6)
+    ap.add_argument("--cpu-grid", type=int, default=64, help="sample grid of the cpu_baseline leg")
+    ap.add_argument("--ref-grid", type=int, default=64, help="sample grid of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        print("warning: timing rules ask for >= 3 warm-up steps", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

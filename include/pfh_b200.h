@@ -145,7 +145,8 @@ int pfh_energy_host(pfh_ctx* ctx, const double* w_host, double out[4]);
 long long pfh_launch_count(const pfh_ctx* ctx);
 int pfh_set_option(pfh_ctx* ctx, const char* key, double value);
 #define PFH_N_TIMERS 16
-int pfh_timers(pfh_ctx* ctx, double ms[PFH_N_TIMERS], long long launches[PFH_N_TIMERS], int reset);
+int pfh_timers(pfh_ctx* ctx, double ms[PFH_N_TIMERS], long long launches[PFH_N_TIMERS],
+               double algorithmic_bytes[PFH_N_TIMERS], int reset);
 const char* pfh_timer_name(int i);
 void* pfh_stream(pfh_ctx* ctx);
 int pfh_synchronize(pfh_ctx* ctx);

@@ -67,7 +67,7 @@ SIGNATURES = {
     "pfh_energy_host": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "pfh_launch_count": (C.c_longlong, [_P]),
     "pfh_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
-    "pfh_timers": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
+    "pfh_timers": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.c_int]),
     "pfh_timer_name": (C.c_char_p, [C.c_int]),
     "pfh_stream": (_P, [_P]),
     "pfh_synchronize": (C.c_int, [_P]),

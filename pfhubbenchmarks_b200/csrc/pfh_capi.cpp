@@ -380,14 +380,15 @@ static const char* kTimerNames[PFH_N_TIMERS] = {"residual", "jac_apply", "cheb_s
                                                "initial_condition", "jacobi", "copy", "other"};
 const char* pfh_timer_name(int i) { return (i >= 0 && i < PFH_N_TIMERS) ? kTimerNames[i] : ""; }
 
-int pfh_timers(pfh_ctx* c, double ms[PFH_N_TIMERS], long long launches[PFH_N_TIMERS], int reset) {
+int pfh_timers(pfh_ctx* c, double ms[PFH_N_TIMERS], long long launches[PFH_N_TIMERS], double bytes[PFH_N_TIMERS], int reset) {
   PFH_API_BEGIN
   PFH_CHECK(c, "null argument");
   pfh_prof_resolve(c);
   for (int i = 0; i < PFH_N_TIMERS; ++i) {
     if (ms) ms[i] = c->t_ms[i];
     if (launches) launches[i] = c->t_n[i];
-    if (reset) { c->t_ms[i] = 0.0; c->t_n[i] = 0; }
+    if (bytes) bytes[i] = c->t_bytes[i];
+    if (reset) { c->t_ms[i] = 0.0; c->t_n[i] = 0; c->t_bytes[i] = 0.0; }
   }
   PFH_API_END
 }

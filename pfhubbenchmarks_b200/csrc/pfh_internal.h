@@ -163,6 +163,7 @@ struct pfh_ctx {
   std::vector<EventPair> ev_pending;
   std::vector<EventPair> ev_free;
   double t_ms[PFH_N_TIMERS] = {0};
+  double t_bytes[PFH_N_TIMERS] = {0};  // algorithmic bytes of the launches timed above
   long long t_n[PFH_N_TIMERS] = {0};
   int variant_nl3 = 0;  // 0 = gather (v1), 1 = cube-centric shared-memory kernel
 };
@@ -178,9 +179,12 @@ void pfh_prof_resolve(pfh_ctx* c);
 struct ProfScope {
   pfh_ctx* c;
   int id;
-  ProfScope(pfh_ctx* c_, int id_) : c(c_), id(id_) {
+  ProfScope(pfh_ctx* c_, int id_, double algorithmic_bytes = 0.0) : c(c_), id(id_) {
     if (id != T_COPY && id != T_HALO && id != T_ALLREDUCE) c->launches++;  // our own kernels only
-    if (c->profiling) pfh_prof_begin(c, id);
+    if (c->profiling) {
+      c->t_bytes[id] += algorithmic_bytes;
+      pfh_prof_begin(c, id);
+    }
   }
   ~ProfScope() {
     if (c->profiling) pfh_prof_end(c, id);

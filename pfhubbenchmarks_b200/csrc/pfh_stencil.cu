@@ -260,8 +260,10 @@ LinCoefs pfh_lin_coefs(const pfh_ctx* c, double dt) {
 }
 
 void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
-  ProfScope ps(c, T_RESIDUAL);
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
+  int nprev = 0;
+  for (int a = 0; a < c->nf; ++a) nprev += L.Mp[a] != 0.0;
+  ProfScope ps(c, T_RESIDUAL, 8.0 * (2 * c->nf + nprev) * c->n_owned);
   if (c->dim == 3) {
     PFH_DISPATCH3(c, (k3_op<P, false><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(
                          P(c->prob), c->m3, L, state_fields<P>(c, u, c->gU_lo, c->gU_hi), state_fields<P>(c, nullptr, nullptr, nullptr),
@@ -273,8 +275,9 @@ void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
 }
 
 void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
-  ProfScope ps(c, T_JAC_APPLY);
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
+  const int nin = c->prob.id == PFH_PROBLEM_BENCH2 ? 5 : (c->prob.id == PFH_PROBLEM_BENCH3 ? 2 : 1);
+  ProfScope ps(c, T_JAC_APPLY, 8.0 * (2 * c->nf + nin) * c->n_owned);
   if (c->dim == 3) {
     PFH_DISPATCH3(c, (k3_op<P, true><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(
                          P(c->prob), c->m3, L, state_fields<P>(c, ulin, c->gU_lo, c->gU_hi), state_fields<P>(c, x, c->gX_lo, c->gX_hi),
@@ -286,7 +289,7 @@ void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
 }
 
 void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out) {
-  ProfScope ps(c, T_LIN_APPLY);
+  ProfScope ps(c, T_LIN_APPLY, 8.0 * (s != 0.0 ? 3 : 2) * c->n_owned);
   PFH_CHECK(s == 0.0 || add != nullptr, "k_lin_apply: add operand missing");
   if (c->dim == 3)
     k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out);
@@ -296,7 +299,7 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
 }
 
 void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z) {
-  ProfScope ps(c, T_CHEB_FIRST);
+  ProfScope ps(c, T_CHEB_FIRST, 16.0 * c->n_owned);
   if (c->dim == 3)
     k3_scalar<1><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z);
   else
@@ -305,7 +308,7 @@ void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, d
 }
 
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev) {
-  ProfScope ps(c, T_CHEB_SWEEP);
+  ProfScope ps(c, T_CHEB_SWEEP, 32.0 * c->n_owned);
   if (c->dim == 3)
     k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev);
   else
@@ -314,7 +317,7 @@ void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const do
 }
 
 void k_jacobi(pfh_ctx* c, const double* /*ulin*/, const double* r, double* z) {
-  ProfScope ps(c, T_JACOBI);
+  ProfScope ps(c, T_JACOBI, 16.0 * c->nf * c->n_owned);
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
   if (c->dim == 3)
     k_jacobi_kernel<3><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, c->m3, L, c->nf, r, z);
@@ -326,7 +329,7 @@ void k_jacobi(pfh_ctx* c, const double* /*ulin*/, const double* r, double* z) {
 void k_energy(pfh_ctx* c, const double* u, double out[4]) {
   const int nb = grid_red(c->n_owned);
   {
-    ProfScope ps(c, T_ENERGY);
+    ProfScope ps(c, T_ENERGY, 8.0 * c->nf * c->n_owned);
     if (c->dim == 3) {
       PFH_DISPATCH3(c, (k3_energy<P><<<nb, TPB, 0, c->stream>>>(P(c->prob), c->m3, state_fields<P>(c, u, c->gU_lo, c->gU_hi), c->d_partial)));
     } else {

@@ -156,15 +156,15 @@ const double* pfh_reduce_finish(pfh_ctx* c, int nblocks, int nvals) {
 }
 
 void v_copy(pfh_ctx* c, double* dst, const double* src, long long n) {
-  ProfScope ps(c, T_COPY);
+  ProfScope ps(c, T_COPY, 16.0 * n);
   PFH_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
 }
 void v_zero(pfh_ctx* c, double* dst, long long n) {
-  ProfScope ps(c, T_COPY);
+  ProfScope ps(c, T_COPY, 8.0 * n);
   PFH_CUDA(cudaMemsetAsync(dst, 0, n * sizeof(double), c->stream));
 }
 void v_axpby(pfh_ctx* c, double a, const double* x, double b, const double* y, double* out, long long n) {
-  ProfScope ps(c, T_VEC);
+  ProfScope ps(c, T_VEC, 8.0 * (b != 0.0 ? 3 : 2) * n);
   k_axpby<<<grid_stream(n), TPB, 0, c->stream>>>(a, x, b, y, out, n);
   PFH_CUDA(cudaGetLastError());
 }
@@ -180,7 +180,7 @@ void v_multidot(pfh_ctx* c, const double* V, long long stride, int nv, const dou
   do {
     const int cnt = nv - k0 < MD ? nv - k0 : MD;
     const bool last = k0 + cnt >= nv;
-    ProfScope ps(c, T_MULTIDOT);
+    ProfScope ps(c, T_MULTIDOT, 8.0 * (cnt + 1) * n);
     if (last)
       k_multidot<true><<<nb, TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, k0, nv, w, n, c->d_partial);
     else
@@ -204,8 +204,8 @@ static void multiaxpy_raw(pfh_ctx* c, const double* V, long long stride, int nv,
     const int cnt = nv - k0 < MD ? nv - k0 : MD;
     Coef cf;
     for (int k = 0; k < MD; ++k) cf.v[k] = k < cnt ? coef[k0 + k] : 0.0;
-    ProfScope ps(c, T_MULTIAXPY);
     const double* win = first ? w : out;
+    ProfScope ps(c, T_MULTIAXPY, 8.0 * (cnt + (win ? 2 : 1)) * n);
     if (win)
       k_multiaxpy<true><<<grid_stream(n), TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, cf, win,
                                                               first ? wscale : 1.0, out, n);
@@ -233,7 +233,7 @@ void v_combine(pfh_ctx* c, const double* V, long long stride, int nv, const doub
 double v_norm2(pfh_ctx* c, const double* x, long long n) {
   const int nb = grid_stream(n);
   {
-    ProfScope ps(c, T_VEC);
+    ProfScope ps(c, T_VEC, 8.0 * n);
     k_norm2<<<nb, TPB, 0, c->stream>>>(x, n, c->d_partial);
     PFH_CUDA(cudaGetLastError());
   }

@@ -193,8 +193,10 @@ class Context:
     def timers(self, reset=False):
         ms = (C.c_double * _lib.N_TIMERS)()
         n = (C.c_longlong * _lib.N_TIMERS)()
-        _lib.check(self.lib.pfh_timers(self._h, ms, n, 1 if reset else 0))
-        return {self.lib.pfh_timer_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(_lib.N_TIMERS)}
+        nbytes = (C.c_double * _lib.N_TIMERS)()
+        _lib.check(self.lib.pfh_timers(self._h, ms, n, nbytes, 1 if reset else 0))
+        return {self.lib.pfh_timer_name(i).decode(): {"ms": float(ms[i]), "launches": int(n[i]), "bytes": float(nbytes[i])}
+                for i in range(_lib.N_TIMERS)}
 
     def synchronize(self):
         _lib.check(self.lib.pfh_synchronize(self._h))

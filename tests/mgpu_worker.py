@@ -1,0 +1,75 @@
+"""Multi-GPU worker (launched by torchrun): z-slab sharded b13d steps must equal the single-GPU run.
+Every rank steps its slab; rank 0 also steps the whole grid on its own GPU and compares."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pfhubbenchmarks_b200 import _lib, engine  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    grid = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    buf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(engine.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    n = grid - 1
+    ncell, length = (n, n + 3, n), (2.0 * n, 2.0 * (n + 3), 2.0 * n)
+    ctx = engine.Context("b13d", ncell, length, device=local, rank=rank, nranks=world, nccl_id=buf.cpu().numpy().tobytes())
+    nxy = (ncell[0] + 1) * (ncell[1] + 1)
+    assert ctx.n_owned == nxy * (ctx.z_range[1] - ctx.z_range[0])
+    w = ctx.initial_condition()
+    # perturb with a z-dependent term so that slabs differ (the reference IC ignores z)
+    z = torch.arange(ctx.z_range[0], ctx.z_range[1], device="cuda", dtype=torch.float64).repeat_interleave(nxy)
+    w[:ctx.n_owned] += 0.01 * torch.cos(0.3 * z)
+    hist = []
+    for dt in (0.1, 0.2, 0.4):
+        w0 = w.clone()
+        ctx.dt = dt
+        rep = ctx.newton_solve(w, w0, absolute_tolerance=1e-10, krylov_rtol=1e-9, maximum_iterations=20)
+        assert rep["converged"], rep
+        hist.append((rep["niters"], rep["krylov_its"]) + ctx.energy(w))
+    # gather slabs on rank 0
+    parts = [None] * world
+    dist.all_gather_object(parts, (ctx.z_range, w.cpu().numpy()))
+    ctx.close()
+    ok = True
+    if rank == 0:
+        one = engine.Context("b13d", ncell, length, device=local)
+        v = one.initial_condition()
+        zz = torch.arange(0, ncell[2] + 1, device="cuda", dtype=torch.float64).repeat_interleave(nxy)
+        v[:one.n_owned] += 0.01 * torch.cos(0.3 * zz)
+        ref_hist = []
+        for dt in (0.1, 0.2, 0.4):
+            v0 = v.clone()
+            one.dt = dt
+            rep = one.newton_solve(v, v0, absolute_tolerance=1e-10, krylov_rtol=1e-9, maximum_iterations=20)
+            assert rep["converged"], rep
+            ref_hist.append((rep["niters"], rep["krylov_its"]) + one.energy(v))
+        ref = v.cpu().numpy().reshape(2, -1)
+        got = np.zeros_like(ref)
+        for (z0, z1), arr in parts:
+            got[:, z0 * nxy:z1 * nxy] = arr.reshape(2, -1)
+        err = [np.linalg.norm(got[f] - ref[f]) / np.linalg.norm(ref[f]) for f in range(2)]
+        de = abs(hist[-1][2] / ref_hist[-1][2] - 1)
+        dm = abs(hist[-1][3] / ref_hist[-1][3] - 1)
+        print("mgpu world=%d grid=%d  rel L2 (c, mu) = %.2e %.2e  dE %.1e dM %.1e  its %s vs %s" % (
+            world, grid, err[0], err[1], de, dm, hist, ref_hist), flush=True)
+        ok = err[0] < 1e-10 and err[1] < 1e-8 and de < 1e-11 and dm < 1e-13
+        one.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
