@@ -367,8 +367,8 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->profiling = value != 0.0;
   } else if (k == "reset_launch_count") {
     c->launches = 0;
-  } else if (k == "nl3_variant") {
-    c->variant_nl3 = (int)value;
+  } else if (k == "use_tma") {
+    c->use_tma = value != 0.0;
   } else {
     throw PfhError("unknown option: " + k);
   }

@@ -165,7 +165,7 @@ struct pfh_ctx {
   double t_ms[PFH_N_TIMERS] = {0};
   double t_bytes[PFH_N_TIMERS] = {0};  // algorithmic bytes of the launches timed above
   long long t_n[PFH_N_TIMERS] = {0};
-  int variant_nl3 = 0;  // 0 = gather (v1), 1 = cube-centric shared-memory kernel
+  bool use_tma = true;  // 3-D fast path: TMA-staged kernels (pfh_stencil3_tma.cu); false = gather kernels only
 };
 
 #define PFH_RED_MAXBLOCKS 1184  // 8 CTAs per SM * 148 SMs
@@ -207,6 +207,12 @@ void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z);
 void k_energy(pfh_ctx* c, const double* u, double out[4]);  // includes final reduction + allreduce + D2H
 void k_initial_condition(pfh_ctx* c, const double* icp, int n, double* w);
 void k_dirichlet_fix(pfh_ctx* c, double* w);  // impose Dirichlet values on the iterate (bench6)
+
+// ---- TMA-staged 3-D kernels (pfh_stencil3_tma.cu); return false when the operands do not qualify ----
+bool pfh_tma_ok(const pfh_ctx* c);
+bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
+                          double* out);
+bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const double* x, double* y);
 
 // ---- vector kernels (pfh_vec.cu) ----
 void v_copy(pfh_ctx* c, double* dst, const double* src, long long n);

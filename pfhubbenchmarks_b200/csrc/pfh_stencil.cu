@@ -278,6 +278,7 @@ void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
   const int nin = c->prob.id == PFH_PROBLEM_BENCH2 ? 5 : (c->prob.id == PFH_PROBLEM_BENCH3 ? 2 : 1);
   ProfScope ps(c, T_JAC_APPLY, 8.0 * (2 * c->nf + nin) * c->n_owned);
+  if (c->dim == 3 && k3_jac_tma_launch(c, L, ulin, x, y)) return;
   if (c->dim == 3) {
     PFH_DISPATCH3(c, (k3_op<P, true><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(
                          P(c->prob), c->m3, L, state_fields<P>(c, ulin, c->gU_lo, c->gU_hi), state_fields<P>(c, x, c->gX_lo, c->gX_hi),
@@ -291,6 +292,7 @@ void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
 void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out) {
   ProfScope ps(c, T_LIN_APPLY, 8.0 * (s != 0.0 ? 3 : 2) * c->n_owned);
   PFH_CHECK(s == 0.0 || add != nullptr, "k_lin_apply: add operand missing");
+  if (c->dim == 3 && k3_scalar_tma_launch(c, 0, am, ak, s, 0.0, in, add, out)) return;
   if (c->dim == 3)
     k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out);
   else
@@ -309,6 +311,7 @@ void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, d
 
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev) {
   ProfScope ps(c, T_CHEB_SWEEP, 32.0 * c->n_owned);
+  if (c->dim == 3 && k3_scalar_tma_launch(c, 2, am, ak, a, b, z, r, zprev)) return;
   if (c->dim == 3)
     k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev);
   else

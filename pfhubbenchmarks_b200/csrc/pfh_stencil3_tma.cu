@@ -1,0 +1,450 @@
+// TMA-staged 3-D stencil kernels for sm_100a (the fast path of the b13d hot loop).
+//
+// Both kernels tile the x-y plane, march along z and keep the vertex planes they need in a ring
+// of shared-memory stages that one elected thread fills with cp.async.bulk.tensor (TMA) loads
+// signalled through mbarriers, so the loads of plane z+2.. overlap the arithmetic of plane z.
+// TMA's out-of-bounds zero fill supplies the halo outside the domain (the boundary rows of M
+// and K come from the stencil tables), and the ghost planes of a z-slab are separate one-plane
+// tensors selected per plane.
+//
+//  k3_scalar_tma : A = am M + ak K on a scalar field (15-point P1 stencil):
+//                  MODE 0  out = s*add + A in                      (lin_apply)
+//                  MODE 2  zprev <- z + a (z - zprev) + b D^-1 (r - A z)   (Jacobi-Chebyshev sweep)
+//                  algorithmic traffic 32 B/vertex (MODE 2), 16-24 B/vertex (MODE 0).
+//  k3_jac_tma    : y = J(u) x for the mixed system.  The nonlinear block int phi_i g'(u_h) x_h is
+//                  evaluated ONCE per tetrahedron (cube-centric, 5-point Zienkiewicz-Taylor rule,
+//                  pfh_elem.cuh) and scattered to the 8 cube corners through shared memory; each
+//                  vertex then gathers its 8 cube contributions, so no quadrature is recomputed
+//                  across the 24 tets around a vertex (the v1 gather kernel does 4x the flops).
+//                  algorithmic traffic 8 (NIN + 2 NF) B/vertex = 40 B/vertex for Cahn-Hilliard.
+//
+// Reference hot loops replaced: PETSc MatMult / PCApply and FFC tabulate_tensor + assembly of
+// J = df.derivative(F, w, dw) (dolfin/b13d.py:68; SURVEY.md section 3.3 loops B-D).
+#include <cuda.h>
+
+#include "pfh_vertex.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------------------------
+// scalar operator kernel
+// ---------------------------------------------------------------------------------------------
+struct Coef15 {
+  double c[PFH_NOFF3];
+};
+
+template <int MODE, int TX, int TY, int RY, int NS>
+__global__ void __launch_bounds__(TX*(TY / RY))
+    k3_scalar_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_lo,
+                  const __grid_constant__ CUtensorMap tm_hi, Mesh3 m, int has_lo, int has_hi, int zchunk, double am, double ak,
+                  Coef15 cI, double a, double b, const double* __restrict__ r, double* __restrict__ out) {
+  constexpr int W = TX + 4, H = TY + 2;  // x halo of 2: the TMA box start (x0-2) must be 16-byte aligned
+  constexpr int STAGE_BYTES = W * H * 8;
+  constexpr int STAGE_STRIDE = round_up(STAGE_BYTES, 128);
+  constexpr int ROWS = TY / RY;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * STAGE_STRIDE);
+  auto stage = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * STAGE_STRIDE); };
+
+  const int tid = threadIdx.y * TX + threadIdx.x;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int zb = blockIdx.z * zchunk, ze = min(m.nzl, zb + zchunk);
+  const int nplanes = ze - zb + 2;  // planes zb-1 .. ze  <->  p = 0 .. nplanes-1
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int p) {
+    const int zl = zb - 1 + p;
+    const CUtensorMap* map = &tm_main;
+    int zc = zl;  // zl = -1 or nzl on a physical boundary: out of bounds in z -> zero fill
+    if (zl < 0 && has_lo) {
+      map = &tm_lo;
+      zc = 0;
+    } else if (zl >= m.nzl && has_hi) {
+      map = &tm_hi;
+      zc = 0;
+    }
+    uint64_t* bar = &bars[p % NS];
+    mbar_expect_tx(bar, STAGE_BYTES);
+    tma_load_3d(smem + (p % NS) * STAGE_STRIDE, map, x0 - 2, y0 - 1, zc, bar);
+  };
+  if (tid == 0)
+    for (int p = 0; p < NS - 1 && p < nplanes; ++p) issue(p);
+
+  const int ix = x0 + threadIdx.x;
+  const int txt = ix == 0 ? 0 : (ix == m.nxv - 1 ? 2 : 1);
+  const double dI = cI.c[0];
+
+  for (int k = 0; k < ze - zb; ++k) {
+    const int zl = zb + k;
+    __syncthreads();  // every thread is done with plane k-1: its stage may be refilled
+    if (tid == 0 && k + NS - 1 < nplanes) issue(k + NS - 1);
+
+    // pointwise operands first, so their latency overlaps the wait on the TMA planes
+    double rv[RY], ov[RY];
+    bool valid[RY];
+    long long idx[RY];
+#pragma unroll
+    for (int rr = 0; rr < RY; ++rr) {
+      const int iy = y0 + threadIdx.y + rr * ROWS;
+      valid[rr] = ix < m.nxv && iy < m.nyv;
+      idx[rr] = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
+      rv[rr] = 0.0;
+      ov[rr] = 0.0;
+      if (valid[rr]) {
+        if (MODE == 2 || a != 0.0) rv[rr] = __ldg(r + idx[rr]);
+        if (MODE == 2) ov[rr] = out[idx[rr]];
+      }
+    }
+    if (k == 0) {
+      mbar_wait(&bars[0], 0);
+      mbar_wait(&bars[1 % NS], (1 / NS) & 1);
+    }
+    mbar_wait(&bars[(k + 2) % NS], ((k + 2) / NS) & 1);
+
+    const double* S0 = stage(k);
+    const double* S1 = stage(k + 1);
+    const double* S2 = stage(k + 2);
+    const int gz = m.z0 + zl;
+    const int tzt = gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1);
+#pragma unroll
+    for (int rr = 0; rr < RY; ++rr) {
+      if (!valid[rr]) continue;
+      const int ly = threadIdx.y + rr * ROWS;
+      const int iy = y0 + ly;
+      const int c = (ly + 1) * W + threadIdx.x + 2;
+      double v[PFH_NOFF3];
+      v[0] = S1[c]; v[1] = S1[c + 1]; v[2] = S1[c - 1]; v[3] = S1[c + W]; v[4] = S1[c - W];
+      v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
+      v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
+      v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
+      const int tyt = iy == 0 ? 0 : (iy == m.nyv - 1 ? 2 : 1);
+      const int type = tzt * 9 + tyt * 3 + txt;
+      double Av = 0.0, d;
+      if (type == 13) {
+#pragma unroll
+        for (int o = 0; o < PFH_NOFF3; ++o) Av += cI.c[o] * v[o];
+        d = dI;
+      } else {
+        vtx::Row3 row;
+        vtx::get_row3(m, type, row);
+        double Ms, Ks;
+        vtx::mk_sums3(row, v, Ms, Ks);
+        Av = am * Ms + ak * Ks;
+        d = am * row.m[0] + ak * row.k[0];
+      }
+      if (MODE == 0) out[idx[rr]] = a * rv[rr] + Av;
+      else out[idx[rr]] = v[0] + a * (v[0] - ov[rr]) + (b / d) * (rv[rr] - Av);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobian-vector product, cube-centric
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct MapSet {
+  CUtensorMap main[N], lo[N], hi[N];
+};
+
+template <class P, int TX, int TY, int NT, int NS>
+__global__ void __launch_bounds__(NT)
+    k3_jac_tma(const __grid_constant__ MapSet<P::NF + P::NIN> maps, P prob, Mesh3 m, LinCoefs L, int has_lo, int has_hi,
+               int zchunk, double* __restrict__ out) {
+  constexpr int NFLD = P::NF + P::NIN;  // ring-buffered fields: x_0..x_{NF-1}, then u_{in(0)}..u_{in(NIN-1)}
+  constexpr int W = TX + 4, H = TY + 2;  // x halo of 2 (16-byte aligned TMA box start)
+  constexpr int STAGE_BYTES = W * H * 8;
+  constexpr int STAGE_STRIDE = round_up(STAGE_BYTES, 128);
+  constexpr int CW = TX + 1, CH = TY + 1, NCUBE = CW * CH;
+  constexpr int CPAD = NCUBE | 1;  // odd pitch: corner arrays start in different banks
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [NFLD][NS] stages | contrib[NOUT][8][CPAD] | mbarriers[NS]
+  double* contrib = reinterpret_cast<double*>(smem + NFLD * NS * STAGE_STRIDE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(contrib + P::NOUT * 8 * CPAD);
+  auto stage = [&](int f, int p) { return reinterpret_cast<const double*>(smem + (f * NS + (p % NS)) * STAGE_STRIDE); };
+
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int zb = blockIdx.z * zchunk, ze = min(m.nzl, zb + zchunk);
+  const int nplanes = ze - zb + 2;  // planes zb-1 .. ze
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int p) {
+    const int zl = zb - 1 + p;
+    uint64_t* bar = &bars[p % NS];
+    mbar_expect_tx(bar, NFLD * STAGE_BYTES);
+#pragma unroll
+    for (int f = 0; f < NFLD; ++f) {
+      const CUtensorMap* map = &maps.main[f];
+      int zc = zl;
+      if (zl < 0 && has_lo) {
+        map = &maps.lo[f];
+        zc = 0;
+      } else if (zl >= m.nzl && has_hi) {
+        map = &maps.hi[f];
+        zc = 0;
+      }
+      tma_load_3d(smem + (f * NS + (p % NS)) * STAGE_STRIDE, map, x0 - 2, y0 - 1, zc, bar);
+    }
+  };
+  if (tid == 0)
+    for (int p = 0; p < NS - 2 && p < nplanes; ++p) issue(p);
+
+  // vertex role (tid < TX*TY)
+  const int vtx_x = tid % TX, vtx_y = tid / TX;
+  const int ix = x0 + vtx_x, iy = y0 + vtx_y;
+  const bool is_vertex = tid < TX * TY && ix < m.nxv && iy < m.nyv;
+  const int txt = ix == 0 ? 0 : (ix == m.nxv - 1 ? 2 : 1);
+  const int tyt = iy == 0 ? 0 : (iy == m.nyv - 1 ? 2 : 1);
+  double acc_hi[P::NOUT];
+#pragma unroll
+  for (int o = 0; o < P::NOUT; ++o) acc_hi[o] = 0.0;
+
+  // iteration `it` handles cube layer l = zb-1+it (between planes l and l+1) and writes plane l (it >= 1)
+  for (int it = 0; it <= ze - zb; ++it) {
+    const int l = zb - 1 + it;
+    __syncthreads();  // plane it-2 and the previous contributions are no longer needed
+    if (tid == 0 && it + NS - 2 < nplanes) issue(it + NS - 2);
+    if (it == 0) mbar_wait(&bars[0], 0);
+    if (it + 1 < nplanes) mbar_wait(&bars[(it + 1) % NS], ((it + 1) / NS) & 1);
+
+    // ---- cube phase ----
+    const int gl = m.z0 + l;
+    for (int q = tid; q < NCUBE; q += NT) {
+      const int qx = q % CW, qy = q / CW;
+      const int cx = x0 - 1 + qx, cy = y0 - 1 + qy;
+      double o8[P::NOUT][8];
+#pragma unroll
+      for (int o = 0; o < P::NOUT; ++o)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) o8[o][kk] = 0.0;
+      if (cx >= 0 && cx <= m.nxv - 2 && cy >= 0 && cy <= m.nyv - 2 && gl >= 0 && gl <= m.nzv - 2) {
+        double u[P::NIN][8], x[P::NIN][8];
+        const int base = qy * W + qx + 1;
+#pragma unroll
+        for (int f = 0; f < P::NIN; ++f) {
+          const double* u0 = stage(P::NF + f, it);
+          const double* u1 = stage(P::NF + f, it + 1);
+          const double* xa = stage(P::in(f), it);
+          const double* xb = stage(P::in(f), it + 1);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int off = base + (kk >> 1) * W + (kk & 1);
+            u[f][kk] = u0[off];
+            u[f][kk + 4] = u1[off];
+            x[f][kk] = xa[off];
+            x[f][kk + 4] = xb[off];
+          }
+        }
+        elem::cube_load<P, true>(prob, u, x, m.detJ, o8);
+      }
+#pragma unroll
+      for (int o = 0; o < P::NOUT; ++o)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) contrib[(o * 8 + kk) * CPAD + q] = o8[o][kk];
+    }
+    __syncthreads();
+
+    // ---- vertex phase ----
+    if (is_vertex) {
+      double lo[P::NOUT], hi[P::NOUT];
+#pragma unroll
+      for (int o = 0; o < P::NOUT; ++o) {
+        double slo = 0.0, shi = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int q = (vtx_y + 1 - (kk >> 1)) * CW + (vtx_x + 1 - (kk & 1));
+          slo += contrib[(o * 8 + kk) * CPAD + q];
+          shi += contrib[(o * 8 + 4 + kk) * CPAD + q];
+        }
+        lo[o] = slo;
+        hi[o] = shi;
+      }
+      if (it >= 1) {
+        const int gz = m.z0 + l;
+        const int tzt = gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1);
+        const int type = tzt * 9 + tyt * 3 + txt;
+        vtx::Row3 row;
+        vtx::get_row3(m, type, row);
+        const int c = (vtx_y + 1) * W + vtx_x + 2;
+        double Ms[P::NF], Ks[P::NF];
+#pragma unroll
+        for (int f = 0; f < P::NF; ++f) {
+          const double* S0 = stage(f, it - 1);
+          const double* S1 = stage(f, it);
+          const double* S2 = stage(f, it + 1);
+          double v[PFH_NOFF3];
+          v[0] = S1[c]; v[1] = S1[c + 1]; v[2] = S1[c - 1]; v[3] = S1[c + W]; v[4] = S1[c - W];
+          v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
+          v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
+          v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
+          vtx::mk_sums3(row, v, Ms[f], Ks[f]);
+        }
+        double y[P::NF];
+#pragma unroll
+        for (int aa = 0; aa < P::NF; ++aa) {
+          double s = 0.0;
+#pragma unroll
+          for (int bb = 0; bb < P::NF; ++bb) s += L.Mc[aa][bb] * Ms[bb] + L.Kc[aa][bb] * Ks[bb];
+          y[aa] = s;
+        }
+#pragma unroll
+        for (int o = 0; o < P::NOUT; ++o) y[P::out(o)] += acc_hi[o] + lo[o];
+        const long long i = (long long)l * m.nxy + (long long)iy * m.nxv + ix;
+#pragma unroll
+        for (int aa = 0; aa < P::NF; ++aa) out[aa * m.n_owned + i] = y[aa];
+      }
+#pragma unroll
+      for (int o = 0; o < P::NOUT; ++o) acc_hi[o] = hi[o];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PFH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    PFH_CHECK(q == cudaDriverEntryPointSuccess && p != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp64 tensor (nxv, nyv, nz) at `ptr`, box (bx, by, 1), zero fill outside
+CUtensorMap make_map(const double* ptr, int nxv, int nyv, int nz, int bx, int by) {
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)nxv, (cuuint64_t)nyv, (cuuint64_t)nz};
+  const cuuint64_t strides[2] = {(cuuint64_t)nxv * 8, (cuuint64_t)nxv * nyv * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult rc = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(ptr), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) throw PfhError("cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
+  return map;
+}
+
+constexpr int S_TX = 64, S_TY = 8, S_RY = 2, S_NS = 5, S_ZCH = 32;
+constexpr int J_TX = 32, J_TY = 8, J_NT = 320, J_NS = 4, J_ZCH = 32;
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+bool pfh_tma_ok(const pfh_ctx* c) {
+  return c->dim == 3 && c->use_tma && (c->m3.nxv % 2) == 0 && c->m3.nxv >= 8 && c->m3.nyv >= 4 && c->m3.nzl >= 2;
+}
+
+// MODE 0 (lin_apply) and MODE 2 (Chebyshev sweep) through the TMA kernel; returns false if the
+// operands do not qualify (caller falls back to the gather kernel)
+bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
+                          double* out) {
+  if (!pfh_tma_ok(c) || !aligned16(in.p)) return false;
+  const Mesh3& m = c->m3;
+  const bool lo = in.glo != nullptr && c->cfg.rank > 0, hi = in.ghi != nullptr && c->cfg.rank < c->cfg.nranks - 1;
+  if ((lo && !aligned16(in.glo)) || (hi && !aligned16(in.ghi))) return false;
+  const CUtensorMap tm = make_map(in.p, m.nxv, m.nyv, m.nzl, S_TX + 4, S_TY + 2);
+  const CUtensorMap tl = lo ? make_map(in.glo, m.nxv, m.nyv, 1, S_TX + 4, S_TY + 2) : tm;
+  const CUtensorMap th = hi ? make_map(in.ghi, m.nxv, m.nyv, 1, S_TX + 4, S_TY + 2) : tm;
+  Coef15 cI;
+  for (int o = 0; o < PFH_NOFF3; ++o) cI.c[o] = am * m.mI[o] + (o < PFH_NKOFF3 ? ak * m.kI[o] : 0.0);
+  const dim3 grid((m.nxv + S_TX - 1) / S_TX, (m.nyv + S_TY - 1) / S_TY, (m.nzl + S_ZCH - 1) / S_ZCH);
+  const dim3 block(S_TX, S_TY / S_RY);
+  constexpr int stage = round_up((S_TX + 4) * (S_TY + 2) * 8, 128);
+  const size_t smem = S_NS * stage + S_NS * sizeof(uint64_t);
+  if (mode == 0)
+    k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, am, ak, cI, a, b, r, out);
+  else
+    k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, am, ak, cI, a, b, r, out);
+  PFH_CUDA(cudaGetLastError());
+  return true;
+}
+
+// y = J(ulin) x for Cahn-Hilliard on the Kuhn mesh; ghosts: gX_* for x, gU_* for ulin
+bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const double* x, double* y) {
+  if (!pfh_tma_ok(c) || c->prob.id != PFH_PROBLEM_CH || !aligned16(ulin) || !aligned16(x)) return false;
+  using P = ProbCH;
+  const Mesh3& m = c->m3;
+  if ((m.n_owned & 1) || (c->nplane & 1)) return false;  // field offsets must stay 16-byte aligned
+  const bool lo = c->nplane > 0 && c->cfg.rank > 0, hi = c->nplane > 0 && c->cfg.rank < c->cfg.nranks - 1;
+  MapSet<P::NF + P::NIN> maps;
+  for (int f = 0; f < P::NF + P::NIN; ++f) {
+    const bool isx = f < P::NF;
+    const int fld = isx ? f : P::in(f - P::NF);
+    const double* base = (isx ? x : ulin) + (long long)fld * m.n_owned;
+    const double* glo = (isx ? c->gX_lo : c->gU_lo);
+    const double* ghi = (isx ? c->gX_hi : c->gU_hi);
+    maps.main[f] = make_map(base, m.nxv, m.nyv, m.nzl, J_TX + 4, J_TY + 2);
+    maps.lo[f] = lo ? make_map(glo + (long long)fld * c->nplane, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[f];
+    maps.hi[f] = hi ? make_map(ghi + (long long)fld * c->nplane, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[f];
+  }
+  constexpr int stage = round_up((J_TX + 4) * (J_TY + 2) * 8, 128);
+  constexpr int ncube = (J_TX + 1) * (J_TY + 1);
+  constexpr size_t smem = (size_t)(P::NF + P::NIN) * J_NS * stage + (size_t)P::NOUT * 8 * (ncube | 1) * 8 + J_NS * sizeof(uint64_t);
+  auto kern = k3_jac_tma<P, J_TX, J_TY, J_NT, J_NS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const dim3 grid((m.nxv + J_TX - 1) / J_TX, (m.nyv + J_TY - 1) / J_TY, (m.nzl + J_ZCH - 1) / J_ZCH);
+  kern<<<grid, J_NT, smem, c->stream>>>(maps, P(c->prob), m, L, lo, hi, J_ZCH, y);
+  PFH_CUDA(cudaGetLastError());
+  return true;
+}

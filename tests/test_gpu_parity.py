@@ -32,6 +32,10 @@ OP_CASES = [
     ("b13d", (5, 4, 3), (10.0, 8.0, 6.0)),
     ("b13d", (70, 9, 21), (140.0, 18.0, 42.0)),      # ragged: not multiples of the tile sizes
     ("b13d", (16, 16, 16), (32.0, 32.0, 32.0)),
+    # even vertex counts in x take the TMA-staged kernels (pfh_stencil3_tma.cu); ragged vs their 64x8 / 32x8 tiles
+    ("b13d", (15, 16, 17), (30.0, 32.0, 34.0)),
+    ("b13d", (71, 9, 40), (142.0, 18.0, 80.0)),
+    ("b13d", (129, 21, 11), (258.0, 42.0, 22.0)),
     ("bench2", (12, 9), (24.0, 18.0)),
     ("bench3", (12, 9), (24.0, 18.0)),
     ("bench6", (12, 9), (24.0, 18.0)),
@@ -158,7 +162,11 @@ def test_reference_solver_settings_semantics():
 def test_b13d_step_matches_oracle():
     """3-D Kuhn mesh (no reference data exists: parity unpinned, oracle self-consistency only)."""
     eng = _engine()
-    ncell, length = (16, 16, 16), (32.0, 32.0, 32.0)
+    _b13d_steps(eng, (16, 16, 16), (32.0, 32.0, 32.0))      # odd vertex count: gather kernels
+    _b13d_steps(eng, (15, 17, 16), (30.0, 34.0, 32.0))      # even vertex count: TMA-staged kernels
+
+
+def _b13d_steps(eng, ncell, length):
     D = discretization("b13d", ncell, length)
     ctx = eng.Context("b13d", ncell, length)
     nv = ctx.n_owned
@@ -175,6 +183,30 @@ def test_b13d_step_matches_oracle():
         assert rel_l2(got[0], u[0]) < 1e-9 and rel_l2(got[1], u[1]) < 1e-7
         E, M = ctx.energy(w)
         assert abs(E / D.energy(u) - 1) < 1e-9 and abs(M / D.mass(u) - 1) < 1e-12
+    ctx.close()
+
+
+def test_tma_kernels_match_gather_kernels():
+    """Fast path (TMA-staged, cube-centric J.v) against the simple gather kernels on a mid-size grid."""
+    eng = _engine()
+    ncell, length = (127, 70, 45), (254.0, 140.0, 90.0)
+    rng = np.random.default_rng(11)
+    ctx = eng.Context("b13d", ncell, length)
+    n = ctx.n_owned
+    U = ctx.initial_condition()
+    U += 0.05 * torch.from_numpy(rng.standard_normal(2 * n)).cuda()
+    X = torch.from_numpy(rng.standard_normal(2 * n)).cuda()
+    ctx.dt = 0.8
+    out = {}
+    for tma in (0, 1):
+        ctx.set_option("use_tma", tma)
+        ctx.jac_setup(U)
+        y = ctx.jac_apply(X)
+        ctx.precond_setup(pc_variant=0, pc_sweeps_mass=3, pc_sweeps_shifted=6)
+        z = ctx.precond_apply(X)
+        out[tma] = (y.cpu().numpy(), z.cpu().numpy())
+    assert rel_max(out[1][0], out[0][0]) < 1e-13
+    assert rel_max(out[1][1], out[0][1]) < 1e-12
     ctx.close()
 
 
