@@ -201,7 +201,7 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
 void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z);
 // zprev <- z + a (z - zprev) + b Dinv (r - (am M + ak K) z)
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z,
-                  double* zprev);
+                  double* zprev, bool zprev_is_zero);  // zprev_is_zero: zprev is write-only (z_{k-1} = 0)
 // point-Jacobi on the Jacobian diagonal blocks: z_a = r_a / diag_a
 void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z);
 void k_energy(pfh_ctx* c, const double* u, double out[4]);  // includes final reduction + allreduce + D2H
@@ -211,8 +211,11 @@ void k_dirichlet_fix(pfh_ctx* c, double* w);  // impose Dirichlet values on the 
 // ---- TMA-staged 3-D kernels (pfh_stencil3_tma.cu); return false when the operands do not qualify ----
 bool pfh_tma_ok(const pfh_ctx* c);
 bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
-                          double* out);
+                          double* out, bool out_is_zero);
 bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const double* x, double* y);
+bool k3_ch_crow_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, FieldRef xc, double* out);
+// out = [J(ulin) (xc, 0)]_mu for Cahn-Hilliard (scalar in, scalar out); false if no fast path applies
+bool k_ch_crow(pfh_ctx* c, const double* ulin, FieldRef xc, double* out);
 
 // ---- vector kernels (pfh_vec.cu) ----
 void v_copy(pfh_ctx* c, double* dst, const double* src, long long n);

@@ -25,6 +25,11 @@
 // ---------------- bench1 / b13d : Cahn-Hilliard, fields (c, mu) ----------------
 struct ProbCH {
   static constexpr int NF = 2, NIN = 1, NOUT = 1;
+  static constexpr bool QUARTIC = true;  // dg(c; x) = (a2 c^2 + a1 c + a0) x : enables the low-flop cube routine
+  PFH_HD void jac_poly(double& a2, double& a1, double& a0) const {  // -f''(c), f = rho (c-ca)^2 (cb-c)^2
+    const double s = ca + cb;
+    a2 = -12.0 * rho; a1 = 12.0 * rho * s; a0 = -rho * (2.0 * s * s + 4.0 * ca * cb);
+  }
   PFH_HD static constexpr int in(int) { return 0; }
   PFH_HD static constexpr int out(int) { return 1; }
   double ca, cb, rho, kappa, Mob;
@@ -63,6 +68,11 @@ struct ProbCH {
 // ---------------- bench6 : CH + electrostatics, fields (c, mu, phi) ----------------
 struct ProbBench6 {
   static constexpr int NF = 3, NIN = 1, NOUT = 1;
+  static constexpr bool QUARTIC = true;
+  PFH_HD void jac_poly(double& a2, double& a1, double& a0) const {
+    const double s = ca + cb;
+    a2 = -12.0 * rho; a1 = 12.0 * rho * s; a0 = -rho * (2.0 * s * s + 4.0 * ca * cb);
+  }
   PFH_HD static constexpr int in(int) { return 0; }
   PFH_HD static constexpr int out(int) { return 1; }
   double ca, cb, rho, kappa, Mob, k, eps;
@@ -108,6 +118,7 @@ struct ProbBench6 {
 // ---------------- bench3 : dendrite (isotropic as coded), fields (U, phi) ----------------
 struct ProbBench3 {
   static constexpr int NF = 2, NIN = 2, NOUT = 2;
+  static constexpr bool QUARTIC = false;
   PFH_HD static constexpr int in(int i) { return i; }
   PFH_HD static constexpr int out(int o) { return o; }
   double W, tau, D, lam, area;
@@ -153,6 +164,7 @@ struct ProbBench3 {
 // ---------------- bench2 : Ostwald ripening, fields (c, mu, eta1..4) ----------------
 struct ProbBench2 {
   static constexpr int NF = 6, NIN = 5, NOUT = 5;
+  static constexpr bool QUARTIC = false;
   PFH_HD static constexpr int in(int i) { return i == 0 ? 0 : i + 1; }   // c, eta1..4
   PFH_HD static constexpr int out(int o) { return o + 1; }               // mu, eta1..4
   double ca, cb, rho2, kc, ke, Mob, w, alpha, L;

@@ -105,8 +105,7 @@ void cheb_solve(pfh_ctx* c, double am, double ak, double lmin, double lmax, int 
   double* prev = (cur == target) ? tmp : target;
   k_cheb_first(c, am, ak, cf[0].b, r, cur);
   for (int k = 1; k < nsweeps; ++k) {
-    if (k == 1) v_zero(c, prev, c->n_owned);
-    k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev);
+    k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev, k == 1);
     std::swap(cur, prev);
   }
   PFH_CHECK(cur == target, "internal: chebyshev ping-pong parity");
@@ -211,12 +210,18 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
       v_copy(c, z + n, S0, n);  // block upper-triangular: dmu = t
     } else {
       // dmu = t + M^-1 (kappa K + M_f'') dc = t - M^-1 [J (dc, 0, ..)]_mu
-      double *PX = c->W2, *PY = c->R;  // free during a linear solve (see gmres below)
-      v_zero(c, PX, c->nf * n);
-      v_copy(c, PX, z, n);
-      s_jac_apply(c, PX, PY);
-      cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, PY + n, S2, S1);
-      v_axpby(c, 1.0, S0, -1.0, S2, z + n, n);
+      if (k_ch_crow(c, c->jac_point, scalar_ref(c, z), S2)) {
+        // fused (mu, c) block apply: reads c and dc only, writes the mu row only
+        cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, S2, S3, S1);
+        v_axpby(c, 1.0, S0, -1.0, S3, z + n, n);
+      } else {
+        double *PX = c->W2, *PY = c->R;  // free during a linear solve (see gmres below)
+        v_zero(c, PX, c->nf * n);
+        v_copy(c, PX, z, n);
+        s_jac_apply(c, PX, PY);
+        cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, PY + n, S2, S1);
+        v_axpby(c, 1.0, S0, -1.0, S2, z + n, n);
+      }
     }
   }
   for (int k = 0; k < L.n_spd; ++k) {

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(BX* BY) k3_op(P prob, Mesh3 m, LinCoefs L, Fie
 // MODE 0: out = s*add + A in ; MODE 1: z = b Dinv r ; MODE 2: zprev <- z + a (z - zprev) + b Dinv (r - A z)
 template <int MODE>
 __global__ void __launch_bounds__(BX* BY) k3_scalar(Mesh3 m, double am, double ak, double a, double b, FieldRef in,
-                                                    const double* __restrict__ r, double* __restrict__ out) {
+                                                    const double* __restrict__ r, double* __restrict__ out, bool out_is_zero) {
   const int ix = blockIdx.x * BX + threadIdx.x, iy = blockIdx.y * BY + threadIdx.y;
   if (ix >= m.nxv || iy >= m.nyv) return;
   const int z_end = min(m.nzl, (int)(blockIdx.z + 1) * ZCHUNK);
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(BX* BY) k3_scalar(Mesh3 m, double am, double a
       double Av, d, self;
       vtx::scalar_op3(m, am, ak, in, ix, iy, zl, Av, d, self);
       if (MODE == 0) out[i] = (a != 0.0 ? a * r[i] : 0.0) + Av;
-      else out[i] = self + a * (self - out[i]) + (b / d) * (r[i] - Av);
+      else out[i] = self + a * (self - (out_is_zero ? 0.0 : out[i])) + (b / d) * (r[i] - Av);
     }
   }
 }
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(TPB) k2_op(P prob, Mesh2 m, LinCoefs L, const 
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k2_scalar(Mesh2 m, double am, double ak, double a, double b,
                                                  const double* __restrict__ in, const double* __restrict__ r,
-                                                 double* __restrict__ out) {
+                                                 double* __restrict__ out, bool out_is_zero) {
   const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
   if (i >= m.n_owned) return;
   if (MODE == 1) {
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(TPB) k2_scalar(Mesh2 m, double am, double ak, 
     double Av, d, self;
     vtx::scalar_op2(m, am, ak, in, i, Av, d, self);
     if (MODE == 0) out[i] = (a != 0.0 ? a * r[i] : 0.0) + Av;
-    else out[i] = self + a * (self - out[i]) + (b / d) * (r[i] - Av);
+    else out[i] = self + a * (self - (out_is_zero ? 0.0 : out[i])) + (b / d) * (r[i] - Av);
   }
 }
 
@@ -289,33 +289,41 @@ void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
   PFH_CUDA(cudaGetLastError());
 }
 
+bool k_ch_crow(pfh_ctx* c, const double* ulin, FieldRef xc, double* out) {
+  if (c->dim != 3 || c->prob.id != PFH_PROBLEM_CH || !pfh_tma_ok(c)) return false;
+  const LinCoefs L = pfh_lin_coefs(c, c->dt);
+  ProfScope ps(c, T_JAC_APPLY, 24.0 * c->n_owned);
+  return k3_ch_crow_tma_launch(c, L, ulin, xc, out);
+}
+
 void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out) {
   ProfScope ps(c, T_LIN_APPLY, 8.0 * (s != 0.0 ? 3 : 2) * c->n_owned);
   PFH_CHECK(s == 0.0 || add != nullptr, "k_lin_apply: add operand missing");
-  if (c->dim == 3 && k3_scalar_tma_launch(c, 0, am, ak, s, 0.0, in, add, out)) return;
+  if (c->dim == 3 && k3_scalar_tma_launch(c, 0, am, ak, s, 0.0, in, add, out, false)) return;
   if (c->dim == 3)
-    k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out);
+    k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false);
   else
-    k2_scalar<0><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, s, 0.0, in.p, add, out);
+    k2_scalar<0><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, s, 0.0, in.p, add, out, false);
   PFH_CUDA(cudaGetLastError());
 }
 
 void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z) {
   ProfScope ps(c, T_CHEB_FIRST, 16.0 * c->n_owned);
   if (c->dim == 3)
-    k3_scalar<1><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z);
+    k3_scalar<1><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z, false);
   else
-    k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z);
+    k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z, false);
   PFH_CUDA(cudaGetLastError());
 }
 
-void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev) {
-  ProfScope ps(c, T_CHEB_SWEEP, 32.0 * c->n_owned);
-  if (c->dim == 3 && k3_scalar_tma_launch(c, 2, am, ak, a, b, z, r, zprev)) return;
+void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev,
+                  bool zprev_is_zero) {
+  ProfScope ps(c, T_CHEB_SWEEP, (zprev_is_zero ? 24.0 : 32.0) * c->n_owned);
+  if (c->dim == 3 && k3_scalar_tma_launch(c, 2, am, ak, a, b, z, r, zprev, zprev_is_zero)) return;
   if (c->dim == 3)
-    k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev);
+    k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero);
   else
-    k2_scalar<2><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, a, b, z.p, r, zprev);
+    k2_scalar<2><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, a, b, z.p, r, zprev, zprev_is_zero);
   PFH_CUDA(cudaGetLastError());
 }
 

@@ -72,10 +72,11 @@ struct Coef15 {
 };
 
 template <int MODE, int TX, int TY, int RY, int NS>
-__global__ void __launch_bounds__(TX*(TY / RY))
+__global__ void __launch_bounds__(TX*(TY / RY), 4)
     k3_scalar_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_lo,
                   const __grid_constant__ CUtensorMap tm_hi, Mesh3 m, int has_lo, int has_hi, int zchunk, double am, double ak,
-                  Coef15 cI, double a, double b, const double* __restrict__ r, double* __restrict__ out) {
+                  Coef15 cI, double a, double b, double bdI, const double* __restrict__ r, double* __restrict__ out,
+                  int out_is_zero) {
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2: the TMA box start (x0-2) must be 16-byte aligned
   constexpr int STAGE_BYTES = W * H * 8;
   constexpr int STAGE_STRIDE = round_up(STAGE_BYTES, 128);
@@ -115,7 +116,17 @@ __global__ void __launch_bounds__(TX*(TY / RY))
 
   const int ix = x0 + threadIdx.x;
   const int txt = ix == 0 ? 0 : (ix == m.nxv - 1 ? 2 : 1);
-  const double dI = cI.c[0];
+  // per-thread row state: validity, boundary type in x-y, running global index (advanced by nxy per plane)
+  bool valid[RY];
+  int txy[RY];
+  long long idx[RY];
+#pragma unroll
+  for (int rr = 0; rr < RY; ++rr) {
+    const int iy = y0 + threadIdx.y + rr * ROWS;
+    valid[rr] = ix < m.nxv && iy < m.nyv;
+    txy[rr] = (iy == 0 ? 0 : (iy == m.nyv - 1 ? 2 : 1)) * 3 + txt;
+    idx[rr] = (long long)zb * m.nxy + (long long)iy * m.nxv + ix;
+  }
 
   for (int k = 0; k < ze - zb; ++k) {
     const int zl = zb + k;
@@ -124,18 +135,13 @@ __global__ void __launch_bounds__(TX*(TY / RY))
 
     // pointwise operands first, so their latency overlaps the wait on the TMA planes
     double rv[RY], ov[RY];
-    bool valid[RY];
-    long long idx[RY];
 #pragma unroll
     for (int rr = 0; rr < RY; ++rr) {
-      const int iy = y0 + threadIdx.y + rr * ROWS;
-      valid[rr] = ix < m.nxv && iy < m.nyv;
-      idx[rr] = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
       rv[rr] = 0.0;
       ov[rr] = 0.0;
       if (valid[rr]) {
         if (MODE == 2 || a != 0.0) rv[rr] = __ldg(r + idx[rr]);
-        if (MODE == 2) ov[rr] = out[idx[rr]];
+        if (MODE == 2 && !out_is_zero) ov[rr] = out[idx[rr]];
       }
     }
     if (k == 0) {
@@ -153,31 +159,31 @@ __global__ void __launch_bounds__(TX*(TY / RY))
     for (int rr = 0; rr < RY; ++rr) {
       if (!valid[rr]) continue;
       const int ly = threadIdx.y + rr * ROWS;
-      const int iy = y0 + ly;
       const int c = (ly + 1) * W + threadIdx.x + 2;
       double v[PFH_NOFF3];
       v[0] = S1[c]; v[1] = S1[c + 1]; v[2] = S1[c - 1]; v[3] = S1[c + W]; v[4] = S1[c - W];
       v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
       v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
       v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
-      const int tyt = iy == 0 ? 0 : (iy == m.nyv - 1 ? 2 : 1);
-      const int type = tzt * 9 + tyt * 3 + txt;
-      double Av = 0.0, d;
+      const int type = tzt * 9 + txy[rr];
+      double Av = 0.0, bd;
       if (type == 13) {
 #pragma unroll
         for (int o = 0; o < PFH_NOFF3; ++o) Av += cI.c[o] * v[o];
-        d = dI;
+        bd = bdI;
       } else {
         vtx::Row3 row;
         vtx::get_row3(m, type, row);
         double Ms, Ks;
         vtx::mk_sums3(row, v, Ms, Ks);
         Av = am * Ms + ak * Ks;
-        d = am * row.m[0] + ak * row.k[0];
+        bd = MODE == 2 ? b / (am * row.m[0] + ak * row.k[0]) : 0.0;
       }
       if (MODE == 0) out[idx[rr]] = a * rv[rr] + Av;
-      else out[idx[rr]] = v[0] + a * (v[0] - ov[rr]) + (b / d) * (rv[rr] - Av);
+      else out[idx[rr]] = v[0] + a * (v[0] - ov[rr]) + bd * (rv[rr] - Av);
     }
+#pragma unroll
+    for (int rr = 0; rr < RY; ++rr) idx[rr] += m.nxy;
   }
 }
 
@@ -189,11 +195,15 @@ struct MapSet {
   CUtensorMap main[N], lo[N], hi[N];
 };
 
-template <class P, int TX, int TY, int NT, int NS>
-__global__ void __launch_bounds__(NT)
-    k3_jac_tma(const __grid_constant__ MapSet<P::NF + P::NIN> maps, P prob, Mesh3 m, LinCoefs L, int has_lo, int has_hi,
-               int zchunk, double* __restrict__ out) {
-  constexpr int NFLD = P::NF + P::NIN;  // ring-buffered fields: x_0..x_{NF-1}, then u_{in(0)}..u_{in(NIN-1)}
+// CROW = false: y = J(u) x (all NF rows).  CROW = true: only the nonlinear row, from its own
+// nonlinear column: out = (Mc[o][i] M + Kc[o][i] K) x_i + N'[x_i], o = P::out(0), i = P::in(0)
+// (the (kappa K + M_f'') block of the Cahn-Hilliard Jacobian that the Schur preconditioner applies).
+template <class P, bool CROW, int TX, int TY, int NT, int NS>
+__global__ void __launch_bounds__(NT, 2)
+    k3_jac_tma(const __grid_constant__ MapSet<(CROW ? 1 : P::NF) + P::NIN> maps, P prob, Mesh3 m, LinCoefs L, int has_lo,
+               int has_hi, int zchunk, double* __restrict__ out) {
+  constexpr int NX = CROW ? 1 : P::NF;  // ring-buffered operand fields x, followed by the NIN linearisation fields u
+  constexpr int NFLD = NX + P::NIN;
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2 (16-byte aligned TMA box start)
   constexpr int STAGE_BYTES = W * H * 8;
   constexpr int STAGE_STRIDE = round_up(STAGE_BYTES, 128);
@@ -204,6 +214,7 @@ __global__ void __launch_bounds__(NT)
   double* contrib = reinterpret_cast<double*>(smem + NFLD * NS * STAGE_STRIDE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(contrib + P::NOUT * 8 * CPAD);
   auto stage = [&](int f, int p) { return reinterpret_cast<const double*>(smem + (f * NS + (p % NS)) * STAGE_STRIDE); };
+  auto xstage = [&](int field, int p) { return stage(CROW ? 0 : field, p); };  // operand field `field`
 
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
@@ -241,11 +252,13 @@ __global__ void __launch_bounds__(NT)
   const int vtx_x = tid % TX, vtx_y = tid / TX;
   const int ix = x0 + vtx_x, iy = y0 + vtx_y;
   const bool is_vertex = tid < TX * TY && ix < m.nxv && iy < m.nyv;
-  const int txt = ix == 0 ? 0 : (ix == m.nxv - 1 ? 2 : 1);
-  const int tyt = iy == 0 ? 0 : (iy == m.nyv - 1 ? 2 : 1);
+  const int txy = (iy == 0 ? 0 : (iy == m.nyv - 1 ? 2 : 1)) * 3 + (ix == 0 ? 0 : (ix == m.nxv - 1 ? 2 : 1));
   double acc_hi[P::NOUT];
 #pragma unroll
   for (int o = 0; o < P::NOUT; ++o) acc_hi[o] = 0.0;
+  double a2 = 0.0, a1 = 0.0, a0 = 0.0;
+  if constexpr (P::QUARTIC) prob.jac_poly(a2, a1, a0);
+  const elem::QuarticJac qj(a2, a1, a0, m.detJ);
 
   // iteration `it` handles cube layer l = zb-1+it (between planes l and l+1) and writes plane l (it >= 1)
   for (int it = 0; it <= ze - zb; ++it) {
@@ -253,9 +266,9 @@ __global__ void __launch_bounds__(NT)
     __syncthreads();  // plane it-2 and the previous contributions are no longer needed
     if (tid == 0 && it + NS - 2 < nplanes) issue(it + NS - 2);
     if (it == 0) mbar_wait(&bars[0], 0);
-    if (it + 1 < nplanes) mbar_wait(&bars[(it + 1) % NS], ((it + 1) / NS) & 1);
+    mbar_wait(&bars[(it + 1) % NS], ((it + 1) / NS) & 1);
 
-    // ---- cube phase ----
+    // ---- cube phase: one cube (6 tets) per thread, quadrature evaluated once per tet ----
     const int gl = m.z0 + l;
     for (int q = tid; q < NCUBE; q += NT) {
       const int qx = q % CW, qy = q / CW;
@@ -270,10 +283,10 @@ __global__ void __launch_bounds__(NT)
         const int base = qy * W + qx + 1;
 #pragma unroll
         for (int f = 0; f < P::NIN; ++f) {
-          const double* u0 = stage(P::NF + f, it);
-          const double* u1 = stage(P::NF + f, it + 1);
-          const double* xa = stage(P::in(f), it);
-          const double* xb = stage(P::in(f), it + 1);
+          const double* u0 = stage(NX + f, it);
+          const double* u1 = stage(NX + f, it + 1);
+          const double* xa = xstage(P::in(f), it);
+          const double* xb = xstage(P::in(f), it + 1);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const int off = base + (kk >> 1) * W + (kk & 1);
@@ -283,7 +296,8 @@ __global__ void __launch_bounds__(NT)
             x[f][kk + 4] = xb[off];
           }
         }
-        elem::cube_load<P, true>(prob, u, x, m.detJ, o8);
+        if constexpr (P::QUARTIC) elem::cube_jac_quartic(qj, u[0], x[0], o8[0]);
+        else elem::cube_load<P, true>(prob, u, x, m.detJ, o8);
       }
 #pragma unroll
       for (int o = 0; o < P::NOUT; ++o)
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(NT)
     }
     __syncthreads();
 
-    // ---- vertex phase ----
+    // ---- vertex phase: gather the 8 cube contributions, add the linear 15-point part, store plane l ----
     if (is_vertex) {
       double lo[P::NOUT], hi[P::NOUT];
 #pragma unroll
@@ -309,14 +323,13 @@ __global__ void __launch_bounds__(NT)
       }
       if (it >= 1) {
         const int gz = m.z0 + l;
-        const int tzt = gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1);
-        const int type = tzt * 9 + tyt * 3 + txt;
+        const int type = (gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1)) * 9 + txy;
         vtx::Row3 row;
         vtx::get_row3(m, type, row);
         const int c = (vtx_y + 1) * W + vtx_x + 2;
-        double Ms[P::NF], Ks[P::NF];
+        double Ms[NX], Ks[NX];
 #pragma unroll
-        for (int f = 0; f < P::NF; ++f) {
+        for (int f = 0; f < NX; ++f) {
           const double* S0 = stage(f, it - 1);
           const double* S1 = stage(f, it);
           const double* S2 = stage(f, it + 1);
@@ -327,19 +340,23 @@ __global__ void __launch_bounds__(NT)
           v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
           vtx::mk_sums3(row, v, Ms[f], Ks[f]);
         }
-        double y[P::NF];
-#pragma unroll
-        for (int aa = 0; aa < P::NF; ++aa) {
-          double s = 0.0;
-#pragma unroll
-          for (int bb = 0; bb < P::NF; ++bb) s += L.Mc[aa][bb] * Ms[bb] + L.Kc[aa][bb] * Ks[bb];
-          y[aa] = s;
-        }
-#pragma unroll
-        for (int o = 0; o < P::NOUT; ++o) y[P::out(o)] += acc_hi[o] + lo[o];
         const long long i = (long long)l * m.nxy + (long long)iy * m.nxv + ix;
+        if (CROW) {
+          out[i] = L.Mc[P::out(0)][P::in(0)] * Ms[0] + L.Kc[P::out(0)][P::in(0)] * Ks[0] + acc_hi[0] + lo[0];
+        } else {
+          double y[P::NF];
 #pragma unroll
-        for (int aa = 0; aa < P::NF; ++aa) out[aa * m.n_owned + i] = y[aa];
+          for (int aa = 0; aa < P::NF; ++aa) {
+            double s = 0.0;
+#pragma unroll
+            for (int bb = 0; bb < P::NF; ++bb) s += L.Mc[aa][bb] * Ms[bb % NX] + L.Kc[aa][bb] * Ks[bb % NX];
+            y[aa] = s;
+          }
+#pragma unroll
+          for (int o = 0; o < P::NOUT; ++o) y[P::out(o)] += acc_hi[o] + lo[o];
+#pragma unroll
+          for (int aa = 0; aa < P::NF; ++aa) out[aa * m.n_owned + i] = y[aa];
+        }
       }
 #pragma unroll
       for (int o = 0; o < P::NOUT; ++o) acc_hi[o] = hi[o];
@@ -380,7 +397,7 @@ CUtensorMap make_map(const double* ptr, int nxv, int nyv, int nz, int bx, int by
   return map;
 }
 
-constexpr int S_TX = 64, S_TY = 8, S_RY = 2, S_NS = 5, S_ZCH = 32;
+constexpr int S_TX = 64, S_TY = 8, S_RY = 2, S_NS = 6, S_ZCH = 32;
 constexpr int J_TX = 32, J_TY = 8, J_NT = 320, J_NS = 4, J_ZCH = 32;
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -394,7 +411,7 @@ bool pfh_tma_ok(const pfh_ctx* c) {
 // MODE 0 (lin_apply) and MODE 2 (Chebyshev sweep) through the TMA kernel; returns false if the
 // operands do not qualify (caller falls back to the gather kernel)
 bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
-                          double* out) {
+                          double* out, bool out_is_zero) {
   if (!pfh_tma_ok(c) || !aligned16(in.p)) return false;
   const Mesh3& m = c->m3;
   const bool lo = in.glo != nullptr && c->cfg.rank > 0, hi = in.ghi != nullptr && c->cfg.rank < c->cfg.nranks - 1;
@@ -409,9 +426,9 @@ bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, 
   constexpr int stage = round_up((S_TX + 4) * (S_TY + 2) * 8, 128);
   const size_t smem = S_NS * stage + S_NS * sizeof(uint64_t);
   if (mode == 0)
-    k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, am, ak, cI, a, b, r, out);
+    k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, am, ak, cI, a, b, 0.0, r, out, 0);
   else
-    k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, am, ak, cI, a, b, r, out);
+    k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, am, ak, cI, a, b, b / cI.c[0], r, out, out_is_zero ? 1 : 0);
   PFH_CUDA(cudaGetLastError());
   return true;
 }
@@ -437,7 +454,7 @@ bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const 
   constexpr int stage = round_up((J_TX + 4) * (J_TY + 2) * 8, 128);
   constexpr int ncube = (J_TX + 1) * (J_TY + 1);
   constexpr size_t smem = (size_t)(P::NF + P::NIN) * J_NS * stage + (size_t)P::NOUT * 8 * (ncube | 1) * 8 + J_NS * sizeof(uint64_t);
-  auto kern = k3_jac_tma<P, J_TX, J_TY, J_NT, J_NS>;
+  auto kern = k3_jac_tma<P, false, J_TX, J_TY, J_NT, J_NS>;
   static bool attr_set = false;
   if (!attr_set) {
     PFH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -445,6 +462,37 @@ bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const 
   }
   const dim3 grid((m.nxv + J_TX - 1) / J_TX, (m.nyv + J_TY - 1) / J_TY, (m.nzl + J_ZCH - 1) / J_ZCH);
   kern<<<grid, J_NT, smem, c->stream>>>(maps, P(c->prob), m, L, lo, hi, J_ZCH, y);
+  PFH_CUDA(cudaGetLastError());
+  return true;
+}
+
+// out = (Mc[mu][c] M + Kc[mu][c] K) xc + M_{g'}(ulin) xc : the (mu, c) block of the Cahn-Hilliard Jacobian applied to a
+// scalar field (ghosts of xc in `xc.glo/ghi`, of ulin in gU_*)
+bool k3_ch_crow_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, FieldRef xc, double* out) {
+  if (!pfh_tma_ok(c) || c->prob.id != PFH_PROBLEM_CH || !aligned16(ulin) || !aligned16(xc.p)) return false;
+  using P = ProbCH;
+  const Mesh3& m = c->m3;
+  if ((m.n_owned & 1) || (c->nplane & 1)) return false;
+  const bool lo = c->nplane > 0 && c->cfg.rank > 0, hi = c->nplane > 0 && c->cfg.rank < c->cfg.nranks - 1;
+  MapSet<1 + P::NIN> maps;
+  maps.main[0] = make_map(xc.p, m.nxv, m.nyv, m.nzl, J_TX + 4, J_TY + 2);
+  maps.lo[0] = lo ? make_map(xc.glo, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[0];
+  maps.hi[0] = hi ? make_map(xc.ghi, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[0];
+  const int fld = P::in(0);
+  maps.main[1] = make_map(ulin + (long long)fld * m.n_owned, m.nxv, m.nyv, m.nzl, J_TX + 4, J_TY + 2);
+  maps.lo[1] = lo ? make_map(c->gU_lo + (long long)fld * c->nplane, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[1];
+  maps.hi[1] = hi ? make_map(c->gU_hi + (long long)fld * c->nplane, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[1];
+  constexpr int stage = round_up((J_TX + 4) * (J_TY + 2) * 8, 128);
+  constexpr int ncube = (J_TX + 1) * (J_TY + 1);
+  constexpr size_t smem = (size_t)(1 + P::NIN) * J_NS * stage + (size_t)P::NOUT * 8 * (ncube | 1) * 8 + J_NS * sizeof(uint64_t);
+  auto kern = k3_jac_tma<P, true, J_TX, J_TY, J_NT, J_NS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const dim3 grid((m.nxv + J_TX - 1) / J_TX, (m.nyv + J_TY - 1) / J_TY, (m.nzl + J_ZCH - 1) / J_ZCH);
+  kern<<<grid, J_NT, smem, c->stream>>>(maps, P(c->prob), m, L, lo, hi, J_ZCH, out);
   PFH_CUDA(cudaGetLastError());
   return true;
 }

@@ -83,3 +83,16 @@ def test_slab_with_ghost_planes_equals_global():
         assert np.abs(Y - Yg[:, sl]).max() < 1e-12 * np.abs(Yg).max()
         Etot += emul.run(3, 1, list(ncell), list(length), params, 0.3, 2, U=U[:, sl], **kw)[0]
     assert abs(Etot / D.energy(U) - 1) < 1e-13
+
+
+def test_low_flop_cube_jacobian_routine():
+    """elem::cube_jac_quartic (folded-constant form used by the TMA J.v kernel) == int phi_i g'(c_h) x_h of the oracle."""
+    rng = np.random.default_rng(4)
+    ncell, length = (4, 5, 3), (8.0, 7.5, 6.0)
+    D = discretization("b13d", ncell, length)
+    U = D.prob.ic(D.mesh) + 0.1 * rng.standard_normal((2, D.nv))
+    X = rng.standard_normal((2, D.nv))
+    got = emul.run(3, 1, list(ncell), list(length), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, 5, U=U, X=X, nf=2)
+    dg = D.prob.dg(D.V.at_quad(U))
+    ref = D.V.weighted_mass(dg[1, 0]) @ X[0]
+    assert rel_max(got, ref) < 1e-13
