@@ -310,9 +310,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=512, help="vertices per edge of the synthetic 3-D grid")
     ap.add_argument("--restart", type=int, default=30)
-    ap.add_argument("--pc-variant", type=int, default=0)
+    ap.add_argument("--pc-variant", type=int, default=1)
     ap.add_argument("--sweeps-mass", type=int, default=3)
-    ap.add_argument("--sweeps-shifted", type=int, default=6)
+    ap.add_argument("--sweeps-shifted", type=int, default=5)
     ap.add_argument("--cpu-grid", type=int, default=64, help="sample grid of the cpu_baseline leg")
     ap.add_argument("--ref-grid", type=int, default=64, help="sample grid of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")

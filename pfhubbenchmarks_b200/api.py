@@ -1,0 +1,222 @@
+"""The reference drivers' Python surface on top of libpfh_b200.so.
+
+The reference scripts (dolfin/bench{1,2,3,6}.py, b13d.py) are module-level programs that build
+`mesh, W, w, w0, dt, F, J, bcs`, then
+
+    problem = df.NonlinearVariationalProblem(F, w, bcs, J)          # bench1.py:76
+    solver  = df.NonlinearVariationalSolver(problem)                # bench1.py:77
+    solver.parameters['nonlinear_solver'] = 'snes'                  # bench1.py:82
+    nlparams = solver.parameters['snes_solver']; nlparams[...] = ...   # bench1.py:83-110
+    niters, converged = solver.solve()                              # bench1.py:162
+
+and loop with the adaptive-dt rule.  This module keeps those object names, parameter keys and call
+semantics (solve() mutates w in place from its current value, reads w0 and the current dt, returns
+(niters, converged) and never raises on non-convergence).  What it does NOT re-implement is UFL:
+the weak form is selected by benchmark name (the four forms the reference ships, pfbase.py:361-460)
+and its coefficients are passed as keyword arguments named as in the reference scripts.
+"""
+import warnings
+
+import numpy as np
+
+from . import _lib, engine
+
+DOLFIN_EPS = 3.0e-16
+
+
+class Point:
+    def __init__(self, *xyz):
+        self.x = tuple(float(v) for v in xyz)
+
+
+class Constant:
+    """df.Constant: float(dt), dt.assign(x)  (bench1.py:29,171,180-183)"""
+
+    def __init__(self, value):
+        self._v = float(value)
+
+    def assign(self, value):
+        self._v = float(value)
+
+    def __float__(self):
+        return self._v
+
+    def __repr__(self):
+        return "Constant(%r)" % self._v
+
+
+class Mesh:
+    def __init__(self, kind, ncell, length):
+        self.kind, self.ncell, self.length = kind, tuple(int(n) for n in ncell), tuple(float(v) for v in length)
+
+    def mpi_comm(self):
+        return None
+
+
+def RectangleMesh(p0, p1, nx, ny, diagonal="crossed"):
+    """df.RectangleMesh(Point, Point, Nx, Ny, 'crossed')  (bench1.py:21-23). Only the crossed split the drivers use."""
+    if diagonal != "crossed":
+        raise NotImplementedError("only the 'crossed' diagonal of the reference drivers is supported")
+    if any(abs(v) > 0 for v in p0.x):
+        raise NotImplementedError("meshes start at the origin in all reference drivers")
+    return Mesh("crossed2d", (nx, ny), p1.x[:2])
+
+
+def BoxMesh(p0, p1, nx, ny, nz):
+    """df.BoxMesh(Point, Point, Nx, Ny, Nz)  (b13d.py:24-26)."""
+    if any(abs(v) > 0 for v in p0.x):
+        raise NotImplementedError("meshes start at the origin in all reference drivers")
+    return Mesh("kuhn3d", (nx, ny, nz), p1.x[:3])
+
+
+class MPI:
+    """df.MPI.rank(mesh.mpi_comm()) guards (bench1.py:150): rank of this process in the torch.distributed job."""
+
+    @staticmethod
+    def rank(_comm=None):
+        try:
+            import torch.distributed as dist
+            return dist.get_rank() if dist.is_initialized() else 0
+        except Exception:
+            return 0
+
+
+class Function:
+    """df.Function on the mixed space: a fp64 device vector [field0 | field1 | ...] owned by torch."""
+
+    def __init__(self, problem):
+        self._p = problem
+        self.tensor = problem.ctx.new_vector()
+
+    def assign(self, other):                      # w0.assign(w), w.assign(w0)  (bench1.py:158,173)
+        self.tensor.copy_(other.tensor)
+
+    def interpolate(self, ic):                    # w.interpolate(w_ic)  (bench1.py:134-135)
+        self._p.ctx.initial_condition(ic.args, out=self.tensor)
+
+    def split(self):                              # c, _ = w.split()  (bench1.py:188)
+        return self._p.ctx.fields(self.tensor)
+
+    def vector(self):
+        return self.tensor
+
+    def to_numpy(self):
+        return self.tensor.cpu().numpy().reshape(self._p.ctx.nf, -1)
+
+
+class _IC:
+    def __init__(self, *args, **kwargs):
+        self.args = [float(a) for a in args]
+
+
+class InitialConditionsBench1(_IC):   # pfbase.py:177-193
+    pass
+
+
+class InitialConditionsBench2(_IC):   # pfbase.py:262-291
+    pass
+
+
+class InitialConditionsBench3(_IC):   # pfbase.py:293-320
+    pass
+
+
+class InitialConditionsBench6(_IC):   # pfbase.py:322-339
+    pass
+
+
+class NonlinearVariationalProblem:
+    """Stands in for `df.NonlinearVariationalProblem(F, w, bcs, J)`.  F and J are implied by `benchmark`
+    ('bench1', 'b13d', 'bench2', 'bench3', 'bench6') and its coefficients; dt is the mutable Constant the
+    time loop re-assigns.  `device`, `rank`, `nranks`, `nccl_id` place the problem (z-slabs for 3-D)."""
+
+    def __init__(self, benchmark, mesh, dt, params=None, device=0, rank=0, nranks=1, nccl_id=None, krylov_basis=30):
+        self.benchmark, self.mesh, self.dt = benchmark, mesh, dt
+        self.ctx = engine.Context(benchmark, mesh.ncell, mesh.length, params=params, device=device, rank=rank,
+                                  nranks=nranks, nccl_id=nccl_id, krylov_basis=krylov_basis)
+        self.w, self.w0 = Function(self), Function(self)
+
+
+class _Params(dict):
+    """Parameter tree with the reference's keys; unknown keys warn instead of raising (dolfin would raise)."""
+
+    def __init__(self, known, **kw):
+        super().__init__(**kw)
+        self._known = set(known) | set(kw)
+
+    def __setitem__(self, k, v):
+        if k not in self._known:
+            warnings.warn("unknown solver parameter %r ignored" % (k,))
+        super().__setitem__(k, v)
+
+
+_LINE_SEARCH = {"basic": 0}
+
+
+class NonlinearVariationalSolver:
+    def __init__(self, problem):
+        self.problem = problem
+        krylov = _Params(["maximum_iterations", "error_on_nonconvergence", "monitor_convergence", "relative_tolerance",
+                          "absolute_tolerance", "restart"],
+                         maximum_iterations=1000, relative_tolerance=1e-5, absolute_tolerance=1e-50, restart=30,
+                         error_on_nonconvergence=False, monitor_convergence=False)
+        snes = _Params(["report", "error_on_nonconvergence", "absolute_tolerance", "relative_tolerance",
+                        "solution_tolerance", "maximum_iterations", "line_search", "linear_solver", "preconditioner",
+                        "krylov_solver", "method"],
+                       report=True, error_on_nonconvergence=False, absolute_tolerance=1e-10, relative_tolerance=1e-9,
+                       solution_tolerance=1e-16, maximum_iterations=50, line_search="basic", linear_solver="gmres",
+                       preconditioner="schur_chebyshev", krylov_solver=krylov)
+        self.parameters = _Params(["nonlinear_solver", "snes_solver", "newton_solver"], nonlinear_solver="snes",
+                                  snes_solver=snes, newton_solver=snes)
+        self.last_report = None
+
+    def _opts(self):
+        p = self.parameters["snes_solver"]
+        k = p["krylov_solver"]
+        ls = p["line_search"]
+        if ls not in _LINE_SEARCH:
+            warnings.warn("line_search %r is not implemented; using 'basic' (full Newton step)" % (ls,))
+        if p["linear_solver"] not in ("gmres", "default"):
+            warnings.warn("linear_solver %r is not implemented; using gmres" % (p["linear_solver"],))
+        pc = {"schur_chebyshev": 0, "sor": 0, "default": 0, "jacobi": 1, "none": 2}.get(p["preconditioner"])
+        if pc is None:
+            warnings.warn("preconditioner %r is not implemented; using the Schur/Chebyshev preconditioner" % (p["preconditioner"],))
+            pc = 0
+        return _lib.default_opts(
+            absolute_tolerance=float(p["absolute_tolerance"]), relative_tolerance=float(p["relative_tolerance"]),
+            solution_tolerance=float(p["solution_tolerance"]), maximum_iterations=int(p["maximum_iterations"]),
+            krylov_rtol=float(k["relative_tolerance"]), krylov_atol=float(k["absolute_tolerance"]),
+            krylov_maximum_iterations=int(k["maximum_iterations"]),
+            krylov_restart=min(int(k["restart"]), 30), preconditioner=pc, verbose=0)
+
+    def solve(self):
+        """niters, converged = solver.solve()  (bench1.py:162). In place on problem.w; never raises on non-convergence
+        unless error_on_nonconvergence is set (the drivers clear it, bench1.py:86)."""
+        pr = self.problem
+        pr.ctx.dt = float(pr.dt)
+        rep = pr.ctx.newton_solve(pr.w.tensor, pr.w0.tensor, opts=self._opts())
+        self.last_report = rep
+        if not rep["converged"] and self.parameters["snes_solver"]["error_on_nonconvergence"]:
+            raise RuntimeError("Newton solver did not converge (reason %d)" % rep["reason"])
+        return rep["niters"], bool(rep["converged"])
+
+
+def total_free_energy(problem, w=None):
+    """df.assemble(f_chem*dx + kappa/2*inner(grad(c), grad(c))*dx) and its bench2/3/6 variants
+    (bench1.py:124-125, bench2.py:187-194, bench3.py:162-167, bench6.py:158-165)."""
+    return problem.ctx.energy((w or problem.w).tensor)[0]
+
+
+def total_solute(problem, w=None):
+    """df.assemble(c*dx) (bench1.py:121-122); bench3: solid_fraction = assemble(0.5*(phi+1)*dx)/(Lx*Ly) (bench3.py:169-170)."""
+    return problem.ctx.energy((w or problem.w).tensor)[1]
+
+
+def diagnostics(problem, w=None):
+    """Both reductions from one fused kernel launch."""
+    return problem.ctx.energy((w or problem.w).tensor)
+
+
+def write_csv(path, rows, header):
+    """np.savetxt(..., fmt='%1.10f', header=..., delimiter=',', comments='')  (bench1.py:210-217): byte-compatible CSV."""
+    np.savetxt(path, np.array(rows), fmt="%1.10f", header=header, delimiter=",", comments="")

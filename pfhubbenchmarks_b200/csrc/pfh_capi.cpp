@@ -80,9 +80,9 @@ void pfh_default_solver_opts(pfh_solver_opts* o) {
   o->krylov_maximum_iterations = 1000;  // bench1.py:110
   o->krylov_restart = 30;               // PETSc GMRES default
   o->preconditioner = 0;
-  o->pc_variant = 0;
+  o->pc_variant = 1;        // block upper-triangular: best time-to-solution in the 256^3 sweep (profiles/r1_pc_sweep_256.txt)
   o->pc_sweeps_mass = 3;
-  o->pc_sweeps_shifted = 6;
+  o->pc_sweeps_shifted = 5;
   o->verbose = 0;
 }
 

@@ -165,6 +165,7 @@ struct pfh_ctx {
   double t_ms[PFH_N_TIMERS] = {0};
   double t_bytes[PFH_N_TIMERS] = {0};  // algorithmic bytes of the launches timed above
   long long t_n[PFH_N_TIMERS] = {0};
+  int scalar_bc = 0;    // 2-D scalar operators: 1 = Dirichlet (identity) rows on the corner vertices of x = 0 and x = Lx
   bool use_tma = true;  // 3-D fast path: TMA-staged kernels (pfh_stencil3_tma.cu); false = gather kernels only
 };
 
@@ -207,6 +208,7 @@ void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z);
 void k_energy(pfh_ctx* c, const double* u, double out[4]);  // includes final reduction + allreduce + D2H
 void k_initial_condition(pfh_ctx* c, const double* icp, int n, double* w);
 void k_dirichlet_fix(pfh_ctx* c, double* w);  // impose Dirichlet values on the iterate (bench6)
+void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst);  // dst = src on the Dirichlet vertices of a scalar field
 
 // ---- TMA-staged 3-D kernels (pfh_stencil3_tma.cu); return false when the operands do not qualify ----
 bool pfh_tma_ok(const pfh_ctx* c);

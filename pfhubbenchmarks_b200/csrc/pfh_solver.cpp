@@ -144,8 +144,7 @@ PcLayout pc_layout(const pfh_ctx* c) {
       break;
     case PFH_PROBLEM_BENCH6:
       L.has_ch = true; L.Mob = p[4]; L.kappa = p[3];
-      // phi row is -K phi + ...: precondition with -(eps_m M + K)^-1
-      L.n_spd = 1; L.spd_field[0] = 2; L.spd_am[0] = 1e-3; L.spd_ak[0] = 1.0; L.spd_sign[0] = -1.0;
+      // the Poisson row of phi is handled separately in s_precond_apply (Dirichlet rows, many sweeps)
       break;
     case PFH_PROBLEM_BENCH2:
       L.has_ch = true; L.Mob = p[5]; L.kappa = p[3];
@@ -193,7 +192,7 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
   }
   const PcLayout L = pc_layout(c);
   const int nM = o.pc_sweeps_mass > 0 ? o.pc_sweeps_mass : 3;
-  const int nA = o.pc_sweeps_shifted > 0 ? o.pc_sweeps_shifted : 6;
+  const int nA = o.pc_sweeps_shifted > 0 ? o.pc_sweeps_shifted : 5;
   if (L.has_ch) {
     const double dt = c->dt, alpha = c->pc_alpha;
     const double *r1 = r, *r2 = r + n;
@@ -232,8 +231,20 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
     if (L.spd_sign[k] < 0.0) v_scale(c, -1.0, z + f * n, z + f * n, n);
   }
   if (c->prob.id == PFH_PROBLEM_BENCH6) {
-    // Dirichlet rows of phi are identity rows of J: z = r there (k2_dirichlet writes values, so do it by hand)
-    // handled approximately by the Krylov solver; exactness is not needed in a preconditioner
+    // phi row of J: (k/eps) M dc - K dphi = r_phi, identity on the Dirichlet vertices (bench6.py:72-90).
+    // Block lower-triangular step: dphi = K_D^-1 ((k/eps) M dc - r_phi), K_D = K with Dirichlet rows, solved by
+    // Jacobi-Chebyshev with the analytic bounds of the Dirichlet/Neumann Laplacian on the crossed mesh
+    // (a multigrid cycle would do this in O(1) sweeps: "next" row N4).
+    const double k_eps = c->prob.p[5] / c->prob.p[6];
+    double *rhs = c->S[2], *tmp = c->S[1];
+    c->scalar_bc = 1;
+    v_scale(c, -1.0, r + 2 * n, c->S[0], n);                                        // -r_phi
+    k_lin_apply(c, k_eps, 0.0, FieldRef{z, nullptr, nullptr}, 1.0, c->S[0], rhs);  // (k/eps) M dc - r_phi (interior rows)
+    k_dirichlet_copy(c, r + 2 * n, rhs);                                            // identity rows: dphi = r_phi
+    const double pi = 3.14159265358979323846;
+    const double lmin = 0.5 * (pi / c->m2.nx) * (pi / c->m2.nx) / 8.0;
+    cheb_solve(c, 0.0, 1.0, lmin, 2.0, 240, rhs, z + 2 * n, tmp);
+    c->scalar_bc = 0;
   }
 }
 

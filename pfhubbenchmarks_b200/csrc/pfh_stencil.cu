@@ -127,9 +127,16 @@ __global__ void __launch_bounds__(TPB) k2_op(P prob, Mesh2 m, LinCoefs L, const 
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k2_scalar(Mesh2 m, double am, double ak, double a, double b,
                                                  const double* __restrict__ in, const double* __restrict__ r,
-                                                 double* __restrict__ out, bool out_is_zero) {
+                                                 double* __restrict__ out, bool out_is_zero, int bc) {
   const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
   if (i >= m.n_owned) return;
+  if (bc && i < m.ncorner) {  // Dirichlet rows (bench6 phi, bench6.py:77-90): identity row, value carried by r
+    const int ix = (int)(i % m.nxv);
+    if (ix == 0 || ix == m.nxv - 1) {
+      out[i] = r[i];
+      return;
+    }
+  }
   if (MODE == 1) {
     out[i] = b / vtx::scalar_diag2(m, am, ak, i) * r[i];
   } else {
@@ -208,6 +215,13 @@ __global__ void __launch_bounds__(TPB) k2_dirichlet(P prob, Mesh2 m, double* __r
     double val;
     if (prob.dirichlet(a, ix, iy, m.nx, iy * m.hy, val)) w[a * m.n_owned + i] = val;
   }
+}
+
+__global__ void __launch_bounds__(TPB) k2_dirichlet_copy(Mesh2 m, const double* __restrict__ src, double* __restrict__ dst) {
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= m.ncorner) return;
+  const int ix = (int)(i % m.nxv);
+  if (ix == 0 || ix == m.nxv - 1) dst[i] = src[i];
 }
 
 // -------- launch helpers --------
@@ -303,7 +317,7 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
   if (c->dim == 3)
     k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false);
   else
-    k2_scalar<0><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, s, 0.0, in.p, add, out, false);
+    k2_scalar<0><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, s, 0.0, in.p, add, out, false, c->scalar_bc);
   PFH_CUDA(cudaGetLastError());
 }
 
@@ -312,7 +326,7 @@ void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, d
   if (c->dim == 3)
     k3_scalar<1><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z, false);
   else
-    k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z, false);
+    k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z, false, c->scalar_bc);
   PFH_CUDA(cudaGetLastError());
 }
 
@@ -323,7 +337,7 @@ void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const do
   if (c->dim == 3)
     k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero);
   else
-    k2_scalar<2><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, a, b, z.p, r, zprev, zprev_is_zero);
+    k2_scalar<2><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, a, b, z.p, r, zprev, zprev_is_zero, c->scalar_bc);
   PFH_CUDA(cudaGetLastError());
 }
 
@@ -374,5 +388,12 @@ void k_dirichlet_fix(pfh_ctx* c, double* w) {
   if (c->dim != 2 || c->prob.id != PFH_PROBLEM_BENCH6) return;
   ProfScope ps(c, T_OTHER);
   k2_dirichlet<ProbBench6><<<grid1(c->m2.ncorner), TPB, 0, c->stream>>>(ProbBench6(c->prob), c->m2, w);
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst) {
+  if (c->dim != 2) return;
+  ProfScope ps(c, T_OTHER);
+  k2_dirichlet_copy<<<grid1(c->m2.ncorner), TPB, 0, c->stream>>>(c->m2, src, dst);
   PFH_CUDA(cudaGetLastError());
 }
