@@ -28,6 +28,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 must print exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+os.environ["NCCL_DEBUG"] = os.environ.get("PFH_NCCL_DEBUG", "WARN")
 
 METRIC = "CH DOF*Newton-steps/s (b13d 3-D Cahn-Hilliard, implicit step)"
 UNIT = "DOF*Newton-steps/s"
@@ -169,11 +171,18 @@ def run_b200(args):
 
     n = args.grid - 1
     L = 2.0 * n
-    ctx = engine.Context("b13d", (n, n, n), (L, L, L), device=local, rank=rank, nranks=world, nccl_id=nccl_id,
-                         krylov_basis=args.restart)
+    if args.workload == "bench1":     # 2-D crossed mesh with `grid` cells per edge (reference: 100), replicas only
+        assert world == 1, "2-D cases do not shard (DESIGN.md section 6)"
+        n = args.grid
+        ctx = engine.Context("bench1", (n, n), (2.0 * n, 2.0 * n), device=local, krylov_basis=args.restart)
+    else:
+        ctx = engine.Context("b13d", (n, n, n), (L, L, L), device=local, rank=rank, nranks=world, nccl_id=nccl_id,
+                             krylov_basis=args.restart)
     dof = 2 * ctx.n_global
+    if world > 1 and os.environ.get("PFH_OVERLAP", "1") == "0":
+        ctx.set_option("overlap", 0)
     opts = _lib.default_opts(krylov_restart=args.restart, pc_variant=args.pc_variant, pc_sweeps_mass=args.sweeps_mass,
-                             pc_sweeps_shifted=args.sweeps_shifted, krylov_maximum_iterations=int(n ** 3 / 10) or 1000)
+                             pc_sweeps_shifted=args.sweeps_shifted, krylov_maximum_iterations=max(1000, int(n ** 3 / 10)) if args.workload == "b13d" else 1000)
     stream = torch.cuda.ExternalStream(ctx.lib.pfh_stream(ctx._h), device=torch.device("cuda", local))
     dts = dt_schedule(args.warmup + args.steps)
 
@@ -284,11 +293,13 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "b13d_kuhn3d_%d" % args.grid, "grid_vertices": [args.grid] * 3, "dof": dof,
+                "config": {"workload": ("b13d_kuhn3d_%d" if args.workload == "b13d" else "bench1_crossed2d_%d") % args.grid,
+                           "grid_vertices": [args.grid] * 3 if args.workload == "b13d" else [args.grid + 1] * 2, "dof": dof,
                            "fields": "c,mu", "h": 2.0, "dt_list": dts[args.warmup:], "parallelism": "z-slabs x%d" % world,
                            "solver": "newton(atol 1e-6, max 10) + GMRES(%d, rtol 1e-5) + Schur/Chebyshev(%d,%d,%s)" % (
                                args.restart, args.sweeps_mass, args.sweeps_shifted, "upper" if args.pc_variant else "full"),
-                           "l2_policy": "inputs_exceed_l2 (every vector is %.0f MB >> 126 MB L2)" % (bytes_vec / 1e6)},
+                           "l2_policy": ("inputs_exceed_l2 (every vector is %.0f MB >> 126 MB L2)" % (bytes_vec / 1e6)) if bytes_vec > 2.6e8
+                           else "L2-resident working set (%.1f MB per vector): launch-bound regime, no flush" % (bytes_vec / 1e6)},
                 "newton_its": newton, "krylov_its": krylov, "energy": reports[-1]["energy"], "solute": reports[-1]["solute"],
                 "gpu_launches": launches_all, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * bytes_vec * world,
@@ -308,7 +319,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--grid", type=int, default=512, help="vertices per edge of the synthetic 3-D grid")
+    ap.add_argument("--grid", type=int, default=512, help="vertices per edge of the synthetic 3-D grid (cells per edge for bench1)")
+    ap.add_argument("--workload", default="b13d", choices=["b13d", "bench1"], help="b13d = 3-D headline; bench1 = 2-D crossed mesh")
     ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--pc-variant", type=int, default=1)
     ap.add_argument("--sweeps-mass", type=int, default=3)

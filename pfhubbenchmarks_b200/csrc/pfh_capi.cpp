@@ -25,7 +25,7 @@ double* pfh_alloc(pfh_ctx* c, size_t n) {
   return p;
 }
 
-void pfh_prof_begin(pfh_ctx* c, int id) {
+void pfh_prof_begin(pfh_ctx* c, int id, cudaStream_t s) {
   EventPair ep;
   if (!c->ev_free.empty()) {
     ep = c->ev_free.back();
@@ -36,14 +36,14 @@ void pfh_prof_begin(pfh_ctx* c, int id) {
   }
   ep.id = id;
   if (c->ev_pending.size() >= 8192) pfh_prof_resolve(c);
-  PFH_CUDA(cudaEventRecord(ep.a, c->stream));
+  PFH_CUDA(cudaEventRecord(ep.a, s ? s : c->stream));
   c->ev_pending.push_back(ep);
 }
-void pfh_prof_end(pfh_ctx* c, int id) {
+void pfh_prof_end(pfh_ctx* c, int id, cudaStream_t s) {
   // scopes nest at most trivially (reduce inside multidot is sequential, not nested): close the last open one of this id
   for (size_t i = c->ev_pending.size(); i-- > 0;)
     if (c->ev_pending[i].id == id) {
-      cudaEventRecord(c->ev_pending[i].b, c->stream);  // called from a destructor: must not throw
+      cudaEventRecord(c->ev_pending[i].b, s ? s : c->stream);  // called from a destructor: must not throw
       c->ev_pending[i].id = id | 0x100;  // closed
       break;
     }
@@ -51,6 +51,7 @@ void pfh_prof_end(pfh_ctx* c, int id) {
 void pfh_prof_resolve(pfh_ctx* c) {
   if (c->ev_pending.empty()) return;
   PFH_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->comm_stream) PFH_CUDA(cudaStreamSynchronize(c->comm_stream));
   for (EventPair& ep : c->ev_pending) {
     if (ep.id & 0x100) {
       float ms = 0.f;
@@ -179,6 +180,13 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
 
     pfh_config cc = *cfg;
     c->comm = comm_create(cc, c->stream);
+    if (cfg->nranks > 1) {
+      int lo_prio = 0, hi_prio = 0;
+      PFH_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+      PFH_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi_prio));
+      PFH_CUDA(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
+      PFH_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    }
     PFH_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
   } catch (const std::exception& e) {
@@ -193,7 +201,11 @@ int pfh_destroy(pfh_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   comm_destroy(c->comm);
+  if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (double* p : c->allocs) cudaFree(p);
   if (c->h_red) cudaFreeHost(c->h_red);
   for (EventPair& e : c->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -367,6 +379,8 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->profiling = value != 0.0;
   } else if (k == "reset_launch_count") {
     c->launches = 0;
+  } else if (k == "overlap") {
+    c->overlap = value != 0.0;
   } else if (k == "use_tma") {
     c->use_tma = value != 0.0;
   } else {

@@ -89,9 +89,10 @@ void comm_allreduce_sum(pfh_ctx* c, double* d_buf, int n) {
 
 // Ghost planes: rank r owns planes [z_begin, z_end); it sends its first plane down to r-1 and its
 // last plane up to r+1, and receives r-1's last plane into glo and r+1's first plane into ghi.
-void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, double* glo, double* ghi) {
+void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, double* glo, double* ghi, cudaStream_t stream) {
   if (!c->comm) return;
-  ProfScope ps(c, T_HALO);
+  cudaStream_t st = stream ? stream : c->stream;
+  ProfScope ps(c, T_HALO, 0.0, st);
   const Comm* cm = c->comm;
   const long long np = c->nplane;
   const long long last = (long long)(c->m3.nzl - 1) * np;
@@ -99,12 +100,12 @@ void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, d
   for (int f = 0; f < nfields; ++f) {
     const double* fb = base + f * fstride;
     if (cm->rank > 0) {
-      ck(api().Send(fb, (size_t)np, ncclDouble, cm->rank - 1, cm->comm, c->stream), "ncclSend");
-      ck(api().Recv(glo + f * np, (size_t)np, ncclDouble, cm->rank - 1, cm->comm, c->stream), "ncclRecv");
+      ck(api().Send(fb, (size_t)np, ncclDouble, cm->rank - 1, cm->comm, st), "ncclSend");
+      ck(api().Recv(glo + f * np, (size_t)np, ncclDouble, cm->rank - 1, cm->comm, st), "ncclRecv");
     }
     if (cm->rank < cm->nranks - 1) {
-      ck(api().Send(fb + last, (size_t)np, ncclDouble, cm->rank + 1, cm->comm, c->stream), "ncclSend");
-      ck(api().Recv(ghi + f * np, (size_t)np, ncclDouble, cm->rank + 1, cm->comm, c->stream), "ncclRecv");
+      ck(api().Send(fb + last, (size_t)np, ncclDouble, cm->rank + 1, cm->comm, st), "ncclSend");
+      ck(api().Recv(ghi + f * np, (size_t)np, ncclDouble, cm->rank + 1, cm->comm, st), "ncclRecv");
     }
   }
   ck(api().GroupEnd(), "ncclGroupEnd");

@@ -125,6 +125,12 @@ struct pfh_ctx {
   double dt = 0.1;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // halo/compute overlap (nranks > 1): ghost planes travel on comm_stream while interior planes are computed
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr;
+  bool overlap = true;
+  // z-range restriction of the next scalar-operator launches: 0 all planes, 1 boundary planes {0, nzl-1}, 2 interior [1, nzl-1)
+  int zpart = 0;
   double* d_tables = nullptr;
 
   // workspaces (device)
@@ -173,22 +179,23 @@ struct pfh_ctx {
 #define PFH_RED_MAXVALS 36
 
 double* pfh_alloc(pfh_ctx* c, size_t n_doubles);
-void pfh_prof_begin(pfh_ctx* c, int id);
-void pfh_prof_end(pfh_ctx* c, int id);
+void pfh_prof_begin(pfh_ctx* c, int id, cudaStream_t s = nullptr);
+void pfh_prof_end(pfh_ctx* c, int id, cudaStream_t s = nullptr);
 void pfh_prof_resolve(pfh_ctx* c);
 
 struct ProfScope {
   pfh_ctx* c;
   int id;
-  ProfScope(pfh_ctx* c_, int id_, double algorithmic_bytes = 0.0) : c(c_), id(id_) {
+  cudaStream_t s;
+  ProfScope(pfh_ctx* c_, int id_, double algorithmic_bytes = 0.0, cudaStream_t s_ = nullptr) : c(c_), id(id_), s(s_) {
     if (id != T_COPY && id != T_HALO && id != T_ALLREDUCE) c->launches++;  // our own kernels only
     if (c->profiling) {
       c->t_bytes[id] += algorithmic_bytes;
-      pfh_prof_begin(c, id);
+      pfh_prof_begin(c, id, s);
     }
   }
   ~ProfScope() {
-    if (c->profiling) pfh_prof_end(c, id);
+    if (c->profiling) pfh_prof_end(c, id, s);
   }
 };
 
@@ -243,7 +250,8 @@ Comm* comm_create(const pfh_config& cfg, cudaStream_t s);
 void comm_destroy(Comm*);
 void comm_allreduce_sum(pfh_ctx* c, double* d_buf, int n);
 // exchange boundary planes of nfields fields stored field-major with stride fstride
-void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, double* glo, double* ghi);
+void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, double* glo, double* ghi,
+               cudaStream_t stream = nullptr);  // stream == nullptr: the ctx stream
 int comm_unique_id(void* out);
 
 // ---- solver (pfh_solver.cpp) ----

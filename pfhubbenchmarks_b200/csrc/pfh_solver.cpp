@@ -103,10 +103,36 @@ void cheb_solve(pfh_ctx* c, double am, double ak, double lmin, double lmax, int 
   const std::vector<ChebCoef> cf = cheb_coeffs(lmin, lmax, nsweeps);
   double* cur = ((nsweeps - 1) % 2 == 0) ? target : tmp;
   double* prev = (cur == target) ? tmp : target;
-  k_cheb_first(c, am, ak, cf[0].b, r, cur);
-  for (int k = 1; k < nsweeps; ++k) {
-    k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev, k == 1);
-    std::swap(cur, prev);
+  const bool ov = c->cfg.nranks > 1 && c->overlap && c->comm_stream && c->dim == 3 && c->m3.nzl >= 4;
+  if (!ov) {
+    k_cheb_first(c, am, ak, cf[0].b, r, cur);
+    for (int k = 1; k < nsweeps; ++k) {
+      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev, k == 1);
+      std::swap(cur, prev);
+    }
+  } else {
+    // Halo/compute overlap: every producer writes its two slab-boundary planes first and signals ev_bnd; the ghost
+    // exchange of those planes runs on comm_stream while the interior planes are computed on the ctx stream; the
+    // next sweep's boundary launch waits for ev_halo.  Only the interior launch never touches ghost planes.
+    c->zpart = 1;
+    k_cheb_first(c, am, ak, cf[0].b, r, cur);
+    PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+    c->zpart = 2;
+    k_cheb_first(c, am, ak, cf[0].b, r, cur);
+    for (int k = 1; k < nsweeps; ++k) {
+      PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+      comm_halo(c, cur, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
+      PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+      PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+      const FieldRef ref{cur, c->gS_lo, c->gS_hi};
+      c->zpart = 1;
+      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, k == 1);
+      PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+      c->zpart = 2;
+      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, k == 1);
+      std::swap(cur, prev);
+    }
+    c->zpart = 0;
   }
   PFH_CHECK(cur == target, "internal: chebyshev ping-pong parity");
 }

@@ -62,11 +62,21 @@ __global__ void __launch_bounds__(BX* BY) k3_op(P prob, Mesh3 m, LinCoefs L, Fie
 // MODE 0: out = s*add + A in ; MODE 1: z = b Dinv r ; MODE 2: zprev <- z + a (z - zprev) + b Dinv (r - A z)
 template <int MODE>
 __global__ void __launch_bounds__(BX* BY) k3_scalar(Mesh3 m, double am, double ak, double a, double b, FieldRef in,
-                                                    const double* __restrict__ r, double* __restrict__ out, bool out_is_zero) {
+                                                    const double* __restrict__ r, double* __restrict__ out, bool out_is_zero,
+                                                    int zpart) {
   const int ix = blockIdx.x * BX + threadIdx.x, iy = blockIdx.y * BY + threadIdx.y;
   if (ix >= m.nxv || iy >= m.nyv) return;
-  const int z_end = min(m.nzl, (int)(blockIdx.z + 1) * ZCHUNK);
-  for (int zl = blockIdx.z * ZCHUNK; zl < z_end; ++zl) {
+  // zpart 0: all planes; 1: slab-boundary planes {0, nzl-1}; 2: interior planes [1, nzl-1)
+  int z_beg, z_end;
+  if (zpart == 1) {
+    z_beg = blockIdx.z == 0 ? 0 : m.nzl - 1;
+    z_end = z_beg + 1;
+  } else {
+    const int zoff = zpart == 2 ? 1 : 0, zlim = zpart == 2 ? m.nzl - 1 : m.nzl;
+    z_beg = zoff + blockIdx.z * ZCHUNK;
+    z_end = min(zlim, z_beg + ZCHUNK);
+  }
+  for (int zl = z_beg; zl < z_end; ++zl) {
     const long long i = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
     if (MODE == 1) {
       out[i] = b / vtx::scalar_diag3(m, am, ak, ix, iy, zl) * r[i];
@@ -224,8 +234,19 @@ __global__ void __launch_bounds__(TPB) k2_dirichlet_copy(Mesh2 m, const double* 
   if (ix == 0 || ix == m.nxv - 1) dst[i] = src[i];
 }
 
+// fraction of the owned planes a scalar-operator launch covers under the current z-range restriction
+double zfrac(const pfh_ctx* c) {
+  if (c->dim != 3 || c->zpart == 0) return 1.0;
+  const double nz = (double)c->m3.nzl;
+  return c->zpart == 1 ? 2.0 / nz : (nz - 2.0) / nz;
+}
+
 // -------- launch helpers --------
 dim3 grid3(const Mesh3& m) { return dim3((m.nxv + BX - 1) / BX, (m.nyv + BY - 1) / BY, (m.nzl + ZCHUNK - 1) / ZCHUNK); }
+dim3 grid3_part(const Mesh3& m, int zpart) {
+  const int nz = zpart == 1 ? 2 * ZCHUNK : (zpart == 2 ? (m.nzl - 2 > 0 ? m.nzl - 2 : 1) : m.nzl);
+  return dim3((m.nxv + BX - 1) / BX, (m.nyv + BY - 1) / BY, (nz + ZCHUNK - 1) / ZCHUNK);
+}
 int grid1(long long n) { return (int)((n + TPB - 1) / TPB); }
 int grid_red(long long n) {
   long long g = (n + TPB - 1) / TPB;
@@ -311,20 +332,20 @@ bool k_ch_crow(pfh_ctx* c, const double* ulin, FieldRef xc, double* out) {
 }
 
 void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out) {
-  ProfScope ps(c, T_LIN_APPLY, 8.0 * (s != 0.0 ? 3 : 2) * c->n_owned);
+  ProfScope ps(c, T_LIN_APPLY, 8.0 * (s != 0.0 ? 3 : 2) * c->n_owned * zfrac(c));
   PFH_CHECK(s == 0.0 || add != nullptr, "k_lin_apply: add operand missing");
   if (c->dim == 3 && k3_scalar_tma_launch(c, 0, am, ak, s, 0.0, in, add, out, false)) return;
   if (c->dim == 3)
-    k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false);
+    k3_scalar<0><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false, c->zpart);
   else
     k2_scalar<0><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, s, 0.0, in.p, add, out, false, c->scalar_bc);
   PFH_CUDA(cudaGetLastError());
 }
 
 void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z) {
-  ProfScope ps(c, T_CHEB_FIRST, 16.0 * c->n_owned);
+  ProfScope ps(c, T_CHEB_FIRST, 16.0 * c->n_owned * zfrac(c));
   if (c->dim == 3)
-    k3_scalar<1><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z, false);
+    k3_scalar<1><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z, false, c->zpart);
   else
     k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z, false, c->scalar_bc);
   PFH_CUDA(cudaGetLastError());
@@ -332,10 +353,10 @@ void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, d
 
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev,
                   bool zprev_is_zero) {
-  ProfScope ps(c, T_CHEB_SWEEP, (zprev_is_zero ? 24.0 : 32.0) * c->n_owned);
+  ProfScope ps(c, T_CHEB_SWEEP, (zprev_is_zero ? 24.0 : 32.0) * c->n_owned * zfrac(c));
   if (c->dim == 3 && k3_scalar_tma_launch(c, 2, am, ak, a, b, z, r, zprev, zprev_is_zero)) return;
   if (c->dim == 3)
-    k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero);
+    k3_scalar<2><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero, c->zpart);
   else
     k2_scalar<2><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, a, b, z.p, r, zprev, zprev_is_zero, c->scalar_bc);
   PFH_CUDA(cudaGetLastError());

@@ -74,8 +74,8 @@ struct Coef15 {
 template <int MODE, int TX, int TY, int RY, int NS>
 __global__ void __launch_bounds__(TX*(TY / RY), 4)
     k3_scalar_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_lo,
-                  const __grid_constant__ CUtensorMap tm_hi, Mesh3 m, int has_lo, int has_hi, int zchunk, double am, double ak,
-                  Coef15 cI, double a, double b, double bdI, const double* __restrict__ r, double* __restrict__ out,
+                  const __grid_constant__ CUtensorMap tm_hi, Mesh3 m, int has_lo, int has_hi, int zchunk, int zpart, double am,
+                  double ak, Coef15 cI, double a, double b, double bdI, const double* __restrict__ r, double* __restrict__ out,
                   int out_is_zero) {
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2: the TMA box start (x0-2) must be 16-byte aligned
   constexpr int STAGE_BYTES = W * H * 8;
@@ -87,7 +87,16 @@ __global__ void __launch_bounds__(TX*(TY / RY), 4)
 
   const int tid = threadIdx.y * TX + threadIdx.x;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-  const int zb = blockIdx.z * zchunk, ze = min(m.nzl, zb + zchunk);
+  // zpart 0: all planes in chunks; 1: the two slab-boundary planes (one per blockIdx.z); 2: interior planes [1, nzl-1)
+  int zb, ze;
+  if (zpart == 1) {
+    zb = blockIdx.z == 0 ? 0 : m.nzl - 1;
+    ze = zb + 1;
+  } else {
+    const int zoff = zpart == 2 ? 1 : 0, zlim = zpart == 2 ? m.nzl - 1 : m.nzl;
+    zb = zoff + blockIdx.z * zchunk;
+    ze = min(zlim, zb + zchunk);
+  }
   const int nplanes = ze - zb + 2;  // planes zb-1 .. ze  <->  p = 0 .. nplanes-1
 
   if (tid == 0) {
@@ -421,14 +430,17 @@ bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, 
   const CUtensorMap th = hi ? make_map(in.ghi, m.nxv, m.nyv, 1, S_TX + 4, S_TY + 2) : tm;
   Coef15 cI;
   for (int o = 0; o < PFH_NOFF3; ++o) cI.c[o] = am * m.mI[o] + (o < PFH_NKOFF3 ? ak * m.kI[o] : 0.0);
-  const dim3 grid((m.nxv + S_TX - 1) / S_TX, (m.nyv + S_TY - 1) / S_TY, (m.nzl + S_ZCH - 1) / S_ZCH);
+  const int zp = c->zpart;
+  const int nz_part = zp == 1 ? 2 * S_ZCH : (zp == 2 ? m.nzl - 2 : m.nzl);  // zpart 1: gridDim.z = 2
+  if (nz_part <= 0) return true;
+  const dim3 grid((m.nxv + S_TX - 1) / S_TX, (m.nyv + S_TY - 1) / S_TY, (nz_part + S_ZCH - 1) / S_ZCH);
   const dim3 block(S_TX, S_TY / S_RY);
   constexpr int stage = round_up((S_TX + 4) * (S_TY + 2) * 8, 128);
   const size_t smem = S_NS * stage + S_NS * sizeof(uint64_t);
   if (mode == 0)
-    k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, am, ak, cI, a, b, 0.0, r, out, 0);
+    k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, zp, am, ak, cI, a, b, 0.0, r, out, 0);
   else
-    k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, am, ak, cI, a, b, b / cI.c[0], r, out, out_is_zero ? 1 : 0);
+    k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, zp, am, ak, cI, a, b, b / cI.c[0], r, out, out_is_zero ? 1 : 0);
   PFH_CUDA(cudaGetLastError());
   return true;
 }
