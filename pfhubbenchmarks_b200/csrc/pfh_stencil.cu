@@ -126,12 +126,21 @@ template <class P, bool JAC>
 __global__ void __launch_bounds__(TPB) k2_op(P prob, Mesh2 m, LinCoefs L, const double* __restrict__ U,
                                              const double* __restrict__ X, const double* __restrict__ U0,
                                              double* __restrict__ out) {
-  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
-  if (i >= m.n_owned) return;
+  // 2-D tiles (64 x 4): thread (ix, iy) evaluates corner vertex (ix, iy) and cell centre (ix, iy)
+  const int ix = blockIdx.x * 64 + (threadIdx.x & 63), iy = blockIdx.y * 4 + (threadIdx.x >> 6);
   double o[P::NF];
-  vtx::vertex_op2<P, JAC>(prob, m, L, U, X, U0, i, o);
+  if (ix < m.nxv && iy < m.nyv) {
+    vtx::vertex_op2_corner<P, JAC>(prob, m, L, U, X, U0, ix, iy, o);
+    const long long i = (long long)iy * m.nxv + ix;
 #pragma unroll
-  for (int a = 0; a < P::NF; ++a) out[a * m.n_owned + i] = o[a];
+    for (int a = 0; a < P::NF; ++a) out[a * m.n_owned + i] = o[a];
+  }
+  if (ix < m.nx && iy < m.ny) {
+    vtx::vertex_op2_centre<P, JAC>(prob, m, L, U, X, U0, ix, iy, o);
+    const long long i = m.ncorner + (long long)iy * m.nx + ix;
+#pragma unroll
+    for (int a = 0; a < P::NF; ++a) out[a * m.n_owned + i] = o[a];
+  }
 }
 
 template <int MODE>
@@ -154,6 +163,60 @@ __global__ void __launch_bounds__(TPB) k2_scalar(Mesh2 m, double am, double ak, 
     vtx::scalar_op2(m, am, ak, in, i, Av, d, self);
     if (MODE == 0) out[i] = (a != 0.0 ? a * r[i] : 0.0) + Av;
     else out[i] = self + a * (self - (out_is_zero ? 0.0 : out[i])) + (b / d) * (r[i] - Av);
+  }
+}
+
+// Tiled 2-D scalar operator: one corner vertex and one cell centre per thread, (T2X x T2Y) tiles so that the rows a
+// tile shares stay in L1; interior rows use constant-bank coefficients, boundary rows the stencil tables.
+// MODE 0: out = a*r + A in ; MODE 2: out <- in + a (in - out) + b D^-1 (r - A in).  32-bit indices.
+constexpr int T2X = 64, T2Y = 4;
+struct Coef2 {
+  double cc[PFH_NOFF2];  // am*M + ak*K, interior corner row
+  double zc[5];          // am*M + ak*K, centre row
+};
+template <int MODE>
+__global__ void __launch_bounds__(T2X* T2Y) k2_scalar_tiled(Mesh2 m, double am, double ak, Coef2 cf, double a, double b,
+                                                             const double* __restrict__ in, const double* __restrict__ r,
+                                                             double* __restrict__ out, int out_is_zero, int bc) {
+  const int ix = blockIdx.x * T2X + threadIdx.x, iy = blockIdx.y * T2Y + threadIdx.y;
+  const int nxv = m.nxv, nx = m.nx, nc = (int)m.ncorner;
+  if (ix < nxv && iy < m.nyv) {  // corner vertex (ix, iy)
+    const int i = iy * nxv + ix;
+    const double ri = (MODE == 2 || a != 0.0) ? __ldg(r + i) : 0.0;
+    if (bc && (ix == 0 || ix == nxv - 1)) {
+      out[i] = ri;  // Dirichlet identity row
+    } else {
+      const int type = vtx::type2(m, ix, iy);
+      double Av, d, self;
+      if (type == 4) {
+        const int cb = nc + iy * nx + ix;
+        self = __ldg(in + i);
+        Av = cf.cc[0] * self + cf.cc[1] * __ldg(in + i + 1) + cf.cc[2] * __ldg(in + i - 1) + cf.cc[3] * __ldg(in + i + nxv) +
+             cf.cc[4] * __ldg(in + i - nxv) + cf.cc[5] * __ldg(in + cb) + cf.cc[6] * __ldg(in + cb - 1) +
+             cf.cc[7] * __ldg(in + cb - nx) + cf.cc[8] * __ldg(in + cb - nx - 1);
+        d = cf.cc[0];
+      } else {
+        vtx::Row2 row;
+        vtx::get_row2(m, type, row);
+        double nb[13], Ms, Ks;
+        vtx::gather13(in, m, ix, iy, nb);
+        vtx::mk_sums2c(row, nb, Ms, Ks);
+        self = nb[4];
+        Av = am * Ms + ak * Ks;
+        d = am * row.m[0] + ak * row.k[0];
+      }
+      if (MODE == 0) out[i] = a * ri + Av;
+      else out[i] = self + a * (self - (out_is_zero ? 0.0 : out[i])) + (b / d) * (ri - Av);
+    }
+  }
+  if (ix < nx && iy < m.ny) {  // cell centre (ix, iy)
+    const int ci = nc + iy * nx + ix, v0 = iy * nxv + ix;
+    const double self = __ldg(in + ci);
+    const double Av = cf.zc[0] * self + cf.zc[1] * __ldg(in + v0) + cf.zc[2] * __ldg(in + v0 + 1) + cf.zc[3] * __ldg(in + v0 + nxv) +
+                      cf.zc[4] * __ldg(in + v0 + nxv + 1);
+    const double ri = (MODE == 2 || a != 0.0) ? __ldg(r + ci) : 0.0;
+    if (MODE == 0) out[ci] = a * ri + Av;
+    else out[ci] = self + a * (self - (out_is_zero ? 0.0 : out[ci])) + (b / cf.zc[0]) * (ri - Av);
   }
 }
 
@@ -242,6 +305,14 @@ double zfrac(const pfh_ctx* c) {
 }
 
 // -------- launch helpers --------
+Coef2 coef2(const Mesh2& m, double am, double ak) {
+  Coef2 cf;
+  for (int o = 0; o < PFH_NOFF2; ++o) cf.cc[o] = am * m.mI[o] + ak * m.kI[o];
+  for (int o = 0; o < 5; ++o) cf.zc[o] = am * m.mC[o] + ak * m.kC[o];
+  return cf;
+}
+dim3 grid2_tiled(const Mesh2& m) { return dim3((m.nxv + T2X - 1) / T2X, (m.nyv + T2Y - 1) / T2Y); }
+
 dim3 grid3(const Mesh3& m) { return dim3((m.nxv + BX - 1) / BX, (m.nyv + BY - 1) / BY, (m.nzl + ZCHUNK - 1) / ZCHUNK); }
 dim3 grid3_part(const Mesh3& m, int zpart) {
   const int nz = zpart == 1 ? 2 * ZCHUNK : (zpart == 2 ? (m.nzl - 2 > 0 ? m.nzl - 2 : 1) : m.nzl);
@@ -304,7 +375,7 @@ void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
                          P(c->prob), c->m3, L, state_fields<P>(c, u, c->gU_lo, c->gU_hi), state_fields<P>(c, nullptr, nullptr, nullptr),
                          state_fields<P>(c, u0, c->gU0_lo, c->gU0_hi), R)));
   } else {
-    PFH_DISPATCH2(c, (k2_op<P, false><<<grid1(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, u, nullptr, u0, R)));
+    PFH_DISPATCH2(c, (k2_op<P, false><<<dim3((c->m2.nxv + 63) / 64, (c->m2.nyv + 3) / 4), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, u, nullptr, u0, R)));
   }
   PFH_CUDA(cudaGetLastError());
 }
@@ -319,7 +390,7 @@ void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
                          P(c->prob), c->m3, L, state_fields<P>(c, ulin, c->gU_lo, c->gU_hi), state_fields<P>(c, x, c->gX_lo, c->gX_hi),
                          state_fields<P>(c, nullptr, nullptr, nullptr), y)));
   } else {
-    PFH_DISPATCH2(c, (k2_op<P, true><<<grid1(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, ulin, x, nullptr, y)));
+    PFH_DISPATCH2(c, (k2_op<P, true><<<dim3((c->m2.nxv + 63) / 64, (c->m2.nyv + 3) / 4), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, ulin, x, nullptr, y)));
   }
   PFH_CUDA(cudaGetLastError());
 }
@@ -338,7 +409,8 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
   if (c->dim == 3)
     k3_scalar<0><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false, c->zpart);
   else
-    k2_scalar<0><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, s, 0.0, in.p, add, out, false, c->scalar_bc);
+    k2_scalar_tiled<0><<<grid2_tiled(c->m2), dim3(T2X, T2Y), 0, c->stream>>>(c->m2, am, ak, coef2(c->m2, am, ak), s, 0.0, in.p, add, out, 0,
+                                                                                  c->scalar_bc);
   PFH_CUDA(cudaGetLastError());
 }
 
@@ -358,7 +430,8 @@ void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const do
   if (c->dim == 3)
     k3_scalar<2><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero, c->zpart);
   else
-    k2_scalar<2><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, a, b, z.p, r, zprev, zprev_is_zero, c->scalar_bc);
+    k2_scalar_tiled<2><<<grid2_tiled(c->m2), dim3(T2X, T2Y), 0, c->stream>>>(c->m2, am, ak, coef2(c->m2, am, ak), a, b, z.p, r, zprev,
+                                                                                  zprev_is_zero ? 1 : 0, c->scalar_bc);
   PFH_CUDA(cudaGetLastError());
 }
 

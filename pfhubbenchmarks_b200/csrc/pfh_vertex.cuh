@@ -310,12 +310,12 @@ PFH_HD void mk_sums2z(const Mesh2& m, const double (&q)[5], double& Ms, double& 
 }
 
 // one vertex i (DOLFIN order: corners first, then centres) of the 2-D operators
+// corner vertex (ix, iy)
 template <class P, bool JAC>
-PFH_HD void vertex_op2(const P& prob, const Mesh2& m, const LinCoefs& L, const double* U, const double* X, const double* U0,
-                       long long i, double (&out)[P::NF]) {
+PFH_HD void vertex_op2_corner(const P& prob, const Mesh2& m, const LinCoefs& L, const double* U, const double* X,
+                              const double* U0, int ix, int iy, double (&out)[P::NF]) {
   const long long n = m.n_owned;
-  if (i < m.ncorner) {
-    const int ix = (int)(i % m.nxv), iy = (int)(i / m.nxv);
+  {
     Row2 r;
     get_row2(m, type2(m, ix, iy), r);
     double nu[P::NF][13];
@@ -386,9 +386,15 @@ PFH_HD void vertex_op2(const P& prob, const Mesh2& m, const LinCoefs& L, const d
         if (prob.dirichlet(a, ix, iy, m.nx, iy * m.hy, val)) out[a] = JAC ? nu[a][4] : nu[a][4] - val;
       }
     }
-  } else {
-    const long long ci = i - m.ncorner;
-    const int cx = (int)(ci % m.nx), cy = (int)(ci / m.nx);
+  }
+}
+
+// cell centre (cx, cy)
+template <class P, bool JAC>
+PFH_HD void vertex_op2_centre(const P& prob, const Mesh2& m, const LinCoefs& L, const double* U, const double* X,
+                              const double* U0, int cx, int cy, double (&out)[P::NF]) {
+  const long long n = m.n_owned;
+  {
     double q[P::NF][5], Ms[P::NF], Ks[P::NF];
 #pragma unroll
     for (int b = 0; b < P::NF; ++b) {
@@ -430,6 +436,18 @@ PFH_HD void vertex_op2(const P& prob, const Mesh2& m, const LinCoefs& L, const d
     elem::square_load<P, JAC>(prob, u, x, m.detJ, o5);
 #pragma unroll
     for (int o = 0; o < P::NOUT; ++o) out[P::out(o)] += o5[o][4];
+  }
+}
+
+// one vertex i in DOLFIN order (corners first, then centres)
+template <class P, bool JAC>
+PFH_HD void vertex_op2(const P& prob, const Mesh2& m, const LinCoefs& L, const double* U, const double* X, const double* U0,
+                       long long i, double (&out)[P::NF]) {
+  if (i < m.ncorner) {
+    vertex_op2_corner<P, JAC>(prob, m, L, U, X, U0, (int)(i % m.nxv), (int)(i / m.nxv), out);
+  } else {
+    const long long ci = i - m.ncorner;
+    vertex_op2_centre<P, JAC>(prob, m, L, U, X, U0, (int)(ci % m.nx), (int)(ci / m.nx), out);
   }
 }
 
