@@ -74,16 +74,19 @@ struct Coef15 {
 template <int MODE, int TX, int TY, int RY, int NS>
 __global__ void __launch_bounds__(TX*(TY / RY), 4)
     k3_scalar_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_lo,
-                  const __grid_constant__ CUtensorMap tm_hi, Mesh3 m, int has_lo, int has_hi, int zchunk, int zpart, double am,
-                  double ak, Coef15 cI, double a, double b, double bdI, const double* __restrict__ r, double* __restrict__ out,
-                  int out_is_zero) {
+                  const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_r,
+                  const __grid_constant__ CUtensorMap tm_o, Mesh3 m, int has_lo, int has_hi, int has_r, int has_o, int zchunk,
+                  int zpart, double am, double ak, Coef15 cI, double a, double b, double bdI, double* __restrict__ out) {
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2: the TMA box start (x0-2) must be 16-byte aligned
-  constexpr int STAGE_BYTES = W * H * 8;
-  constexpr int STAGE_STRIDE = round_up(STAGE_BYTES, 128);
+  constexpr int ZT_BYTES = W * H * 8, PT_BYTES = TX * TY * 8;
+  constexpr int ZT_STRIDE = round_up(ZT_BYTES, 128);
+  constexpr int STAGE_STRIDE = ZT_STRIDE + 2 * PT_BYTES;  // [z tile + halo | r tile | zprev tile]
   constexpr int ROWS = TY / RY;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * STAGE_STRIDE);
-  auto stage = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * STAGE_STRIDE); };
+  auto ztile = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * STAGE_STRIDE); };
+  auto rtile = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * STAGE_STRIDE + ZT_STRIDE); };
+  auto otile = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * STAGE_STRIDE + ZT_STRIDE + PT_BYTES); };
 
   const int tid = threadIdx.y * TX + threadIdx.x;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(TX*(TY / RY), 4)
   }
   __syncthreads();
 
+  // plane p <-> zl = zb-1+p: the stencil operand with halo, and (owned planes only) the pointwise operands r, zprev
   auto issue = [&](int p) {
     const int zl = zb - 1 + p;
     const CUtensorMap* map = &tm_main;
@@ -117,8 +121,12 @@ __global__ void __launch_bounds__(TX*(TY / RY), 4)
       zc = 0;
     }
     uint64_t* bar = &bars[p % NS];
-    mbar_expect_tx(bar, STAGE_BYTES);
-    tma_load_3d(smem + (p % NS) * STAGE_STRIDE, map, x0 - 2, y0 - 1, zc, bar);
+    unsigned char* st = smem + (p % NS) * STAGE_STRIDE;
+    const bool owned = p >= 1 && p <= ze - zb;
+    mbar_expect_tx(bar, ZT_BYTES + (owned && has_r ? PT_BYTES : 0) + (owned && has_o ? PT_BYTES : 0));
+    tma_load_3d(st, map, x0 - 2, y0 - 1, zc, bar);
+    if (owned && has_r) tma_load_3d(st + ZT_STRIDE, &tm_r, x0, y0, zl, bar);
+    if (owned && has_o) tma_load_3d(st + ZT_STRIDE + PT_BYTES, &tm_o, x0, y0, zl, bar);
   };
   if (tid == 0)
     for (int p = 0; p < NS - 1 && p < nplanes; ++p) issue(p);
@@ -141,27 +149,17 @@ __global__ void __launch_bounds__(TX*(TY / RY), 4)
     const int zl = zb + k;
     __syncthreads();  // every thread is done with plane k-1: its stage may be refilled
     if (tid == 0 && k + NS - 1 < nplanes) issue(k + NS - 1);
-
-    // pointwise operands first, so their latency overlaps the wait on the TMA planes
-    double rv[RY], ov[RY];
-#pragma unroll
-    for (int rr = 0; rr < RY; ++rr) {
-      rv[rr] = 0.0;
-      ov[rr] = 0.0;
-      if (valid[rr]) {
-        if (MODE == 2 || a != 0.0) rv[rr] = __ldg(r + idx[rr]);
-        if (MODE == 2 && !out_is_zero) ov[rr] = out[idx[rr]];
-      }
-    }
     if (k == 0) {
       mbar_wait(&bars[0], 0);
       mbar_wait(&bars[1 % NS], (1 / NS) & 1);
     }
     mbar_wait(&bars[(k + 2) % NS], ((k + 2) / NS) & 1);
 
-    const double* S0 = stage(k);
-    const double* S1 = stage(k + 1);
-    const double* S2 = stage(k + 2);
+    const double* S0 = ztile(k);
+    const double* S1 = ztile(k + 1);
+    const double* S2 = ztile(k + 2);
+    const double* Rt = rtile(k + 1);
+    const double* Ot = otile(k + 1);
     const int gz = m.z0 + zl;
     const int tzt = gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1);
 #pragma unroll
@@ -169,16 +167,23 @@ __global__ void __launch_bounds__(TX*(TY / RY), 4)
       if (!valid[rr]) continue;
       const int ly = threadIdx.y + rr * ROWS;
       const int c = (ly + 1) * W + threadIdx.x + 2;
+      const int pc = ly * TX + threadIdx.x;
+      const double rv = has_r ? Rt[pc] : 0.0;
+      const double ov = has_o ? Ot[pc] : 0.0;
       double v[PFH_NOFF3];
       v[0] = S1[c]; v[1] = S1[c + 1]; v[2] = S1[c - 1]; v[3] = S1[c + W]; v[4] = S1[c - W];
       v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
       v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
       v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
       const int type = tzt * 9 + txy[rr];
-      double Av = 0.0, bd;
+      double Av, bd;
       if (type == 13) {
-#pragma unroll
-        for (int o = 0; o < PFH_NOFF3; ++o) Av += cI.c[o] * v[o];
+        // four independent partial sums: the 15 fused multiply-adds are not one dependent chain
+        double s0 = cI.c[0] * v[0], s1 = cI.c[1] * v[1], s2 = cI.c[2] * v[2], s3 = cI.c[3] * v[3];
+        s0 += cI.c[4] * v[4]; s1 += cI.c[5] * v[5]; s2 += cI.c[6] * v[6]; s3 += cI.c[7] * v[7];
+        s0 += cI.c[8] * v[8]; s1 += cI.c[9] * v[9]; s2 += cI.c[10] * v[10]; s3 += cI.c[11] * v[11];
+        s0 += cI.c[12] * v[12]; s1 += cI.c[13] * v[13]; s2 += cI.c[14] * v[14];
+        Av = (s0 + s1) + (s2 + s3);
         bd = bdI;
       } else {
         vtx::Row3 row;
@@ -188,8 +193,8 @@ __global__ void __launch_bounds__(TX*(TY / RY), 4)
         Av = am * Ms + ak * Ks;
         bd = MODE == 2 ? b / (am * row.m[0] + ak * row.k[0]) : 0.0;
       }
-      if (MODE == 0) out[idx[rr]] = a * rv[rr] + Av;
-      else out[idx[rr]] = v[0] + a * (v[0] - ov[rr]) + bd * (rv[rr] - Av);
+      if (MODE == 0) out[idx[rr]] = a * rv + Av;
+      else out[idx[rr]] = v[0] + a * (v[0] - ov) + bd * (rv - Av);
     }
 #pragma unroll
     for (int rr = 0; rr < RY; ++rr) idx[rr] += m.nxy;
@@ -406,7 +411,7 @@ CUtensorMap make_map(const double* ptr, int nxv, int nyv, int nz, int bx, int by
   return map;
 }
 
-constexpr int S_TX = 64, S_TY = 8, S_RY = 2, S_NS = 6, S_ZCH = 32;
+constexpr int S_TX = 64, S_TY = 8, S_RY = 2, S_NS = 4, S_ZCH = 32;
 constexpr int J_TX = 32, J_TY = 8, J_NT = 320, J_NS = 4, J_ZCH = 32;
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -421,13 +426,17 @@ bool pfh_tma_ok(const pfh_ctx* c) {
 // operands do not qualify (caller falls back to the gather kernel)
 bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
                           double* out, bool out_is_zero) {
-  if (!pfh_tma_ok(c) || !aligned16(in.p)) return false;
+  if (!pfh_tma_ok(c) || !aligned16(in.p) || !aligned16(out) || (r && !aligned16(r))) return false;
   const Mesh3& m = c->m3;
   const bool lo = in.glo != nullptr && c->cfg.rank > 0, hi = in.ghi != nullptr && c->cfg.rank < c->cfg.nranks - 1;
   if ((lo && !aligned16(in.glo)) || (hi && !aligned16(in.ghi))) return false;
+  const bool has_r = (mode == 2 || a != 0.0) && r != nullptr;
+  const bool has_o = mode == 2 && !out_is_zero;
   const CUtensorMap tm = make_map(in.p, m.nxv, m.nyv, m.nzl, S_TX + 4, S_TY + 2);
   const CUtensorMap tl = lo ? make_map(in.glo, m.nxv, m.nyv, 1, S_TX + 4, S_TY + 2) : tm;
   const CUtensorMap th = hi ? make_map(in.ghi, m.nxv, m.nyv, 1, S_TX + 4, S_TY + 2) : tm;
+  const CUtensorMap tr = has_r ? make_map(r, m.nxv, m.nyv, m.nzl, S_TX, S_TY) : tm;
+  const CUtensorMap to = has_o ? make_map(out, m.nxv, m.nyv, m.nzl, S_TX, S_TY) : tm;
   Coef15 cI;
   for (int o = 0; o < PFH_NOFF3; ++o) cI.c[o] = am * m.mI[o] + (o < PFH_NKOFF3 ? ak * m.kI[o] : 0.0);
   const int zp = c->zpart;
@@ -435,12 +444,20 @@ bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, 
   if (nz_part <= 0) return true;
   const dim3 grid((m.nxv + S_TX - 1) / S_TX, (m.nyv + S_TY - 1) / S_TY, (nz_part + S_ZCH - 1) / S_ZCH);
   const dim3 block(S_TX, S_TY / S_RY);
-  constexpr int stage = round_up((S_TX + 4) * (S_TY + 2) * 8, 128);
-  const size_t smem = S_NS * stage + S_NS * sizeof(uint64_t);
+  constexpr int stage = round_up((S_TX + 4) * (S_TY + 2) * 8, 128) + 2 * S_TX * S_TY * 8;
+  constexpr size_t smem = S_NS * stage + S_NS * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   if (mode == 0)
-    k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, zp, am, ak, cI, a, b, 0.0, r, out, 0);
+    k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, tr, to, m, lo, hi, has_r, 0, S_ZCH, zp, am, ak, cI,
+                                                                              a, b, 0.0, out);
   else
-    k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, m, lo, hi, S_ZCH, zp, am, ak, cI, a, b, b / cI.c[0], r, out, out_is_zero ? 1 : 0);
+    k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, tr, to, m, lo, hi, has_r, has_o, S_ZCH, zp, am,
+                                                                              ak, cI, a, b, b / cI.c[0], out);
   PFH_CUDA(cudaGetLastError());
   return true;
 }
