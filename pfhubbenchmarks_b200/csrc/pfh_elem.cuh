@@ -111,6 +111,36 @@ PFH_HD void cube_jac_quartic(const QuarticJac& k, const double (&c)[8], const do
   }
 }
 
+// Residual counterpart: load of a cubic g(c) = a3 c^3 + a2 c^2 + a1 c + a0 (= -f'(c) of the double well) over one cube,
+// with the same folding: corner k gets Q(s + 2 c_k) + 1/2 sum_j Q(s + 2 c_j) + R(s).
+struct QuarticRes {
+  double Q3, Q2, Q1, Q0, R3, R2, R1, R0;
+  PFH_HD QuarticRes(double a3, double a2, double a1, double a0, double detJ) {
+    const double q = detJ * TET_W1 / 3.0, r = detJ * TET_W0 / 4.0;
+    Q3 = q * a3 / 216.0; Q2 = q * a2 / 36.0; Q1 = q * a1 / 6.0; Q0 = q * a0;
+    R3 = r * a3 / 64.0; R2 = r * a2 / 16.0; R1 = r * a1 / 4.0; R0 = r * a0;
+  }
+};
+PFH_HD void cube_res_quartic(const QuarticRes& k, const double (&c)[8], double (&out)[8]) {
+  const double c07 = c[0] + c[7];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    const int p = kuhn_mid(t, 0), q = kuhn_mid(t, 1);
+    const double s = c07 + c[p] + c[q];
+    const int v[4] = {0, 7, p, q};
+    double h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double tc = 2.0 * c[v[j]] + s;
+      h[j] = ((k.Q3 * tc + k.Q2) * tc + k.Q1) * tc + k.Q0;
+    }
+    const double S = (h[0] + h[1]) + (h[2] + h[3]);
+    const double base = 0.5 * S + (((k.R3 * s + k.R2) * s + k.R1) * s + k.R0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[v[j]] += base + h[j];
+  }
+}
+
 // Nonlinear load of one crossed square: out[o][k] += int_{square} phi_k g_o(u_h), k = 0..4
 template <class P, bool JAC>
 PFH_DEV void square_load(const P& prob, const double (&u)[P::NIN][5], const double (&x)[P::NIN][5], double detJ,

@@ -222,6 +222,7 @@ bool pfh_tma_ok(const pfh_ctx* c);
 bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
                           double* out, bool out_is_zero);
 bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const double* x, double* y);
+bool k3_res_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* u, const double* u0, double* R);
 bool k3_ch_crow_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, FieldRef xc, double* out);
 // out = [J(ulin) (xc, 0)]_mu for Cahn-Hilliard (scalar in, scalar out); false if no fast path applies
 bool k_ch_crow(pfh_ctx* c, const double* ulin, FieldRef xc, double* out);

@@ -30,6 +30,10 @@ struct ProbCH {
     const double s = ca + cb;
     a2 = -12.0 * rho; a1 = 12.0 * rho * s; a0 = -rho * (2.0 * s * s + 4.0 * ca * cb);
   }
+  PFH_HD void res_poly(double& a3, double& a2, double& a1, double& a0) const {  // g(c) = -f'(c)
+    const double s = ca + cb;
+    a3 = -4.0 * rho; a2 = 6.0 * rho * s; a1 = -2.0 * rho * (s * s + 2.0 * ca * cb); a0 = 2.0 * rho * s * ca * cb;
+  }
   PFH_HD static constexpr int in(int) { return 0; }
   PFH_HD static constexpr int out(int) { return 1; }
   double ca, cb, rho, kappa, Mob;
@@ -72,6 +76,10 @@ struct ProbBench6 {
   PFH_HD void jac_poly(double& a2, double& a1, double& a0) const {
     const double s = ca + cb;
     a2 = -12.0 * rho; a1 = 12.0 * rho * s; a0 = -rho * (2.0 * s * s + 4.0 * ca * cb);
+  }
+  PFH_HD void res_poly(double& a3, double& a2, double& a1, double& a0) const {  // g(c) = -f'(c)
+    const double s = ca + cb;
+    a3 = -4.0 * rho; a2 = 6.0 * rho * s; a1 = -2.0 * rho * (s * s + 2.0 * ca * cb); a0 = 2.0 * rho * s * ca * cb;
   }
   PFH_HD static constexpr int in(int) { return 0; }
   PFH_HD static constexpr int out(int) { return 1; }

@@ -370,6 +370,7 @@ void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
   int nprev = 0;
   for (int a = 0; a < c->nf; ++a) nprev += L.Mp[a] != 0.0;
   ProfScope ps(c, T_RESIDUAL, 8.0 * (2 * c->nf + nprev) * c->n_owned);
+  if (c->dim == 3 && k3_res_tma_launch(c, L, u, u0, R)) return;
   if (c->dim == 3) {
     PFH_DISPATCH3(c, (k3_op<P, false><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(
                          P(c->prob), c->m3, L, state_fields<P>(c, u, c->gU_lo, c->gU_hi), state_fields<P>(c, nullptr, nullptr, nullptr),

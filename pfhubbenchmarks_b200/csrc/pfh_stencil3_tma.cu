@@ -209,14 +209,17 @@ struct MapSet {
   CUtensorMap main[N], lo[N], hi[N];
 };
 
-// CROW = false: y = J(u) x (all NF rows).  CROW = true: only the nonlinear row, from its own
-// nonlinear column: out = (Mc[o][i] M + Kc[o][i] K) x_i + N'[x_i], o = P::out(0), i = P::in(0)
-// (the (kappa K + M_f'') block of the Cahn-Hilliard Jacobian that the Schur preconditioner applies).
-template <class P, bool CROW, int TX, int TY, int NT, int NS>
+// KIND 0: y = J(u) x (all NF rows).
+// KIND 1: only the nonlinear row, from its own nonlinear column: out = (Mc[o][i] M + Kc[o][i] K) x_i + N'[x_i],
+//         o = P::out(0), i = P::in(0) (the (kappa K + M_f'') block of the Cahn-Hilliard Jacobian for the Schur preconditioner).
+// KIND 2: residual R(u; u0): the operand fields are u, the extra ring fields hold u0 of the fields in(.) (for the
+//         problems served here the fields with a time derivative are the nonlinear inputs: c for Cahn-Hilliard).
+template <class P, int KIND, int TX, int TY, int NT, int NS>
 __global__ void __launch_bounds__(NT, 2)
-    k3_jac_tma(const __grid_constant__ MapSet<(CROW ? 1 : P::NF) + P::NIN> maps, P prob, Mesh3 m, LinCoefs L, int has_lo,
+    k3_jac_tma(const __grid_constant__ MapSet<(KIND == 1 ? 1 : P::NF) + P::NIN> maps, P prob, Mesh3 m, LinCoefs L, int has_lo,
                int has_hi, int zchunk, double* __restrict__ out) {
-  constexpr int NX = CROW ? 1 : P::NF;  // ring-buffered operand fields x, followed by the NIN linearisation fields u
+  constexpr bool CROW = KIND == 1, RES = KIND == 2;
+  constexpr int NX = CROW ? 1 : P::NF;  // ring-buffered operand fields x, followed by NIN fields (u for J.v, u0 for RES)
   constexpr int NFLD = NX + P::NIN;
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2 (16-byte aligned TMA box start)
   constexpr int STAGE_BYTES = W * H * 8;
@@ -270,9 +273,13 @@ __global__ void __launch_bounds__(NT, 2)
   double acc_hi[P::NOUT];
 #pragma unroll
   for (int o = 0; o < P::NOUT; ++o) acc_hi[o] = 0.0;
-  double a2 = 0.0, a1 = 0.0, a0 = 0.0;
-  if constexpr (P::QUARTIC) prob.jac_poly(a2, a1, a0);
+  double a3 = 0.0, a2 = 0.0, a1 = 0.0, a0 = 0.0;
+  if constexpr (P::QUARTIC) {
+    if (RES) prob.res_poly(a3, a2, a1, a0);
+    else prob.jac_poly(a2, a1, a0);
+  }
   const elem::QuarticJac qj(a2, a1, a0, m.detJ);
+  const elem::QuarticRes qr(a3, a2, a1, a0, m.detJ);
 
   // iteration `it` handles cube layer l = zb-1+it (between planes l and l+1) and writes plane l (it >= 1)
   for (int it = 0; it <= ze - zb; ++it) {
@@ -297,8 +304,9 @@ __global__ void __launch_bounds__(NT, 2)
         const int base = qy * W + qx + 1;
 #pragma unroll
         for (int f = 0; f < P::NIN; ++f) {
-          const double* u0 = stage(NX + f, it);
-          const double* u1 = stage(NX + f, it + 1);
+          // J.v: u = linearisation point (extra ring field), x = operand; residual: u = the operand itself
+          const double* u0 = RES ? xstage(P::in(f), it) : stage(NX + f, it);
+          const double* u1 = RES ? xstage(P::in(f), it + 1) : stage(NX + f, it + 1);
           const double* xa = xstage(P::in(f), it);
           const double* xb = xstage(P::in(f), it + 1);
 #pragma unroll
@@ -310,8 +318,13 @@ __global__ void __launch_bounds__(NT, 2)
             x[f][kk + 4] = xb[off];
           }
         }
-        if constexpr (P::QUARTIC) elem::cube_jac_quartic(qj, u[0], x[0], o8[0]);
-        else elem::cube_load<P, true>(prob, u, x, m.detJ, o8);
+        if constexpr (P::QUARTIC) {
+          if (RES) elem::cube_res_quartic(qr, u[0], o8[0]);
+          else elem::cube_jac_quartic(qj, u[0], x[0], o8[0]);
+        } else {
+          if (RES) elem::cube_load<P, false>(prob, u, x, m.detJ, o8);
+          else elem::cube_load<P, true>(prob, u, x, m.detJ, o8);
+        }
       }
 #pragma unroll
       for (int o = 0; o < P::NOUT; ++o)
@@ -368,6 +381,21 @@ __global__ void __launch_bounds__(NT, 2)
           }
 #pragma unroll
           for (int o = 0; o < P::NOUT; ++o) y[P::out(o)] += acc_hi[o] + lo[o];
+          if (RES) {  // - Mp_a M u0_a for the fields with a time derivative
+#pragma unroll
+            for (int f = 0; f < P::NIN; ++f) {
+              const double* S0 = stage(NX + f, it - 1);
+              const double* S1 = stage(NX + f, it);
+              const double* S2 = stage(NX + f, it + 1);
+              double v[PFH_NOFF3], ms0, ks0;
+              v[0] = S1[c]; v[1] = S1[c + 1]; v[2] = S1[c - 1]; v[3] = S1[c + W]; v[4] = S1[c - W];
+              v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
+              v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
+              v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
+              vtx::mk_sums3(row, v, ms0, ks0);
+              y[P::in(f)] -= L.Mp[P::in(f)] * ms0;
+            }
+          }
 #pragma unroll
           for (int aa = 0; aa < P::NF; ++aa) out[aa * m.n_owned + i] = y[aa];
         }
@@ -483,7 +511,7 @@ bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const 
   constexpr int stage = round_up((J_TX + 4) * (J_TY + 2) * 8, 128);
   constexpr int ncube = (J_TX + 1) * (J_TY + 1);
   constexpr size_t smem = (size_t)(P::NF + P::NIN) * J_NS * stage + (size_t)P::NOUT * 8 * (ncube | 1) * 8 + J_NS * sizeof(uint64_t);
-  auto kern = k3_jac_tma<P, false, J_TX, J_TY, J_NT, J_NS>;
+  auto kern = k3_jac_tma<P, 0, J_TX, J_TY, J_NT, J_NS>;
   static bool attr_set = false;
   if (!attr_set) {
     PFH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -514,7 +542,7 @@ bool k3_ch_crow_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, Fi
   constexpr int stage = round_up((J_TX + 4) * (J_TY + 2) * 8, 128);
   constexpr int ncube = (J_TX + 1) * (J_TY + 1);
   constexpr size_t smem = (size_t)(1 + P::NIN) * J_NS * stage + (size_t)P::NOUT * 8 * (ncube | 1) * 8 + J_NS * sizeof(uint64_t);
-  auto kern = k3_jac_tma<P, true, J_TX, J_TY, J_NT, J_NS>;
+  auto kern = k3_jac_tma<P, 1, J_TX, J_TY, J_NT, J_NS>;
   static bool attr_set = false;
   if (!attr_set) {
     PFH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -522,6 +550,44 @@ bool k3_ch_crow_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, Fi
   }
   const dim3 grid((m.nxv + J_TX - 1) / J_TX, (m.nyv + J_TY - 1) / J_TY, (m.nzl + J_ZCH - 1) / J_ZCH);
   kern<<<grid, J_NT, smem, c->stream>>>(maps, P(c->prob), m, L, lo, hi, J_ZCH, out);
+  PFH_CUDA(cudaGetLastError());
+  return true;
+}
+
+// R = R(u; u0, dt) for Cahn-Hilliard on the Kuhn mesh (ghosts: gU_* for u, gU0_* for u0)
+bool k3_res_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* u, const double* u0, double* R) {
+  if (!pfh_tma_ok(c) || c->prob.id != PFH_PROBLEM_CH || !aligned16(u) || !aligned16(u0)) return false;
+  using P = ProbCH;
+  const Mesh3& m = c->m3;
+  if ((m.n_owned & 1) || (c->nplane & 1)) return false;
+  for (int a = 0; a < P::NF; ++a) {  // the kernel subtracts Mp_a M u0_a only for the nonlinear input fields
+    bool is_in = false;
+    for (int f = 0; f < P::NIN; ++f) is_in |= P::in(f) == a;
+    if (L.Mp[a] != 0.0 && !is_in) return false;
+  }
+  const bool lo = c->nplane > 0 && c->cfg.rank > 0, hi = c->nplane > 0 && c->cfg.rank < c->cfg.nranks - 1;
+  MapSet<P::NF + P::NIN> maps;
+  for (int f = 0; f < P::NF + P::NIN; ++f) {
+    const bool isx = f < P::NF;
+    const int fld = isx ? f : P::in(f - P::NF);
+    const double* base = (isx ? u : u0) + (long long)fld * m.n_owned;
+    const double* glo = (isx ? c->gU_lo : c->gU0_lo);
+    const double* ghi = (isx ? c->gU_hi : c->gU0_hi);
+    maps.main[f] = make_map(base, m.nxv, m.nyv, m.nzl, J_TX + 4, J_TY + 2);
+    maps.lo[f] = lo ? make_map(glo + (long long)fld * c->nplane, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[f];
+    maps.hi[f] = hi ? make_map(ghi + (long long)fld * c->nplane, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[f];
+  }
+  constexpr int stage = round_up((J_TX + 4) * (J_TY + 2) * 8, 128);
+  constexpr int ncube = (J_TX + 1) * (J_TY + 1);
+  constexpr size_t smem = (size_t)(P::NF + P::NIN) * J_NS * stage + (size_t)P::NOUT * 8 * (ncube | 1) * 8 + J_NS * sizeof(uint64_t);
+  auto kern = k3_jac_tma<P, 2, J_TX, J_TY, J_NT, J_NS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const dim3 grid((m.nxv + J_TX - 1) / J_TX, (m.nyv + J_TY - 1) / J_TY, (m.nzl + J_ZCH - 1) / J_ZCH);
+  kern<<<grid, J_NT, smem, c->stream>>>(maps, P(c->prob), m, L, lo, hi, J_ZCH, R);
   PFH_CUDA(cudaGetLastError());
   return true;
 }

@@ -42,7 +42,7 @@ def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=
     else:
         n = (ncell[0] + 1) * (ncell[1] + 1) + ncell[0] * ncell[1]
     arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (U, X, U0, glo, ghi)]
-    out = np.zeros({0: nf * n, 1: nf * n, 2: 2, 3: 2 * n, 4: nf * n, 5: n}[mode])
+    out = np.zeros({0: nf * n, 1: nf * n, 2: 2, 3: 2 * n, 4: nf * n, 5: n, 6: n}[mode])
     icp = np.ascontiguousarray(icp if icp is not None else [0.0], dtype=np.float64)
     rc = lib.emul_run(mesh_kind, problem, nc, ln, _p(pr), len(pr), ctypes.c_double(dt), mode, z0, nzl,
                       _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(out), _p(icp))
@@ -51,6 +51,6 @@ def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=
         return out.reshape(nf, n)
     if mode == 3:
         return out.reshape(2, n)
-    if mode == 5:
+    if mode in (5, 6):
         return out
     return out

@@ -83,6 +83,25 @@ int run(const Setup& S, const ProblemParams& pp, double dt, int mode, const doub
         }
     if (mode == 2) { out[0] = E; out[1] = Mm; }
     if constexpr (P::QUARTIC) {
+      if (mode == 6) {  // nonlinear residual load only, cube-centric scatter with the low-flop routine
+        double a3, a2, a1, a0;
+        prob.res_poly(a3, a2, a1, a0);
+        const elem::QuarticRes qr(a3, a2, a1, a0, m.detJ);
+        for (long long i = 0; i < n; ++i) out[i] = 0.0;
+        const double* cu = U + P::in(0) * n;
+        for (int cz = 0; cz < m.nzv - 1; ++cz)
+          for (int cy = 0; cy < m.nyv - 1; ++cy)
+            for (int cxi = 0; cxi < m.nxv - 1; ++cxi) {
+              double c8[8], o8[8] = {0};
+              long long idx[8];
+              for (int l = 0; l < 8; ++l) {
+                idx[l] = (long long)(cz + (l >> 2)) * m.nxy + (long long)(cy + ((l >> 1) & 1)) * m.nxv + cxi + (l & 1);
+                c8[l] = cu[idx[l]];
+              }
+              elem::cube_res_quartic(qr, c8, o8);
+              for (int l = 0; l < 8; ++l) out[idx[l]] += o8[l];
+            }
+      }
       if (mode == 5) {  // nonlinear Jacobian block only, cube-centric scatter with the low-flop routine
         double a2, a1, a0;
         prob.jac_poly(a2, a1, a0);

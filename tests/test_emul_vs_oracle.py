@@ -96,3 +96,14 @@ def test_low_flop_cube_jacobian_routine():
     dg = D.prob.dg(D.V.at_quad(U))
     ref = D.V.weighted_mass(dg[1, 0]) @ X[0]
     assert rel_max(got, ref) < 1e-13
+
+
+def test_low_flop_cube_residual_routine():
+    """elem::cube_res_quartic == int phi_i g(c_h), g = -f'(c), of the oracle."""
+    rng = np.random.default_rng(5)
+    ncell, length = (4, 5, 3), (8.0, 7.5, 6.0)
+    D = discretization("b13d", ncell, length)
+    U = D.prob.ic(D.mesh) + 0.1 * rng.standard_normal((2, D.nv))
+    got = emul.run(3, 1, list(ncell), list(length), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, 6, U=U, nf=2)
+    ref = D.V.load(D.prob.g(D.V.at_quad(U)))[1]
+    assert rel_max(got, ref) < 1e-13
