@@ -244,3 +244,32 @@ def test_large_grid_properties():
             assert E < E0 and abs(M / M0 - 1) < 1e-12
             E0 = E
         ctx.close()
+
+
+def test_bench1_100_steps_fields_and_energy_vs_oracle():
+    """North-star bar at its stated horizon: 100 backward-Euler steps of bench1 (reference mesh, dt list of SURVEY
+    section 8(d): 0.1, 0.2, 0.4, 0.8, 1.6, 1.6, ...), CUDA vs the exactly converged oracle trajectory:
+    concentration within 1e-8 relative L2 and free energy within 1e-6 relative at EVERY step."""
+    eng = _engine()
+    ncell, length = REFERENCE_MESH["bench1"]
+    D = discretization("bench1", ncell, length)
+    ctx = eng.Context("bench1", ncell, length)
+    nv = ctx.n_owned
+    w = ctx.initial_condition()
+    u = D.prob.ic(D.mesh)
+    worst_c = worst_e = 0.0
+    for k in range(100):
+        dt = min(0.1 * 2 ** k, 1.6) if k < 6 else 1.6
+        w0 = w.clone()
+        ctx.dt = dt
+        rep = ctx.newton_solve(w, w0, absolute_tolerance=1e-10, krylov_rtol=1e-8, maximum_iterations=30)
+        assert rep["converged"], (k, rep)
+        u, n, ok = D.solve_step(u, u, dt, atol=1e-10)
+        assert ok, k
+        E, M = ctx.energy(w)
+        worst_c = max(worst_c, rel_l2(w[:nv].cpu().numpy(), u[0]))
+        worst_e = max(worst_e, abs(E / D.energy(u) - 1))
+        assert abs(M / D.mass(u) - 1) < 1e-11
+    print("100 steps: worst rel L2(c) %.2e, worst rel energy %.2e" % (worst_c, worst_e))
+    assert worst_c < 1e-8 and worst_e < 1e-6
+    ctx.close()
