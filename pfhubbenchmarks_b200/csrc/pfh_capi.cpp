@@ -381,6 +381,8 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->launches = 0;
   } else if (k == "overlap") {
     c->overlap = value != 0.0;
+  } else if (k == "scalar_variant") {
+    c->scalar_variant = (int)value;
   } else if (k == "use_tma") {
     c->use_tma = value != 0.0;
   } else {

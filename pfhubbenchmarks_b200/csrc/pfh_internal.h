@@ -172,6 +172,7 @@ struct pfh_ctx {
   double t_bytes[PFH_N_TIMERS] = {0};  // algorithmic bytes of the launches timed above
   long long t_n[PFH_N_TIMERS] = {0};
   int scalar_bc = 0;    // 2-D scalar operators: 1 = Dirichlet (identity) rows on the corner vertices of x = 0 and x = Lx
+  int scalar_variant = 0;  // tile/ring variant of the TMA scalar kernel (tuning; pfh_set_option "scalar_variant")
   bool use_tma = true;  // 3-D fast path: TMA-staged kernels (pfh_stencil3_tma.cu); false = gather kernels only
 };
 

@@ -223,17 +223,16 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
     const double dt = c->dt, alpha = c->pc_alpha;
     const double *r1 = r, *r2 = r + n;
     double *S0 = c->S[0], *S1 = c->S[1], *S2 = c->S[2], *S3 = c->S[3], *S4 = c->S[4];
-    // t = M^-1 r2
-    cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, r2, S0, S1);
+    // t = M^-1 r2   (block upper-triangular variant: t IS dmu, so it is solved straight into z_mu)
+    double* T = o.pc_variant == 1 ? z + n : S0;
+    cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, r2, T, S1);
     // q = dt r1 - dt Mob K t
-    k_lin_apply(c, 0.0, -dt * L.Mob, scalar_ref(c, S0), dt, r1, S2);
+    k_lin_apply(c, 0.0, -dt * L.Mob, scalar_ref(c, T), dt, r1, S2);
     // dc = A^-1 M A^-1 q,  A = M + alpha K
     cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, S3, S4);
     k_lin_apply(c, 1.0, 0.0, scalar_ref(c, S3), 0.0, nullptr, S2);
     cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, z, S4);
-    if (o.pc_variant == 1) {
-      v_copy(c, z + n, S0, n);  // block upper-triangular: dmu = t
-    } else {
+    if (o.pc_variant != 1) {
       // dmu = t + M^-1 (kappa K + M_f'') dc = t - M^-1 [J (dc, 0, ..)]_mu
       if (k_ch_crow(c, c->jac_point, scalar_ref(c, z), S2)) {
         // fused (mu, c) block apply: reads c and dc only, writes the mu row only

@@ -72,7 +72,7 @@ struct Coef15 {
 };
 
 template <int MODE, int TX, int TY, int RY, int NS>
-__global__ void __launch_bounds__(TX*(TY / RY), 4)
+__global__ void __launch_bounds__(TX*(TY / RY))
     k3_scalar_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_lo,
                   const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_r,
                   const __grid_constant__ CUtensorMap tm_o, Mesh3 m, int has_lo, int has_hi, int has_r, int has_o, int zchunk,
@@ -450,6 +450,51 @@ bool pfh_tma_ok(const pfh_ctx* c) {
   return c->dim == 3 && c->use_tma && (c->m3.nxv % 2) == 0 && c->m3.nxv >= 8 && c->m3.nyv >= 4 && c->m3.nzl >= 2;
 }
 
+struct ScalarArgs {
+  CUtensorMap tm, tl, th, tr, to;
+  Mesh3 m;
+  bool lo, hi, has_r, has_o;
+  int zpart;
+  double am, ak;
+  Coef15 cI;
+  double a, b, bdI;
+  FieldRef in;
+  const double* r;
+  double* out;
+  int mode;
+};
+
+template <int TX, int TY, int RY, int NS, int ZCH>
+bool scalar_launch(pfh_ctx* c, ScalarArgs& A) {
+  const Mesh3& m = A.m;
+  A.tm = make_map(A.in.p, m.nxv, m.nyv, m.nzl, TX + 4, TY + 2);
+  A.tl = A.lo ? make_map(A.in.glo, m.nxv, m.nyv, 1, TX + 4, TY + 2) : A.tm;
+  A.th = A.hi ? make_map(A.in.ghi, m.nxv, m.nyv, 1, TX + 4, TY + 2) : A.tm;
+  A.tr = A.has_r ? make_map(A.r, m.nxv, m.nyv, m.nzl, TX, TY) : A.tm;
+  A.to = A.has_o ? make_map(A.out, m.nxv, m.nyv, m.nzl, TX, TY) : A.tm;
+  const int zp = A.zpart;
+  const int nz_part = zp == 1 ? 2 * ZCH : (zp == 2 ? m.nzl - 2 : m.nzl);  // zpart 1: gridDim.z = 2
+  if (nz_part <= 0) return true;
+  const dim3 grid((m.nxv + TX - 1) / TX, (m.nyv + TY - 1) / TY, (nz_part + ZCH - 1) / ZCH);
+  const dim3 block(TX, TY / RY);
+  constexpr int stage = round_up((TX + 4) * (TY + 2) * 8, 128) + 2 * TX * TY * 8;
+  constexpr size_t smem = NS * stage + NS * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<0, TX, TY, RY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<2, TX, TY, RY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  if (A.mode == 0)
+    k3_scalar_tma<0, TX, TY, RY, NS><<<grid, block, smem, c->stream>>>(A.tm, A.tl, A.th, A.tr, A.to, m, A.lo, A.hi, A.has_r, 0, ZCH, zp, A.am,
+                                                                      A.ak, A.cI, A.a, A.b, 0.0, A.out);
+  else
+    k3_scalar_tma<2, TX, TY, RY, NS><<<grid, block, smem, c->stream>>>(A.tm, A.tl, A.th, A.tr, A.to, m, A.lo, A.hi, A.has_r, A.has_o, ZCH, zp,
+                                                                      A.am, A.ak, A.cI, A.a, A.b, A.bdI, A.out);
+  PFH_CUDA(cudaGetLastError());
+  return true;
+}
+
 // MODE 0 (lin_apply) and MODE 2 (Chebyshev sweep) through the TMA kernel; returns false if the
 // operands do not qualify (caller falls back to the gather kernel)
 bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
@@ -460,34 +505,18 @@ bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, 
   if ((lo && !aligned16(in.glo)) || (hi && !aligned16(in.ghi))) return false;
   const bool has_r = (mode == 2 || a != 0.0) && r != nullptr;
   const bool has_o = mode == 2 && !out_is_zero;
-  const CUtensorMap tm = make_map(in.p, m.nxv, m.nyv, m.nzl, S_TX + 4, S_TY + 2);
-  const CUtensorMap tl = lo ? make_map(in.glo, m.nxv, m.nyv, 1, S_TX + 4, S_TY + 2) : tm;
-  const CUtensorMap th = hi ? make_map(in.ghi, m.nxv, m.nyv, 1, S_TX + 4, S_TY + 2) : tm;
-  const CUtensorMap tr = has_r ? make_map(r, m.nxv, m.nyv, m.nzl, S_TX, S_TY) : tm;
-  const CUtensorMap to = has_o ? make_map(out, m.nxv, m.nyv, m.nzl, S_TX, S_TY) : tm;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
   Coef15 cI;
   for (int o = 0; o < PFH_NOFF3; ++o) cI.c[o] = am * m.mI[o] + (o < PFH_NKOFF3 ? ak * m.kI[o] : 0.0);
-  const int zp = c->zpart;
-  const int nz_part = zp == 1 ? 2 * S_ZCH : (zp == 2 ? m.nzl - 2 : m.nzl);  // zpart 1: gridDim.z = 2
-  if (nz_part <= 0) return true;
-  const dim3 grid((m.nxv + S_TX - 1) / S_TX, (m.nyv + S_TY - 1) / S_TY, (nz_part + S_ZCH - 1) / S_ZCH);
-  const dim3 block(S_TX, S_TY / S_RY);
-  constexpr int stage = round_up((S_TX + 4) * (S_TY + 2) * 8, 128) + 2 * S_TX * S_TY * 8;
-  constexpr size_t smem = S_NS * stage + S_NS * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  ScalarArgs A{tm, tm, tm, tm, tm, m, lo, hi, has_r, has_o, c->zpart, am, ak, cI, a, b, b / cI.c[0], in, r, out, mode};
+  switch (c->scalar_variant) {
+    case 1: return scalar_launch<64, 8, 2, 5, 32>(c, A);
+    case 2: return scalar_launch<64, 8, 2, 4, 64>(c, A);
+    case 3: return scalar_launch<64, 16, 4, 3, 32>(c, A);
+    case 4: return scalar_launch<64, 8, 2, 3, 32>(c, A);
+    default: return scalar_launch<S_TX, S_TY, S_RY, S_NS, S_ZCH>(c, A);
   }
-  if (mode == 0)
-    k3_scalar_tma<0, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, tr, to, m, lo, hi, has_r, 0, S_ZCH, zp, am, ak, cI,
-                                                                              a, b, 0.0, out);
-  else
-    k3_scalar_tma<2, S_TX, S_TY, S_RY, S_NS><<<grid, block, smem, c->stream>>>(tm, tl, th, tr, to, m, lo, hi, has_r, has_o, S_ZCH, zp, am,
-                                                                              ak, cI, a, b, b / cI.c[0], out);
-  PFH_CUDA(cudaGetLastError());
-  return true;
 }
 
 // y = J(ulin) x for Cahn-Hilliard on the Kuhn mesh; ghosts: gX_* for x, gU_* for ulin

@@ -55,7 +55,8 @@ def main():
     nlparams["krylov_solver"]["error_on_nonconvergence"] = False
     # b13d.py writes results/bench1_out.csv (b13d.py:200)
     return time_loop(problem, solver, w_ic, 1e-1, 1e-2, args.end_time, os.path.join(args.outdir, "bench1_out.csv"),
-                     "time,total_free_energy,total_solute", args.max_steps, args.quiet)
+                     "time,total_free_energy,total_solute", args.max_steps, args.quiet,
+                     save_dir=os.path.join(args.outdir, os.path.basename(__file__)[:-3]) if args.save_solution else None)
 
 
 if __name__ == "__main__":

@@ -38,7 +38,8 @@ def main():
     nlparams["krylov_solver"]["maximum_iterations"] = 1000
     # time integration + CSV (bench1.py:128-217): dt0 = 1e-1, dt_min = 1e-2
     return time_loop(problem, solver, w_ic, 1e-1, 1e-2, args.end_time, os.path.join(args.outdir, "bench1", "stats.csv"),
-                     "time,total_free_energy,total_solute", args.max_steps, args.quiet)
+                     "time,total_free_energy,total_solute", args.max_steps, args.quiet,
+                     save_dir=os.path.join(args.outdir, os.path.basename(__file__)[:-3]) if args.save_solution else None)
 
 
 if __name__ == "__main__":

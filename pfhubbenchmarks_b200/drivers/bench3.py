@@ -29,7 +29,8 @@ def main():
     nlparams["krylov_solver"]["maximum_iterations"] = 1000
     # dt0 = 1e-2, dt_min = 1e-4 (bench3.py time-integration block)
     return time_loop(problem, solver, w_ic, 1e-2, 1e-4, args.end_time, os.path.join(args.outdir, "bench3_out.csv"),
-                     "time,total_free_energy,solid_fraction", args.max_steps, args.quiet, abort_on_negative_energy=True)
+                     "time,total_free_energy,solid_fraction", args.max_steps, args.quiet, abort_on_negative_energy=True,
+                     save_dir=os.path.join(args.outdir, 'bench3') if args.save_solution else None, save_fields=(0, 1))
 
 
 if __name__ == "__main__":

@@ -29,7 +29,8 @@ def main():
     nlparams["krylov_solver"]["maximum_iterations"] = 5000
     # dt0 = 1e-2, dt_min = 1e-4 (bench6.py time-integration block)
     return time_loop(problem, solver, w_ic, 1e-2, 1e-4, args.end_time, os.path.join(args.outdir, "bench6_out.csv"),
-                     "time,total_free_energy,total_solute", args.max_steps, args.quiet)
+                     "time,total_free_energy,total_solute", args.max_steps, args.quiet,
+                     save_dir=os.path.join(args.outdir, os.path.basename(__file__)[:-3]) if args.save_solution else None)
 
 
 if __name__ == "__main__":

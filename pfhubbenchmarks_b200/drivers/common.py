@@ -24,6 +24,7 @@ def parse_args(name, end_time):
     ap.add_argument("--reference-dir", default=os.environ.get("PFHUB_REFERENCE", "/root/reference"))
     ap.add_argument("--atol", type=float, default=1e-6, help="snes absolute_tolerance (reference: 1e-6)")
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--save-solution", action="store_true", help="write <outdir>/<name>/<field>.pvd + VTU per step (bench1.py:9,116-119,191)")
     return ap.parse_args()
 
 
@@ -38,7 +39,7 @@ def run_fenics(args, script):
 
 
 def time_loop(problem, solver, w_ic, dt0, dt_min, end_time, csv_path, header, max_steps=0, quiet=False, max_retries=20,
-              abort_on_negative_energy=False):
+              abort_on_negative_energy=False, save_dir=None, save_fields=(0,)):
     w, w0, dt = problem.w, problem.w0, problem.dt
     rank0 = df.MPI.rank() == 0
     t = df.Constant(0.0)
@@ -46,6 +47,13 @@ def time_loop(problem, solver, w_ic, dt0, dt_min, end_time, csv_path, header, ma
     w0.interpolate(w_ic)
     benchmark_output = []
     iteration_count = 0
+    files = {}
+    if save_dir and rank0 and problem.ctx.nranks == 1:      # field dumps: `cfile << (c, t)` (b13d.py:179, bench2.py:269-274)
+        from .. import io
+        os.makedirs(save_dir, exist_ok=True)
+        names = problem.ctx.field_names
+        files = {k: io.File(os.path.join(save_dir, ('conc' if names[k] == 'c' else names[k]) + '.pvd'), 'ascii', mesh=problem.mesh,
+                            name='f_%d' % k) for k in save_fields}
     dt.assign(dt0)
     t1 = time.time()
     while float(t) < end_time + df.DOLFIN_EPS:
@@ -73,6 +81,8 @@ def time_loop(problem, solver, w_ic, dt0, dt_min, end_time, csv_path, header, ma
             dt.assign(max(0.5 * float(dt), dt_min))
         F_total, C_total = df.diagnostics(problem)            # analysis
         benchmark_output.append([float(t), F_total, C_total])
+        for k, fh in files.items():
+            fh << (w.split()[k].cpu().numpy(), float(t))
         if rank0 and not quiet:
             print("Converged in %d Newton iterations; C_total: %r TFE: %r" % (niters, C_total, F_total))
         if abort_on_negative_energy and F_total < 0.0:        # bench3.py:254-258

@@ -1,0 +1,121 @@
+"""Field output in the formats the reference drivers write ("next" row N2 of SURVEY.md section 8f).
+
+* `File(path + ".pvd") << (c, t)`  (dolfin/bench2.py:178-182,269-274; b13d.py:104-106,179): a PVD collection
+  plus one VTU per step, `format="ascii"` with 17 significant digits (as committed under results/bench2,
+  results/bench6) or `format="binary"` with vtkZLibDataCompressor (as committed under results/bench1).
+* Points / connectivity follow DOLFIN's structured meshes: crossed rectangle (corners x-fastest, then cell
+  centres; 4 triangles per square) and BoxMesh (6 Kuhn tetrahedra per cube).
+Host-side only; fields arrive as numpy arrays (one value per mesh vertex, DOLFIN vertex order).
+"""
+import base64
+import os
+import struct
+import zlib
+
+import numpy as np
+
+
+def crossed_mesh(nx, ny, Lx, Ly):
+    """(points (n,3), cells (m,3)) of df.RectangleMesh(Point(0,0), Point(Lx,Ly), nx, ny, 'crossed')."""
+    hx, hy = Lx / nx, Ly / ny
+    jx, jy = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")
+    corners = np.stack([jx.ravel() * hx, jy.ravel() * hy, np.zeros(jx.size)], axis=1)
+    cx, cy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    centres = np.stack([(cx.ravel() + 0.5) * hx, (cy.ravel() + 0.5) * hy, np.zeros(cx.size)], axis=1)
+    v0 = (cy * (nx + 1) + cx).ravel()
+    vm = (nx + 1) * (ny + 1) + (cy * nx + cx).ravel()
+    tri = np.stack([v0, v0 + 1, vm, v0, v0 + nx + 1, vm, v0 + 1, v0 + nx + 2, vm, v0 + nx + 1, v0 + nx + 2, vm], axis=1)
+    return np.concatenate([corners, centres]), tri.reshape(-1, 3)
+
+
+_KUHN = ((0, 1, 3, 7), (0, 1, 7, 5), (0, 5, 7, 4), (0, 3, 2, 7), (0, 6, 4, 7), (0, 2, 6, 7))
+
+
+def box_mesh(nx, ny, nz, Lx, Ly, Lz):
+    """(points, cells (m,4)) of df.BoxMesh(Point(0,0,0), Point(Lx,Ly,Lz), nx, ny, nz)."""
+    kz, ky, kx = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    pts = np.stack([kx.ravel() * (Lx / nx), ky.ravel() * (Ly / ny), kz.ravel() * (Lz / nz)], axis=1)
+    cz, cy, cx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    sy, sz = nx + 1, (nx + 1) * (ny + 1)
+    v0 = (cz * sz + cy * sy + cx).ravel()
+    loc = [v0 + (l & 1) + ((l >> 1) & 1) * sy + (l >> 2) * sz for l in range(8)]
+    cells = np.stack([np.stack([loc[a] for a in t], axis=1) for t in _KUHN], axis=1).reshape(-1, 4)
+    return pts, cells
+
+
+def mesh_of(mesh):
+    """Points / cells of a pfhubbenchmarks_b200.api.Mesh."""
+    if mesh.kind == "crossed2d":
+        return crossed_mesh(mesh.ncell[0], mesh.ncell[1], mesh.length[0], mesh.length[1])
+    return box_mesh(*mesh.ncell, *mesh.length)
+
+
+def _b64_zlib(arr, block=32768):
+    raw = np.ascontiguousarray(arr).tobytes()
+    blocks = [raw[i:i + block] for i in range(0, len(raw), block)] or [b""]
+    comp = [zlib.compress(b) for b in blocks]
+    header = struct.pack("<%dI" % (3 + len(comp)), len(blocks), block, len(blocks[-1]) if len(blocks[-1]) != block else block,
+                         *[len(cb) for cb in comp])
+    if len(blocks[-1]) == block:   # VTK convention: last-block size 0 means "full block"
+        header = struct.pack("<%dI" % (3 + len(comp)), len(blocks), block, 0, *[len(cb) for cb in comp])
+    return base64.b64encode(header).decode() + base64.b64encode(b"".join(comp)).decode()
+
+
+def _fmt(arr, binary):
+    if binary:
+        return _b64_zlib(arr)
+    if arr.dtype.kind == "f":
+        return "  ".join(" ".join("%.17g" % v for v in row) for row in np.atleast_2d(arr)) + "  "
+    return "  ".join(" ".join(str(int(v)) for v in row) for row in np.atleast_2d(arr)) + "  "
+
+
+def write_vtu(path, points, cells, values, name="f", binary=False):
+    """One scalar per vertex on a simplicial mesh, DOLFIN VTU layout (Points, connectivity, offsets, types, PointData)."""
+    points = np.asarray(points, dtype=np.float64)
+    cells = np.asarray(cells)
+    values = np.asarray(values, dtype=np.float64).ravel()
+    assert values.size == points.shape[0]
+    nper = cells.shape[1]
+    vtk_type = 5 if nper == 3 else 10
+    fmt = 'format="binary"' if binary else 'format="ascii"'
+    comp = ' byte_order="LittleEndian" compressor="vtkZLibDataCompressor"' if binary else ""
+    offsets = (np.arange(cells.shape[0], dtype=np.uint32) + 1) * nper
+    types = np.full(cells.shape[0], vtk_type, dtype=np.uint8)
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid"  version="0.1" %s>\n<UnstructuredGrid>\n' % comp)
+        f.write('<Piece  NumberOfPoints="%d" NumberOfCells="%d">\n<Points>\n' % (points.shape[0], cells.shape[0]))
+        f.write('<DataArray  type="Float64"  NumberOfComponents="3"  %s>%s</DataArray>\n</Points>\n<Cells>\n' % (fmt, _fmt(points, binary)))
+        f.write('<DataArray  type="UInt32"  Name="connectivity"  %s>%s</DataArray>\n' % (fmt, _fmt(cells.astype(np.uint32), binary)))
+        f.write('<DataArray  type="UInt32"  Name="offsets"  %s>%s</DataArray>\n' % (fmt, _fmt(offsets[None, :], binary)))
+        f.write('<DataArray  type="UInt8"  Name="types"  %s>%s</DataArray>\n</Cells>\n' % (fmt, _fmt(types[None, :], binary)))
+        f.write('<PointData  Scalars="%s"> \n<DataArray  type="Float64"  Name="%s"  %s>%s</DataArray>\n</PointData> \n' % (
+            name, name, fmt, _fmt(values[None, :] if binary else values[:, None], binary)))
+        f.write("</Piece>\n</UnstructuredGrid>\n</VTKFile>")
+
+
+class File:
+    """`cfile = File(filename + ".pvd", "compressed")` ; `cfile << (c, t)`  (dolfin/b13d.py:106,179)."""
+
+    def __init__(self, path, mode="ascii", mesh=None, name="f"):
+        assert path.endswith(".pvd")
+        self.path, self.binary, self.mesh, self.name = path, mode == "compressed", mesh, name
+        self.entries = []
+        self._geom = None
+
+    def write(self, values, t):
+        if self._geom is None:
+            self._geom = mesh_of(self.mesh)
+        stem = os.path.basename(self.path)[:-4]
+        fn = "%s%06d.vtu" % (stem, len(self.entries))
+        write_vtu(os.path.join(os.path.dirname(self.path) or ".", fn), self._geom[0], self._geom[1], values, self.name, self.binary)
+        self.entries.append((float(t), fn))
+        with open(self.path, "w") as f:
+            f.write('<?xml version="1.0"?>\n<VTKFile type="Collection" version="0.1">\n  <Collection>\n')
+            for (tt, name) in self.entries:
+                f.write('    <DataSet timestep="%s" part="0" file="%s" />\n' % (repr(tt), name))
+            f.write("  </Collection>\n</VTKFile>\n")
+
+    def __lshift__(self, pair):
+        values, t = pair
+        self.write(values, float(t))
+        return self

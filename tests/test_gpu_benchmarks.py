@@ -125,3 +125,22 @@ def test_bench1_driver_reproduces_reference_csv(golden, tmp_path):
     print("driver rows matching the reference CSV time for time:", prefix, "of", len(rows))
     assert np.all(np.diff(rows[:, 1]) < 0)                     # energy decays
     problem.ctx.close()
+
+
+def test_driver_cli_writes_csv_and_fields(tmp_path):
+    """`python -m pfhubbenchmarks_b200.drivers.bench1 --max-steps 3 --save-solution`: CSV + PVD/VTU come out, and the
+    dumped concentration of step 1 equals the FEniCS snapshot results/bench1/conc000000.vtu to solver tolerance."""
+    import subprocess
+    import sys
+    from oracle import golden_io
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pfhubbenchmarks_b200.drivers.bench1", "--max-steps", "3", "--save-solution",
+                        "--outdir", str(tmp_path), "--quiet", "--atol", "1e-10"], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(str(tmp_path / "bench1" / "stats.csv"), delimiter=",", skiprows=1)
+    assert rows.shape == (3, 3) and np.allclose(rows[:, 0], [0.1, 0.3, 0.7])
+    entries = golden_io.read_pvd(str(tmp_path / "bench1" / "conc.pvd"))
+    assert len(entries) == 3
+    c1 = golden_io.read_vtu_scalar(str(tmp_path / "bench1" / entries[0][1]))
+    g = np.load(os.path.join(root, "tests", "golden", "bench1_fields.npz"))
+    assert rel_l2(c1, g["c"][0]) < 1e-9
