@@ -29,7 +29,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # rank 0 must print exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-os.environ["NCCL_DEBUG"] = os.environ.get("PFH_NCCL_DEBUG", "WARN")
+os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its version line on stdout for VERSION/WARN/INFO
+if os.environ.get("PFH_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = os.environ["PFH_NCCL_DEBUG"]
 
 METRIC = "CH DOF*Newton-steps/s (b13d 3-D Cahn-Hilliard, implicit step)"
 UNIT = "DOF*Newton-steps/s"
@@ -207,30 +209,46 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, inputs resident in HBM ----
-    ctx.timers(reset=True)
-    ctx.set_option("profiling", 1)
-    ctx.set_option("reset_launch_count", 0)
+    # Per-launch CUDA events (two cudaEventRecord per kernel, ~8 us) are kept inside the timed region only when they
+    # are negligible against the kernels (vectors larger than L2); for small, launch-bound grids the timed region runs
+    # unprofiled and the kernel table comes from an identical second pass.
+    bytes_vec = 8 * 2 * ctx.n_owned
+    profile_in_timed = bytes_vec > 2.6e8
+
+    def timed_pass(profile):
+        w.copy_(start_host, non_blocking=False)
+        torch.cuda.synchronize()
+        ctx.timers(reset=True)
+        ctx.set_option("profiling", 1 if profile else 0)
+        ctx.set_option("reset_launch_count", 0)
+        reps = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(args.steps):
+            reps.append(one_step(dts[args.warmup + k]))
+        e1.record(stream)
+        barrier()
+        t_ms = e0.elapsed_time(e1)
+        n_launch = ctx.launch_count()
+        tm = ctx.timers(reset=True)
+        ctx.set_option("profiling", 0)
+        return t_ms, n_launch, tm, reps
+
     sampler = ClockSampler(local)
     sampler.start()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for k in range(args.steps):
-        rep = one_step(dts[args.warmup + k])
-        reports.append(rep)
-    ev1.record(stream)
-    barrier()
+    ms, launches, timers, reports = timed_pass(profile_in_timed)
     clocks = sampler.finish()
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count()
-    timers = ctx.timers(reset=True)
-    ctx.set_option("profiling", 0)
+    if not profile_in_timed:
+        ms_prof, _, timers, _ = timed_pass(True)
+    else:
+        ms_prof = ms
     assert all(r["converged"] for r in reports), reports
     newton = sum(r["niters"] for r in reports)
     krylov = sum(r["krylov_its"] for r in reports)
 
     # ---- e2e: the same K steps through the host-buffer plugin call ----
-    h_w = start_host.numpy().copy() if False else start_host.numpy()
+    h_w = start_host.numpy()
     h_w0 = torch.empty(w.shape, dtype=w.dtype, pin_memory=True).numpy()
     e2e_ms, e2e_newton = 0.0, 0
     for k in range(args.steps):
@@ -244,7 +262,6 @@ def run_b200(args):
         e2e_ms += a.elapsed_time(b)
         e2e_newton += rep["niters"]
         assert rep["converged"], rep
-    bytes_vec = 8 * 2 * ctx.n_owned
 
     def allmax(x):
         if world == 1:
@@ -277,15 +294,16 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            traffic = json.load(open(tpath)).get(("b13d_kuhn3d_%d" if args.workload == "b13d" else "bench1_crossed2d_%d") % args.grid, {}).get(dom) if world == 1 else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": d["bytes"] / d["launches"],
-                "ms_per_launch": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms}
+                "ms_per_launch": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms_prof,
+                "timed_region_profiled": bool(profile_in_timed)}
     kernels = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                    "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
-                   "share": round(v["ms"] / ms, 4)} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+                   "share": round(v["ms"] / ms_prof, 4)} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
 
     line = None
     if rank == 0:
@@ -304,7 +322,7 @@ def run_b200(args):
                 "gpu_launches": launches_all, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * bytes_vec * world,
                         "d2h_bytes_per_step": bytes_vec * world + 32, "ms_per_step": e2e_ms / args.steps},
-                "roofline": roofline, "kernels": kernels, "kernel_time_coverage": total_fam_ms / ms}
+                "roofline": roofline, "kernels": kernels, "kernel_time_coverage": total_fam_ms / ms_prof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

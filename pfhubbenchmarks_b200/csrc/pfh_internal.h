@@ -129,6 +129,7 @@ struct pfh_ctx {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr;
   bool overlap = true;
+  const double* gS_prefetched = nullptr;  // scalar field whose ghost planes are already travelling into gS (ev_halo)
   // z-range restriction of the next scalar-operator launches: 0 all planes, 1 boundary planes {0, nzl-1}, 2 interior [1, nzl-1)
   int zpart = 0;
   double* d_tables = nullptr;

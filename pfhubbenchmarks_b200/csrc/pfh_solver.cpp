@@ -28,7 +28,15 @@ void s_exchange_state(pfh_ctx* c, const double* u, double* glo, double* ghi) {
 }
 
 static FieldRef scalar_ref(pfh_ctx* c, const double* p) {
-  if (c->cfg.nranks > 1) comm_halo(c, p, 0, 1, c->gS_lo, c->gS_hi);
+  if (c->cfg.nranks > 1) {
+    if (c->gS_prefetched == p) {
+      // the producer (cheb_solve) already sent these ghost planes on comm_stream: just order the consumer after them
+      PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+    } else {
+      comm_halo(c, p, 0, 1, c->gS_lo, c->gS_hi);
+    }
+  }
+  c->gS_prefetched = nullptr;
   return FieldRef{p, c->gS_lo, c->gS_hi};
 }
 
@@ -99,7 +107,7 @@ double lmin_estimate(const pfh_ctx* c, double am, double ak, const std::vector<d
 
 // result is guaranteed to land in `target`; `tmp` is scratch of the same size
 void cheb_solve(pfh_ctx* c, double am, double ak, double lmin, double lmax, int nsweeps, const double* r, double* target,
-                double* tmp) {
+                double* tmp, bool consumer_needs_ghosts = false) {
   const std::vector<ChebCoef> cf = cheb_coeffs(lmin, lmax, nsweeps);
   double* cur = ((nsweeps - 1) % 2 == 0) ? target : tmp;
   double* prev = (cur == target) ? tmp : target;
@@ -128,6 +136,13 @@ void cheb_solve(pfh_ctx* c, double am, double ak, double lmin, double lmax, int 
       c->zpart = 1;
       k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, k == 1);
       PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+      if (k == nsweeps - 1 && consumer_needs_ghosts) {
+        // the result's slab-boundary planes are final: ship its ghost planes now, under the last interior launch
+        PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+        comm_halo(c, prev, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
+        PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+        c->gS_prefetched = prev;
+      }
       c->zpart = 2;
       k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, k == 1);
       std::swap(cur, prev);
@@ -225,13 +240,13 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
     double *S0 = c->S[0], *S1 = c->S[1], *S2 = c->S[2], *S3 = c->S[3], *S4 = c->S[4];
     // t = M^-1 r2   (block upper-triangular variant: t IS dmu, so it is solved straight into z_mu)
     double* T = o.pc_variant == 1 ? z + n : S0;
-    cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, r2, T, S1);
+    cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, r2, T, S1, true);
     // q = dt r1 - dt Mob K t
     k_lin_apply(c, 0.0, -dt * L.Mob, scalar_ref(c, T), dt, r1, S2);
     // dc = A^-1 M A^-1 q,  A = M + alpha K
-    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, S3, S4);
+    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, S3, S4, true);
     k_lin_apply(c, 1.0, 0.0, scalar_ref(c, S3), 0.0, nullptr, S2);
-    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, z, S4);
+    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, z, S4, o.pc_variant != 1);
     if (o.pc_variant != 1) {
       // dmu = t + M^-1 (kappa K + M_f'') dc = t - M^-1 [J (dc, 0, ..)]_mu
       if (k_ch_crow(c, c->jac_point, scalar_ref(c, z), S2)) {
