@@ -172,6 +172,9 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
       c->gU0_lo = pfh_alloc(c, g); c->gU0_hi = pfh_alloc(c, g);
       c->gX_lo = pfh_alloc(c, g); c->gX_hi = pfh_alloc(c, g);
       c->gS_lo = pfh_alloc(c, c->nplane); c->gS_hi = pfh_alloc(c, c->nplane);
+      c->g2S_lo = pfh_alloc(c, 2 * c->nplane); c->g2S_hi = pfh_alloc(c, 2 * c->nplane);
+      c->g2R_lo = pfh_alloc(c, 2 * c->nplane); c->g2R_hi = pfh_alloc(c, 2 * c->nplane);
+      c->g2P_lo = pfh_alloc(c, 2 * c->nplane); c->g2P_hi = pfh_alloc(c, 2 * c->nplane);
     }
     c->d_partial = pfh_alloc(c, (size_t)PFH_RED_MAXBLOCKS * PFH_RED_MAXVALS);
     c->d_red = pfh_alloc(c, PFH_RED_MAXVALS);
@@ -383,6 +386,8 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->overlap = value != 0.0;
   } else if (k == "scalar_variant") {
     c->scalar_variant = (int)value;
+  } else if (k == "use_fused") {
+    c->use_fused = value != 0.0;
   } else if (k == "use_tma") {
     c->use_tma = value != 0.0;
   } else {

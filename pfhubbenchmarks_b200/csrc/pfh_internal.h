@@ -147,6 +147,8 @@ struct pfh_ctx {
   double *gU0_lo = nullptr, *gU0_hi = nullptr;  // previous step
   double *gX_lo = nullptr, *gX_hi = nullptr;    // operand of an operator apply
   double *gS_lo = nullptr, *gS_hi = nullptr;    // scalar operand (preconditioner sweeps)
+  // two-plane ghosts of the fused (temporally blocked) Chebyshev kernels: operand z_k, right-hand side r, z_{k-1}
+  double *g2S_lo = nullptr, *g2S_hi = nullptr, *g2R_lo = nullptr, *g2R_hi = nullptr, *g2P_lo = nullptr, *g2P_hi = nullptr;
   const double* jac_point = nullptr;            // device pointer to linearisation point (nf*n_owned)
   bool jac_ghost_valid = false;
 
@@ -174,6 +176,9 @@ struct pfh_ctx {
   long long t_n[PFH_N_TIMERS] = {0};
   int scalar_bc = 0;    // 2-D scalar operators: 1 = Dirichlet (identity) rows on the corner vertices of x = 0 and x = Lx
   int scalar_variant = 0;  // tile/ring variant of the TMA scalar kernel (tuning; pfh_set_option "scalar_variant")
+  // fused two-sweep (temporally blocked) Chebyshev kernels (pfh_cheb2_tma.cu): correct, but shared-memory-bandwidth
+  // bound and 1.45x slower per solve than the per-sweep TMA kernel at 512^3 (profiles/README.md), so opt-in only
+  bool use_fused = false;
   bool use_tma = true;  // 3-D fast path: TMA-staged kernels (pfh_stencil3_tma.cu); false = gather kernels only
 };
 
@@ -224,6 +229,8 @@ bool pfh_tma_ok(const pfh_ctx* c);
 bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
                           double* out, bool out_is_zero);
 bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const double* x, double* y);
+bool k3_cheb2_launch(pfh_ctx* c, bool first, double am, double ak, double b0, double aX, double bX, double aY, double bY,
+                     const double* zk, const double* zkm1, const double* r, double* outX, double* outY);
 bool k3_res_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* u, const double* u0, double* R);
 bool k3_ch_crow_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, FieldRef xc, double* out);
 // out = [J(ulin) (xc, 0)]_mu for Cahn-Hilliard (scalar in, scalar out); false if no fast path applies
@@ -255,6 +262,8 @@ void comm_allreduce_sum(pfh_ctx* c, double* d_buf, int n);
 // exchange boundary planes of nfields fields stored field-major with stride fstride
 void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, double* glo, double* ghi,
                cudaStream_t stream = nullptr);  // stream == nullptr: the ctx stream
+// exchange the first / last `nplanes` planes of one scalar field (ghost width nplanes)
+void comm_halo_n(pfh_ctx* c, const double* base, int nplanes, double* glo, double* ghi);
 int comm_unique_id(void* out);
 
 // ---- solver (pfh_solver.cpp) ----

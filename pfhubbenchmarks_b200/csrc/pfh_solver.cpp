@@ -106,9 +106,35 @@ double lmin_estimate(const pfh_ctx* c, double am, double ak, const std::vector<d
 }
 
 // result is guaranteed to land in `target`; `tmp` is scratch of the same size
+// Whole solve in one (3 sweeps) or two (5 sweeps) temporally blocked passes (pfh_cheb2_tma.cu); false: not applicable
+bool cheb_solve_fused(pfh_ctx* c, double am, double ak, const std::vector<ChebCoef>& cf, const double* r, double* target,
+                      double* tmp, double* tmp2) {
+  const int ns = (int)cf.size();
+  if (c->dim != 3 || !c->use_fused || !pfh_tma_ok(c) || (ns != 3 && ns != 5) || c->m3.nzl < 2) return false;
+  if (ns == 5 && (tmp == nullptr || tmp2 == nullptr)) return false;
+  const bool multi = c->cfg.nranks > 1;
+  const double n = (double)c->n_owned;
+  if (multi) comm_halo_n(c, r, 2, c->g2R_lo, c->g2R_hi);
+  if (ns == 3) {
+    ProfScope ps(c, T_CHEB_SWEEP, 16.0 * n);
+    return k3_cheb2_launch(c, true, am, ak, cf[0].b, cf[1].a, cf[1].b, cf[2].a, cf[2].b, nullptr, nullptr, r, nullptr, target);
+  }
+  {  // r -> z2 (tmp), z3 (tmp2)
+    ProfScope ps(c, T_CHEB_SWEEP, 24.0 * n);
+    if (!k3_cheb2_launch(c, true, am, ak, cf[0].b, cf[1].a, cf[1].b, cf[2].a, cf[2].b, nullptr, nullptr, r, tmp, tmp2)) return false;
+  }
+  if (multi) {
+    comm_halo_n(c, tmp2, 2, c->g2S_lo, c->g2S_hi);
+    comm_halo_n(c, tmp, 2, c->g2P_lo, c->g2P_hi);
+  }
+  ProfScope ps(c, T_CHEB_SWEEP, 32.0 * n);  // z3, z2, r -> z5
+  return k3_cheb2_launch(c, false, am, ak, 0.0, cf[3].a, cf[3].b, cf[4].a, cf[4].b, tmp2, tmp, r, nullptr, target);
+}
+
 void cheb_solve(pfh_ctx* c, double am, double ak, double lmin, double lmax, int nsweeps, const double* r, double* target,
-                double* tmp, bool consumer_needs_ghosts = false) {
+                double* tmp, bool consumer_needs_ghosts = false, double* tmp2 = nullptr) {
   const std::vector<ChebCoef> cf = cheb_coeffs(lmin, lmax, nsweeps);
+  if (cheb_solve_fused(c, am, ak, cf, r, target, tmp, tmp2)) return;
   double* cur = ((nsweeps - 1) % 2 == 0) ? target : tmp;
   double* prev = (cur == target) ? tmp : target;
   const bool ov = c->cfg.nranks > 1 && c->overlap && c->comm_stream && c->dim == 3 && c->m3.nzl >= 4;
@@ -244,9 +270,9 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
     // q = dt r1 - dt Mob K t
     k_lin_apply(c, 0.0, -dt * L.Mob, scalar_ref(c, T), dt, r1, S2);
     // dc = A^-1 M A^-1 q,  A = M + alpha K
-    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, S3, S4, true);
+    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, S3, S4, true, S1);
     k_lin_apply(c, 1.0, 0.0, scalar_ref(c, S3), 0.0, nullptr, S2);
-    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, z, S4, o.pc_variant != 1);
+    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, z, S4, o.pc_variant != 1, S1);
     if (o.pc_variant != 1) {
       // dmu = t + M^-1 (kappa K + M_f'') dc = t - M^-1 [J (dc, 0, ..)]_mu
       if (k_ch_crow(c, c->jac_point, scalar_ref(c, z), S2)) {

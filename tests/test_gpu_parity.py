@@ -210,6 +210,26 @@ def test_tma_kernels_match_gather_kernels():
     ctx.close()
 
 
+def test_fused_chebyshev_kernels_match_per_sweep_path():
+    """Opt-in temporally blocked Chebyshev kernels (pfh_cheb2_tma.cu) give the same preconditioner as the per-sweep kernels."""
+    eng = _engine()
+    ncell, length = (127, 70, 45), (254.0, 140.0, 90.0)
+    rng = np.random.default_rng(13)
+    ctx = eng.Context("b13d", ncell, length)
+    U = ctx.initial_condition()
+    X = torch.from_numpy(rng.standard_normal(2 * ctx.n_owned)).cuda()
+    ctx.dt = 1.6
+    ctx.jac_setup(U)
+    out = {}
+    for variant in (0, 1):
+        for fused in (0, 1):
+            ctx.set_option("use_fused", fused)
+            ctx.precond_setup(pc_variant=variant, pc_sweeps_mass=3, pc_sweeps_shifted=5)
+            out[(variant, fused)] = ctx.precond_apply(X).cpu().numpy()
+        assert rel_max(out[(variant, 1)], out[(variant, 0)]) < 1e-12
+    ctx.close()
+
+
 def test_step_host_equals_device_path():
     eng = _engine()
     ncell, length = (40, 30), (80.0, 60.0)
