@@ -173,20 +173,23 @@ def run_b200(args):
 
     n = args.grid - 1
     L = 2.0 * n
-    if args.workload == "bench1":     # 2-D crossed mesh with `grid` cells per edge (reference: 100), replicas only
+    if args.workload != "b13d":       # 2-D crossed mesh with `grid` cells per edge (reference: 100 / 350), replicas only
         assert world == 1, "2-D cases do not shard (DESIGN.md section 6)"
         n = args.grid
-        ctx = engine.Context("bench1", (n, n), (2.0 * n, 2.0 * n), device=local, krylov_basis=args.restart)
+        h = {"bench1": 2.0, "bench2": 2.0, "bench3": 960.0 / 350.0, "bench6": 1.0}[args.workload]   # reference cell sizes
+        ctx = engine.Context(args.workload, (n, n), (h * n, h * n), device=local, krylov_basis=args.restart)
     else:
         ctx = engine.Context("b13d", (n, n, n), (L, L, L), device=local, rank=rank, nranks=world, nccl_id=nccl_id,
                              krylov_basis=args.restart)
-    dof = 2 * ctx.n_global
+    dof = ctx.nf * ctx.n_global
     if world > 1 and os.environ.get("PFH_OVERLAP", "1") == "0":
         ctx.set_option("overlap", 0)
     opts = _lib.default_opts(krylov_restart=args.restart, pc_variant=args.pc_variant, pc_sweeps_mass=args.sweeps_mass,
                              pc_sweeps_shifted=args.sweeps_shifted, krylov_maximum_iterations=max(1000, int(n ** 3 / 10)) if args.workload == "b13d" else 1000)
     stream = torch.cuda.ExternalStream(ctx.lib.pfh_stream(ctx._h), device=torch.device("cuda", local))
     dts = dt_schedule(args.warmup + args.steps)
+    if args.workload in ("bench2", "bench3", "bench6"):      # these drivers start at dt = 1e-2 (bench2.py:222)
+        dts = [min(0.01 * 2 ** k, 0.16) for k in range(args.warmup + args.steps)]
 
     w = ctx.initial_condition()
     w0 = torch.empty_like(w)
@@ -212,7 +215,7 @@ def run_b200(args):
     # Per-launch CUDA events (two cudaEventRecord per kernel, ~8 us) are kept inside the timed region only when they
     # are negligible against the kernels (vectors larger than L2); for small, launch-bound grids the timed region runs
     # unprofiled and the kernel table comes from an identical second pass.
-    bytes_vec = 8 * 2 * ctx.n_owned
+    bytes_vec = 8 * ctx.nf * ctx.n_owned
     profile_in_timed = bytes_vec > 2.6e8
 
     def timed_pass(profile):
@@ -294,7 +297,7 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(("b13d_kuhn3d_%d" if args.workload == "b13d" else "bench1_crossed2d_%d") % args.grid, {}).get(dom) if world == 1 else None
+            traffic = json.load(open(tpath)).get(("b13d_kuhn3d_%d" if args.workload == "b13d" else args.workload + "_crossed2d_%d") % args.grid, {}).get(dom) if world == 1 else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -311,9 +314,9 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": ("b13d_kuhn3d_%d" if args.workload == "b13d" else "bench1_crossed2d_%d") % args.grid,
+                "config": {"workload": ("b13d_kuhn3d_%d" % args.grid) if args.workload == "b13d" else "%s_crossed2d_%d" % (args.workload, args.grid),
                            "grid_vertices": [args.grid] * 3 if args.workload == "b13d" else [args.grid + 1] * 2, "dof": dof,
-                           "fields": "c,mu", "h": 2.0, "dt_list": dts[args.warmup:], "parallelism": "z-slabs x%d" % world,
+                           "fields": ",".join(ctx.field_names), "dt_list": dts[args.warmup:], "parallelism": "z-slabs x%d" % world,
                            "solver": "newton(atol 1e-6, max 10) + GMRES(%d, rtol 1e-5) + Schur/Chebyshev(%d,%d,%s)" % (
                                args.restart, args.sweeps_mass, args.sweeps_shifted, "upper" if args.pc_variant else "full"),
                            "l2_policy": ("inputs_exceed_l2 (every vector is %.0f MB >> 126 MB L2)" % (bytes_vec / 1e6)) if bytes_vec > 2.6e8
@@ -338,7 +341,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=512, help="vertices per edge of the synthetic 3-D grid (cells per edge for bench1)")
-    ap.add_argument("--workload", default="b13d", choices=["b13d", "bench1"], help="b13d = 3-D headline; bench1 = 2-D crossed mesh")
+    ap.add_argument("--workload", default="b13d", choices=["b13d", "bench1", "bench2", "bench3", "bench6"],
+                    help="b13d = 3-D headline; bench1/2/3/6 = the 2-D problems on a crossed mesh with `grid` cells per edge")
     ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--pc-variant", type=int, default=1)
     ap.add_argument("--sweeps-mass", type=int, default=3)

@@ -141,7 +141,6 @@ struct pfh_ctx {
   double* V = nullptr;                                               // (basis+1) * nf*n_owned
   double *W1 = nullptr, *W2 = nullptr;                               // nf*n_owned Krylov temporaries
   double* S[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // scalar temporaries (n_owned)
-  double* zero_field = nullptr;                                      // n_owned zeros
   // ghost planes: [nf][nplane] each
   double *gU_lo = nullptr, *gU_hi = nullptr;    // linearisation point / current iterate
   double *gU0_lo = nullptr, *gU0_hi = nullptr;  // previous step
@@ -150,13 +149,11 @@ struct pfh_ctx {
   // two-plane ghosts of the fused (temporally blocked) Chebyshev kernels: operand z_k, right-hand side r, z_{k-1}
   double *g2S_lo = nullptr, *g2S_hi = nullptr, *g2R_lo = nullptr, *g2R_hi = nullptr, *g2P_lo = nullptr, *g2P_hi = nullptr;
   const double* jac_point = nullptr;            // device pointer to linearisation point (nf*n_owned)
-  bool jac_ghost_valid = false;
 
   // reductions
   double* d_partial = nullptr;  // [PFH_RED_MAXBLOCKS][PFH_RED_MAXVALS]
   double* d_red = nullptr;      // final values (device)
   double* h_red = nullptr;      // pinned host mirror
-  unsigned int* d_counter = nullptr;
 
   // preconditioner state
   pfh_solver_opts pc_opts;

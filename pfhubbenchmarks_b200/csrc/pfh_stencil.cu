@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(TPB) k3_energy(P prob, Mesh3 m, Fields<P::NF> 
 }
 
 template <class P>
-__global__ void __launch_bounds__(TPB) k3_ic(P prob, Mesh3 m, Fields<1> /*unused*/, const double* __restrict__ q, double* __restrict__ w) {
+__global__ void __launch_bounds__(TPB) k3_ic(P prob, Mesh3 m, const double* __restrict__ q, double* __restrict__ w) {
   double qq[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) qq[k] = q[k];
@@ -471,7 +471,7 @@ void k_initial_condition(pfh_ctx* c, const double* icp, int n, double* w) {
   PFH_CUDA(cudaMemcpyAsync(c->d_red, q, sizeof q, cudaMemcpyHostToDevice, c->stream));
   ProfScope ps(c, T_IC);
   if (c->dim == 3) {
-    PFH_DISPATCH3(c, (k3_ic<P><<<grid_red(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m3, Fields<1>(), c->d_red, w)));
+    PFH_DISPATCH3(c, (k3_ic<P><<<grid_red(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m3, c->d_red, w)));
   } else {
     PFH_DISPATCH2(c, (k2_ic<P><<<grid1(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m2, c->d_red, w)));
   }

@@ -293,3 +293,28 @@ def test_bench1_100_steps_fields_and_energy_vs_oracle():
     print("100 steps: worst rel L2(c) %.2e, worst rel energy %.2e" % (worst_c, worst_e))
     assert worst_c < 1e-8 and worst_e < 1e-6
     ctx.close()
+
+
+def test_c_abi_error_behaviour():
+    """Argument errors come back as return codes + pfh_last_error (never a crash); non-convergence is not an error."""
+    import ctypes as C
+    from pfhubbenchmarks_b200 import _lib
+    eng = _engine()
+    lib = _lib.load()
+    with pytest.raises(_lib.PfhError, match="3-D meshes support"):
+        eng.Context("bench2", (8, 8, 8), (16.0, 16.0, 16.0))            # only Cahn-Hilliard exists in 3-D (b13d)
+    with pytest.raises(_lib.PfhError, match="number of problem parameters"):
+        eng.Context("bench1", (8, 8), (16.0, 16.0), params=[0.3, 0.7])
+    cfg = _lib.Config(mesh_kind=7, problem=1)
+    h = C.c_void_p()
+    assert lib.pfh_create(C.byref(cfg), C.byref(h)) < 0 and b"mesh kind" in lib.pfh_last_error()
+    ctx = eng.Context("bench1", (16, 16), (32.0, 32.0), krylov_basis=10)
+    w0 = ctx.initial_condition(); w = w0.clone()
+    with pytest.raises(_lib.PfhError, match="krylov_restart"):
+        ctx.newton_solve(w, w0, krylov_restart=20)
+    with pytest.raises(_lib.PfhError, match="dt must be positive"):
+        ctx.dt = -1.0
+    ctx.dt = 0.1
+    rep = ctx.newton_solve(w, w0, krylov_restart=10, krylov_maximum_iterations=2, maximum_iterations=3)
+    assert rep["converged"] == 0 and rep["reason"] < 0        # reported, not raised (bench1.py:86)
+    ctx.close()
