@@ -443,6 +443,9 @@ bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, 
     case 2: return scalar_launch<64, 8, 2, 4, 64>(c, A);
     case 3: return scalar_launch<64, 16, 4, 3, 32>(c, A);
     case 4: return scalar_launch<64, 8, 2, 3, 32>(c, A);
+    case 5: return scalar_launch<64, 7, 1, 4, 64>(c, A);   // 8 x 74 = 592 tiles on a 512^2 plane = 148 SMs x 4 exactly
+    case 6: return scalar_launch<64, 8, 2, 4, 64>(c, A);
+    case 7: return scalar_launch<64, 7, 1, 4, 32>(c, A);
     default: return scalar_launch<S_TX, S_TY, S_RY, S_NS, S_ZCH>(c, A);
   }
 }

@@ -4,7 +4,8 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from pfhubbenchmarks_b200 import engine
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 511
-ctx = engine.Context("b13d", (n, n, n), (2.0 * n,) * 3, krylov_basis=2)
+nz = int(sys.argv[2]) if len(sys.argv) > 2 else n
+ctx = engine.Context("b13d", (n, n, nz), (2.0 * n, 2.0 * n, 2.0 * nz), krylov_basis=2)
 U = ctx.initial_condition()
 X = torch.randn(2 * ctx.n_owned, dtype=torch.float64, device="cuda")
 ctx.dt = 1.6
@@ -12,7 +13,7 @@ ctx.jac_setup(U)
 ctx.precond_setup(pc_variant=1, pc_sweeps_mass=3, pc_sweeps_shifted=5)
 z = ctx.new_vector()
 ref = None
-for v in (0, 1, 2, 3, 4, 0):
+for v in (0, 5, 6, 7, 2, 0):
     ctx.set_option("scalar_variant", v)
     ctx.precond_apply(X, out=z)          # warm-up / attribute setup
     ctx.set_option("profiling", 1); ctx.timers(reset=True)
