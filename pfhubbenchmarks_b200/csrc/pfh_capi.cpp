@@ -166,6 +166,8 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     c->W1 = pfh_alloc(c, vs); c->W2 = pfh_alloc(c, vs);
     c->V = pfh_alloc(c, (size_t)vs * (c->cfg.krylov_basis + 1));
     for (int i = 0; i < 5; ++i) c->S[i] = pfh_alloc(c, c->n_owned + 32);
+    if (c->dim == 2 && (cfg->problem == PFH_PROBLEM_BENCH2 || cfg->problem == PFH_PROBLEM_BENCH3))
+      for (int i = 0; i < 4; ++i) c->SIG[i] = pfh_alloc(c, c->n_owned + 32);
     if (c->nplane) {
       const size_t g = (size_t)c->nf * c->nplane;
       c->gU_lo = pfh_alloc(c, g); c->gU_hi = pfh_alloc(c, g);

@@ -171,6 +171,8 @@ struct pfh_ctx {
   double t_ms[PFH_N_TIMERS] = {0};
   double t_bytes[PFH_N_TIMERS] = {0};  // algorithmic bytes of the launches timed above
   long long t_n[PFH_N_TIMERS] = {0};
+  const double* scalar_sig = nullptr;  // 2-D scalar operators: optional per-vertex diagonal shift (lumped reaction term)
+  double* SIG[4] = {nullptr, nullptr, nullptr, nullptr};
   int scalar_bc = 0;    // 2-D scalar operators: 1 = Dirichlet (identity) rows on the corner vertices of x = 0 and x = Lx
   int scalar_variant = 0;  // tile/ring variant of the TMA scalar kernel (tuning; pfh_set_option "scalar_variant")
   // fused two-sweep (temporally blocked) Chebyshev kernels (pfh_cheb2_tma.cu): correct, but shared-memory-bandwidth
@@ -219,7 +221,9 @@ void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z);
 void k_energy(pfh_ctx* c, const double* u, double out[4]);  // includes final reduction + allreduce + D2H
 void k_initial_condition(pfh_ctx* c, const double* icp, int n, double* w);
 void k_dirichlet_fix(pfh_ctx* c, double* w);  // impose Dirichlet values on the iterate (bench6)
-void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst);  // dst = src on the Dirichlet vertices of a scalar field
+void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst);
+// sig_i = max(d g_field / d u_field (u_i), floor_coef) * rowsum(M)_i  (2-D)
+void k_reaction_diag(pfh_ctx* c, const double* u, int field, double floor_coef, double* sig);  // dst = src on the Dirichlet vertices of a scalar field
 
 // ---- TMA-staged 3-D kernels (pfh_stencil3_tma.cu); return false when the operands do not qualify ----
 bool pfh_tma_ok(const pfh_ctx* c);

@@ -242,6 +242,11 @@ void s_precond_setup(pfh_ctx* c, const pfh_solver_opts* o) {
     const HostTables t = host_tables(c);
     c->lmin_a = std::fmin(0.5, lmin_estimate(c, 1.0, c->pc_alpha, t.mT, t.kT));
   }
+  // lumped reaction term d g_a / d u_a of the parabolic fields' diagonal blocks at the linearisation point
+  // (Allen-Cahn eta_i of bench2, U and phi of bench3); clipped at -1/2 of the block's mass coefficient
+  if (c->jac_point != nullptr)
+    for (int k = 0; k < L.n_spd; ++k)
+      if (c->SIG[k] != nullptr) k_reaction_diag(c, c->jac_point, L.spd_field[k], -0.5 * L.spd_am[k], c->SIG[k]);
   c->pc_ready = true;
 }
 
@@ -292,8 +297,11 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
   for (int k = 0; k < L.n_spd; ++k) {
     const int f = L.spd_field[k];
     const HostTables t = host_tables(c);
-    const double lmin = std::fmin(0.5, lmin_estimate(c, L.spd_am[k], L.spd_ak[k], t.mT, t.kT));
+    // with the clipped reaction shift the constant mode's Rayleigh quotient is at least half the unshifted one
+    const double lmin = 0.5 * std::fmin(0.5, lmin_estimate(c, L.spd_am[k], L.spd_ak[k], t.mT, t.kT));
+    c->scalar_sig = (c->SIG[k] != nullptr && c->jac_point != nullptr) ? c->SIG[k] : nullptr;
     cheb_solve(c, L.spd_am[k], L.spd_ak[k], lmin, c->lmax, nA, r + f * n, z + f * n, c->S[1]);
+    c->scalar_sig = nullptr;
     if (L.spd_sign[k] < 0.0) v_scale(c, -1.0, z + f * n, z + f * n, n);
   }
   if (c->prob.id == PFH_PROBLEM_BENCH6) {

@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(TPB) k2_op(P prob, Mesh2 m, LinCoefs L, const 
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k2_scalar(Mesh2 m, double am, double ak, double a, double b,
                                                  const double* __restrict__ in, const double* __restrict__ r,
-                                                 double* __restrict__ out, bool out_is_zero, int bc) {
+                                                 double* __restrict__ out, bool out_is_zero, int bc,
+                                                 const double* __restrict__ sig) {
   const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
   if (i >= m.n_owned) return;
   if (bc && i < m.ncorner) {  // Dirichlet rows (bench6 phi, bench6.py:77-90): identity row, value carried by r
@@ -156,11 +157,14 @@ __global__ void __launch_bounds__(TPB) k2_scalar(Mesh2 m, double am, double ak, 
       return;
     }
   }
+  const double sg = sig ? sig[i] : 0.0;  // lumped reaction term added to the diagonal
   if (MODE == 1) {
-    out[i] = b / vtx::scalar_diag2(m, am, ak, i) * r[i];
+    out[i] = b / (vtx::scalar_diag2(m, am, ak, i) + sg) * r[i];
   } else {
     double Av, d, self;
     vtx::scalar_op2(m, am, ak, in, i, Av, d, self);
+    Av += sg * self;
+    d += sg;
     if (MODE == 0) out[i] = (a != 0.0 ? a * r[i] : 0.0) + Av;
     else out[i] = self + a * (self - (out_is_zero ? 0.0 : out[i])) + (b / d) * (r[i] - Av);
   }
@@ -177,7 +181,8 @@ struct Coef2 {
 template <int MODE>
 __global__ void __launch_bounds__(T2X* T2Y) k2_scalar_tiled(Mesh2 m, double am, double ak, Coef2 cf, double a, double b,
                                                              const double* __restrict__ in, const double* __restrict__ r,
-                                                             double* __restrict__ out, int out_is_zero, int bc) {
+                                                             double* __restrict__ out, int out_is_zero, int bc,
+                                                             const double* __restrict__ sig) {
   const int ix = blockIdx.x * T2X + threadIdx.x, iy = blockIdx.y * T2Y + threadIdx.y;
   const int nxv = m.nxv, nx = m.nx, nc = (int)m.ncorner;
   if (ix < nxv && iy < m.nyv) {  // corner vertex (ix, iy)
@@ -205,6 +210,11 @@ __global__ void __launch_bounds__(T2X* T2Y) k2_scalar_tiled(Mesh2 m, double am, 
         Av = am * Ms + ak * Ks;
         d = am * row.m[0] + ak * row.k[0];
       }
+      if (sig) {
+        const double sg = sig[i];
+        Av += sg * self;
+        d += sg;
+      }
       if (MODE == 0) out[i] = a * ri + Av;
       else out[i] = self + a * (self - (out_is_zero ? 0.0 : out[i])) + (b / d) * (ri - Av);
     }
@@ -212,11 +222,12 @@ __global__ void __launch_bounds__(T2X* T2Y) k2_scalar_tiled(Mesh2 m, double am, 
   if (ix < nx && iy < m.ny) {  // cell centre (ix, iy)
     const int ci = nc + iy * nx + ix, v0 = iy * nxv + ix;
     const double self = __ldg(in + ci);
+    const double sg = sig ? sig[ci] : 0.0;
     const double Av = cf.zc[0] * self + cf.zc[1] * __ldg(in + v0) + cf.zc[2] * __ldg(in + v0 + 1) + cf.zc[3] * __ldg(in + v0 + nxv) +
-                      cf.zc[4] * __ldg(in + v0 + nxv + 1);
+                      cf.zc[4] * __ldg(in + v0 + nxv + 1) + sg * self;
     const double ri = (MODE == 2 || a != 0.0) ? __ldg(r + ci) : 0.0;
     if (MODE == 0) out[ci] = a * ri + Av;
-    else out[ci] = self + a * (self - (out_is_zero ? 0.0 : out[ci])) + (b / cf.zc[0]) * (ri - Av);
+    else out[ci] = self + a * (self - (out_is_zero ? 0.0 : out[ci])) + (b / (cf.zc[0] + sg)) * (ri - Av);
   }
 }
 
@@ -302,6 +313,42 @@ double zfrac(const pfh_ctx* c) {
   if (c->dim != 3 || c->zpart == 0) return 1.0;
   const double nz = (double)c->m3.nzl;
   return c->zpart == 1 ? 2.0 / nz : (nz - 2.0) / nz;
+}
+
+// sig_i = clip(d g_a / d u_a (u_i)) * rowsum(M)_i : lumped reaction term of the diagonal Jacobian block of field a
+// (the M_{g'} block is replaced by its row-sum lumping at the vertex value; clipped so that the block stays positive)
+template <class P>
+__global__ void __launch_bounds__(TPB) k2_reaction_diag(P prob, Mesh2 m, const double* __restrict__ U, int field, double floor_coef,
+                                                         double* __restrict__ sig) {
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= m.n_owned) return;
+  double u[P::NIN], x[P::NIN], o[P::NOUT];
+  int oi = -1;
+#pragma unroll
+  for (int f = 0; f < P::NIN; ++f) {
+    u[f] = U[P::in(f) * m.n_owned + i];
+    x[f] = P::in(f) == field ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < P::NOUT; ++k)
+    if (P::out(k) == field) oi = k;
+  double s = 0.0;
+  if (oi >= 0) {
+    prob.dg(u, x, o);
+    s = o[oi];
+  }
+  // row sum of M at this vertex
+  double ml;
+  if (i < m.ncorner) {
+    vtx::Row2 row;
+    vtx::get_row2(m, vtx::type2(m, (int)(i % m.nxv), (int)(i / m.nxv)), row);
+    ml = 0.0;
+#pragma unroll
+    for (int k = 0; k < PFH_NOFF2; ++k) ml += row.m[k];
+  } else {
+    ml = m.mC[0] + m.mC[1] + m.mC[2] + m.mC[3] + m.mC[4];
+  }
+  sig[i] = fmax(s, floor_coef) * ml;
 }
 
 // -------- launch helpers --------
@@ -411,7 +458,7 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
     k3_scalar<0><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false, c->zpart);
   else
     k2_scalar_tiled<0><<<grid2_tiled(c->m2), dim3(T2X, T2Y), 0, c->stream>>>(c->m2, am, ak, coef2(c->m2, am, ak), s, 0.0, in.p, add, out, 0,
-                                                                                  c->scalar_bc);
+                                                                                  c->scalar_bc, c->scalar_sig);
   PFH_CUDA(cudaGetLastError());
 }
 
@@ -420,7 +467,7 @@ void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, d
   if (c->dim == 3)
     k3_scalar<1><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z, false, c->zpart);
   else
-    k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z, false, c->scalar_bc);
+    k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z, false, c->scalar_bc, c->scalar_sig);
   PFH_CUDA(cudaGetLastError());
 }
 
@@ -432,7 +479,7 @@ void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const do
     k3_scalar<2><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero, c->zpart);
   else
     k2_scalar_tiled<2><<<grid2_tiled(c->m2), dim3(T2X, T2Y), 0, c->stream>>>(c->m2, am, ak, coef2(c->m2, am, ak), a, b, z.p, r, zprev,
-                                                                                  zprev_is_zero ? 1 : 0, c->scalar_bc);
+                                                                                  zprev_is_zero ? 1 : 0, c->scalar_bc, c->scalar_sig);
   PFH_CUDA(cudaGetLastError());
 }
 
@@ -490,5 +537,12 @@ void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst) {
   if (c->dim != 2) return;
   ProfScope ps(c, T_OTHER);
   k2_dirichlet_copy<<<grid1(c->m2.ncorner), TPB, 0, c->stream>>>(c->m2, src, dst);
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k_reaction_diag(pfh_ctx* c, const double* u, int field, double floor_coef, double* sig) {
+  PFH_CHECK(c->dim == 2, "reaction diagonal is only used by the 2-D multi-field problems");
+  ProfScope ps(c, T_OTHER);
+  PFH_DISPATCH2(c, (k2_reaction_diag<P><<<grid1(c->n_owned), TPB, 0, c->stream>>>(P(c->prob), c->m2, u, field, floor_coef, sig)));
   PFH_CUDA(cudaGetLastError());
 }

@@ -146,8 +146,8 @@ def test_driver_cli_writes_csv_and_fields(tmp_path):
     assert rel_l2(c1, g["c"][0]) < 1e-9
 
 
-@pytest.mark.parametrize("name,ic,ncsv", [("bench2", (0.5, 0.05, 0.1, 1.5), 6), ("bench3", (-0.3, 8.0, 1.0, 1.0, -1.0), 6),
-                                          ("bench6", (0.5, 0.04), 5)])
+@pytest.mark.parametrize("name,ic,ncsv", [("bench2", (0.5, 0.05, 0.1, 1.5), 40), ("bench3", (-0.3, 8.0, 1.0, 1.0, -1.0), 46),
+                                          ("bench6", (0.5, 0.04), 14)])
 def test_other_drivers_follow_reference_csv(golden, tmp_path, name, ic, ncsv):
     """Driver loop with the reference's solver settings (atol 1e-6, 10 its, dt0 = 1e-2, niters < 5 doubling): the first
     rows reproduce results/<name>_out.csv (same accepted times; energy to 1e-6, second column to 1e-9 / 1e-6 abs)."""
@@ -171,7 +171,10 @@ def test_other_drivers_follow_reference_csv(golden, tmp_path, name, ic, ncsv):
     prefix = 0
     while prefix < len(rows) and abs(rows[prefix, 0] - csv[prefix, 0]) < 1e-9:
         prefix += 1
-    assert prefix >= 3, (rows[:, 0], csv[:ncsv, 0])
+    print("%s: %d of %d driver rows match the reference CSV time for time" % (name, prefix, len(rows)))
+    # bench3's whole committed run (46 rows, t = 0.01 .. 103) is reproduced time for time; for bench2 / bench6 the dt
+    # sequence depends on the nonlinear solver's iteration counts after the first rows
+    assert prefix >= (46 if name == "bench3" else 3), (rows[:, 0], csv[:ncsv, 0])
     etol = 2e-6 if name == "bench6" else 1e-6          # bench6's committed CSV is itself only converged to ~1e-6
     for k in range(prefix):
         assert abs(rows[k, 1] / csv[k, 1] - 1) < etol, (k, rows[k], csv[k])
