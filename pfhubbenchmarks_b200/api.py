@@ -150,7 +150,7 @@ class _Params(dict):
         super().__setitem__(k, v)
 
 
-_LINE_SEARCH = {"basic": 0}
+_LINE_SEARCH = {"basic": 0, "cp": 1}
 
 
 class NonlinearVariationalSolver:
@@ -187,7 +187,7 @@ class NonlinearVariationalSolver:
             solution_tolerance=float(p["solution_tolerance"]), maximum_iterations=int(p["maximum_iterations"]),
             krylov_rtol=float(k["relative_tolerance"]), krylov_atol=float(k["absolute_tolerance"]),
             krylov_maximum_iterations=int(k["maximum_iterations"]),
-            krylov_restart=min(int(k["restart"]), 30), preconditioner=pc, verbose=0)
+            krylov_restart=min(int(k["restart"]), 30), preconditioner=pc, line_search=_LINE_SEARCH.get(ls, 0), verbose=0)
 
     def solve(self):
         """niters, converged = solver.solve()  (bench1.py:162). In place on problem.w; never raises on non-convergence

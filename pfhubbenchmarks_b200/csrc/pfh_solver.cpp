@@ -482,6 +482,21 @@ void s_newton(pfh_ctx* c, double* w, const double* w0, const pfh_solver_opts* op
       break;
     }
     v_axpy(c, 1.0, c->DX, U, N);  // 'basic' line search: full step
+    if (o.line_search == 1) {
+      // 'cp' (critical point, PETSc SNESLINESEARCHCP with its default single secant iteration; bench2.py:140,
+      // bench6.py:117): find lambda with F(x + lambda dx) . dx = 0 from the values at lambda = 0 and 1
+      double d0[2], d1[2];
+      v_multidot(c, c->DX, 0, 1, c->R, N, d0);   // F(x) . dx
+      s_residual(c, U, w0, c->W1, true);
+      rep->residual_evals++;
+      v_multidot(c, c->DX, 0, 1, c->W1, N, d1);  // F(x + dx) . dx
+      const double den = d1[0] - d0[0];
+      double lambda = 1.0;
+      if (std::fabs(den) > 1e-300) lambda = -d0[0] / den;
+      if (!(lambda == lambda) || lambda <= 1e-3 || lambda > 4.0) lambda = 1.0;  // guard: keep the full step
+      if (o.verbose) fprintf(stderr, "    cp line search: lambda = %.4f\n", lambda);
+      if (lambda != 1.0) v_axpy(c, lambda - 1.0, c->DX, U, N);
+    }
     if (o.solution_tolerance > 1e-14) {
       const double dn = std::sqrt(v_norm2(c, c->DX, N)), un = std::sqrt(v_norm2(c, U, N));
       if (dn < o.solution_tolerance * un) {

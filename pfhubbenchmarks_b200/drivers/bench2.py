@@ -23,7 +23,7 @@ def main():
     nlparams["error_on_nonconvergence"] = False
     nlparams["absolute_tolerance"] = args.atol
     nlparams["maximum_iterations"] = 10
-    nlparams["line_search"] = "cp"        # 'cp' in the reference; only the full Newton step is implemented
+    nlparams["line_search"] = "cp"        # as the reference (bench2.py:140 / bench6.py:117)
     nlparams["linear_solver"] = "gmres"
     nlparams["preconditioner"] = "sor"
     nlparams["krylov_solver"]["maximum_iterations"] = 1000

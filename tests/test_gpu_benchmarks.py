@@ -163,6 +163,7 @@ def test_other_drivers_follow_reference_csv(golden, tmp_path, name, ic, ncsv):
     nl["absolute_tolerance"] = 1e-6
     nl["maximum_iterations"] = 10
     nl["krylov_solver"]["maximum_iterations"] = 5000 if name == "bench6" else 1000
+    nl["line_search"] = "basic" if name == "bench3" else "cp"        # bench3.py:124 / bench2.py:140, bench6.py:117
     ic_cls = {"bench2": df.InitialConditionsBench2, "bench3": df.InitialConditionsBench3, "bench6": df.InitialConditionsBench6}[name]
     hdr = "time,total_free_energy,solid_fraction" if name == "bench3" else "time,total_free_energy,total_solute"
     rows, _ = common.time_loop(problem, solver, ic_cls(*ic, degree=2), 1e-2, 1e-4, 100.0, str(tmp_path / (name + "_out.csv")), hdr,
