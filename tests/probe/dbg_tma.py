@@ -2,7 +2,7 @@
 import sys, os
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from pfhubbenchmarks_b200 import engine
 
 which = sys.argv[1]
