@@ -34,7 +34,7 @@ struct Coef15 {
 };
 
 template <int MODE, int TX, int TY, int RY, int NS>
-__global__ void __launch_bounds__(TX*(TY / RY))
+__global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
     k3_scalar_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_lo,
                   const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_r,
                   const __grid_constant__ CUtensorMap tm_o, Mesh3 m, int has_lo, int has_hi, int has_r, int has_o, int zchunk,
@@ -42,13 +42,16 @@ __global__ void __launch_bounds__(TX*(TY / RY))
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2: the TMA box start (x0-2) must be 16-byte aligned
   constexpr int ZT_BYTES = W * H * 8, PT_BYTES = TX * TY * 8;
   constexpr int ZT_STRIDE = round_up(ZT_BYTES, 128);
-  constexpr int STAGE_STRIDE = ZT_STRIDE + 2 * PT_BYTES;  // [z tile + halo | r tile | zprev tile]
+  constexpr int NR = 3;  // ring depth of the pointwise operand tiles (needed for one plane only) vs NS for the stencil operand
   constexpr int ROWS = TY / RY;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * STAGE_STRIDE);
-  auto ztile = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * STAGE_STRIDE); };
-  auto rtile = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * STAGE_STRIDE + ZT_STRIDE); };
-  auto otile = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * STAGE_STRIDE + ZT_STRIDE + PT_BYTES); };
+  // layout: NS stencil-operand tiles (tile + halo) | NR x [r tile | zprev tile] | NS + NR mbarriers
+  unsigned char* ro_base = smem + NS * ZT_STRIDE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ro_base + NR * 2 * PT_BYTES);
+  uint64_t* bars_ro = bars + NS;
+  auto ztile = [&](int p) { return reinterpret_cast<const double*>(smem + (p % NS) * ZT_STRIDE); };
+  auto rtile = [&](int k) { return reinterpret_cast<const double*>(ro_base + (k % NR) * 2 * PT_BYTES); };
+  auto otile = [&](int k) { return reinterpret_cast<const double*>(ro_base + (k % NR) * 2 * PT_BYTES + PT_BYTES); };
 
   const int tid = threadIdx.y * TX + threadIdx.x;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
@@ -65,12 +68,12 @@ __global__ void __launch_bounds__(TX*(TY / RY))
   const int nplanes = ze - zb + 2;  // planes zb-1 .. ze  <->  p = 0 .. nplanes-1
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < NS + NR; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
 
-  // plane p <-> zl = zb-1+p: the stencil operand with halo, and (owned planes only) the pointwise operands r, zprev
+  // plane p <-> zl = zb-1+p: the stencil operand with halo
   auto issue = [&](int p) {
     const int zl = zb - 1 + p;
     const CUtensorMap* map = &tm_main;
@@ -83,15 +86,22 @@ __global__ void __launch_bounds__(TX*(TY / RY))
       zc = 0;
     }
     uint64_t* bar = &bars[p % NS];
-    unsigned char* st = smem + (p % NS) * STAGE_STRIDE;
-    const bool owned = p >= 1 && p <= ze - zb;
-    mbar_expect_tx(bar, ZT_BYTES + (owned && has_r ? PT_BYTES : 0) + (owned && has_o ? PT_BYTES : 0));
-    tma_load_3d(st, map, x0 - 2, y0 - 1, zc, bar);
-    if (owned && has_r) tma_load_3d(st + ZT_STRIDE, &tm_r, x0, y0, zl, bar);
-    if (owned && has_o) tma_load_3d(st + ZT_STRIDE + PT_BYTES, &tm_o, x0, y0, zl, bar);
+    mbar_expect_tx(bar, ZT_BYTES);
+    tma_load_3d(smem + (p % NS) * ZT_STRIDE, map, x0 - 2, y0 - 1, zc, bar);
   };
-  if (tid == 0)
+  // output plane k <-> zl = zb+k: the pointwise operands r and zprev (tile only)
+  auto issue_ro = [&](int k) {
+    if (!has_r && !has_o) return;
+    uint64_t* bar = &bars_ro[k % NR];
+    unsigned char* st = ro_base + (k % NR) * 2 * PT_BYTES;
+    mbar_expect_tx(bar, (has_r ? PT_BYTES : 0) + (has_o ? PT_BYTES : 0));
+    if (has_r) tma_load_3d(st, &tm_r, x0, y0, zb + k, bar);
+    if (has_o) tma_load_3d(st + PT_BYTES, &tm_o, x0, y0, zb + k, bar);
+  };
+  if (tid == 0) {
     for (int p = 0; p < NS - 1 && p < nplanes; ++p) issue(p);
+    for (int k = 0; k < NR - 1 && k < ze - zb; ++k) issue_ro(k);
+  }
 
   const int ix = x0 + threadIdx.x;
   const int txt = ix == 0 ? 0 : (ix == m.nxv - 1 ? 2 : 1);
@@ -110,18 +120,22 @@ __global__ void __launch_bounds__(TX*(TY / RY))
   for (int k = 0; k < ze - zb; ++k) {
     const int zl = zb + k;
     __syncthreads();  // every thread is done with plane k-1: its stage may be refilled
-    if (tid == 0 && k + NS - 1 < nplanes) issue(k + NS - 1);
+    if (tid == 0) {
+      if (k + NS - 1 < nplanes) issue(k + NS - 1);
+      if (k + NR - 1 < ze - zb) issue_ro(k + NR - 1);
+    }
     if (k == 0) {
       mbar_wait(&bars[0], 0);
       mbar_wait(&bars[1 % NS], (1 / NS) & 1);
     }
     mbar_wait(&bars[(k + 2) % NS], ((k + 2) / NS) & 1);
+    if (has_r || has_o) mbar_wait(&bars_ro[k % NR], (k / NR) & 1);
 
     const double* S0 = ztile(k);
     const double* S1 = ztile(k + 1);
     const double* S2 = ztile(k + 2);
-    const double* Rt = rtile(k + 1);
-    const double* Ot = otile(k + 1);
+    const double* Rt = rtile(k);
+    const double* Ot = otile(k);
     const int gz = m.z0 + zl;
     const int tzt = gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1);
 #pragma unroll
@@ -405,8 +419,7 @@ bool scalar_launch(pfh_ctx* c, ScalarArgs& A) {
   if (nz_part <= 0) return true;
   const dim3 grid((m.nxv + TX - 1) / TX, (m.nyv + TY - 1) / TY, (nz_part + ZCH - 1) / ZCH);
   const dim3 block(TX, TY / RY);
-  constexpr int stage = round_up((TX + 4) * (TY + 2) * 8, 128) + 2 * TX * TY * 8;
-  constexpr size_t smem = NS * stage + NS * sizeof(uint64_t);
+  constexpr size_t smem = NS * round_up((TX + 4) * (TY + 2) * 8, 128) + 3 * 2 * TX * TY * 8 + (NS + 3) * sizeof(uint64_t);
   static bool attr_set = false;
   if (!attr_set) {
     PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<0, TX, TY, RY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

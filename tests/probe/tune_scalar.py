@@ -13,7 +13,7 @@ ctx.jac_setup(U)
 ctx.precond_setup(pc_variant=1, pc_sweeps_mass=3, pc_sweeps_shifted=5)
 z = ctx.new_vector()
 ref = None
-for v in (0, 5, 6, 7, 2, 0):
+for v in (0, 1, 2, 0):
     ctx.set_option("scalar_variant", v)
     ctx.precond_apply(X, out=z)          # warm-up / attribute setup
     ctx.set_option("profiling", 1); ctx.timers(reset=True)

@@ -318,3 +318,24 @@ def test_c_abi_error_behaviour():
     rep = ctx.newton_solve(w, w0, krylov_restart=10, krylov_maximum_iterations=2, maximum_iterations=3)
     assert rep["converged"] == 0 and rep["reason"] < 0        # reported, not raised (bench1.py:86)
     ctx.close()
+
+
+def test_snes_callback_boundary_drives_the_same_operators():
+    """N3: an external Newton-GMRES that only uses the SNES-style callbacks (F, J, mult, pc_apply) reaches the same
+    step solution as pfh_newton_solve and as the FEniCS snapshot."""
+    from pfhubbenchmarks_b200 import pde_problems
+    eng = _engine()
+    ncell, length = REFERENCE_MESH["bench1"]
+    ctx = eng.Context("bench1", ncell, length)
+    nv = ctx.n_owned
+    w0 = ctx.initial_condition()
+    ctx.dt = 0.1
+    x = w0.clone()
+    prob = pde_problems.SnesPDEProblem(ctx, w0)
+    its, ok = pde_problems.newton_krylov(prob, x, atol=1e-10)
+    assert ok and its <= 6
+    w = w0.clone()
+    rep = ctx.newton_solve(w, w0, absolute_tolerance=1e-10, krylov_rtol=1e-8, maximum_iterations=20)
+    assert rep["converged"]
+    assert rel_l2(x.cpu().numpy(), w.cpu().numpy()) < 1e-10
+    ctx.close()
