@@ -185,3 +185,32 @@ def test_other_drivers_follow_reference_csv(golden, tmp_path, name, ic, ncsv):
         else:
             assert abs(rows[k, 2] / csv[k, 2] - 1) < 1e-8
     problem.ctx.close()
+
+
+def test_bench1_full_length_run_statistics(golden, tmp_path):
+    """The complete bench1 run (end_time = 1e3, dolfin/bench1.py:138) through the driver loop.  Long spinodal runs are
+    compared on domain-averaged statistics (north star): the run completes, the free energy decays monotonically, the
+    solute is conserved to round-off, and the energy-vs-time curve stays within 2 % of results/bench1_out.csv."""
+    from pfhubbenchmarks_b200 import api as df
+    from pfhubbenchmarks_b200.drivers import common
+    g = golden["csv"]["bench1"]
+    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(200.0, 200.0), 100, 100, "crossed")
+    dt = df.Constant(1e-1)
+    problem = df.NonlinearVariationalProblem("bench1", mesh, dt)
+    solver = df.NonlinearVariationalSolver(problem)
+    nl = solver.parameters["snes_solver"]
+    nl["absolute_tolerance"] = 1e-6
+    nl["maximum_iterations"] = 10
+    nl["krylov_solver"]["maximum_iterations"] = 1000
+    rows, spent = common.time_loop(problem, solver, df.InitialConditionsBench1(0.5, 0.05, degree=2), 1e-1, 1e-2, 1e3,
+                                   str(tmp_path / "stats.csv"), "time,total_free_energy,total_solute", quiet=True)
+    rows = np.array(rows)
+    assert rows[-1, 0] >= 1e3 and len(rows) < 200
+    assert np.all(np.diff(rows[:, 1]) < 0)
+    assert abs(rows[-1, 2] / rows[0, 2] - 1) < 1e-12
+    Ei = np.interp(np.log(g[:, 0]), np.log(rows[:, 0]), rows[:, 1])
+    sel = g[:, 0] <= rows[-1, 0]
+    assert np.max(np.abs(Ei[sel] / g[sel, 1] - 1)) < 2e-2
+    print("bench1 to t = %.0f: %d steps in %.1f s; energy curve within %.2e of the reference" % (
+        rows[-1, 0], len(rows), spent, np.max(np.abs(Ei[sel] / g[sel, 1] - 1))))
+    problem.ctx.close()
