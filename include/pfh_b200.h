@@ -132,6 +132,11 @@ int pfh_newton_solve_dev(pfh_ctx* ctx, double* w, const double* w0,
  * (bench3: solid fraction), out[2], out[3] reserved (0).  Global (all ranks) values. */
 int pfh_energy_dev(pfh_ctx* ctx, const double* w, double out[4]);
 
+/* One piece of a df.assemble functional: out = u_a^T (am M + ak K) u_b over the global mesh, u_a and u_b fields
+ * of w (M = consistent mass, K = stiffness).  bench2.py:190-192 assembles kappa_eta/2 |grad eta_i|^2 per order
+ * parameter: that is ak = kappa_eta/2, a = b = 2+i.  am = 1, ak = 0 gives int u_a u_b dx. */
+int pfh_bilinear_dev(pfh_ctx* ctx, const double* w, int field_a, int field_b, double am, double ak, double* out);
+
 /* Host-buffer entry points (reference-facing plugin call; copies inside): one full
  * backward-Euler step w0 -> w at the given dt, plus the step's diagnostics. */
 int pfh_step_host(pfh_ctx* ctx, double* w_host /* in: guess, out: solution */, const double* w0_host,

@@ -301,6 +301,26 @@ int pfh_energy_dev(pfh_ctx* c, const double* w, double out[4]) {
   PFH_API_END
 }
 
+int pfh_bilinear_dev(pfh_ctx* c, const double* w, int fa, int fb, double am, double ak, double* out) {
+  PFH_API_BEGIN
+  PFH_CHECK(c && w && out, "null argument");
+  PFH_CHECK(fa >= 0 && fa < c->nf && fb >= 0 && fb < c->nf, "field index out of range");
+  PFH_CUDA(cudaSetDevice(c->cfg.device));
+  const long long n = c->n_owned;
+  const int bc = c->scalar_bc;
+  const double* sig = c->scalar_sig;
+  c->scalar_bc = 0;       // the plain operators: no Dirichlet rows, no reaction diagonal
+  c->scalar_sig = nullptr;
+  s_bilinear_apply(c, w + fb * n, am, ak, c->S[0]);
+  c->scalar_bc = bc;
+  c->scalar_sig = sig;
+  v_copy(c, c->S[1], w + fa * n, n);   // field offsets are only 8-byte aligned when n_owned is odd
+  double dots[2];
+  v_multidot(c, c->S[0], 0, 1, c->S[1], n, dots);
+  *out = dots[0];
+  PFH_API_END
+}
+
 static void stage(pfh_ctx* c) {
   const long long N = c->nf * c->n_owned;
   if (!c->U) {

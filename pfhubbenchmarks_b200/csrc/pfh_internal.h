@@ -270,6 +270,7 @@ int comm_unique_id(void* out);
 // ---- solver (pfh_solver.cpp) ----
 void s_exchange_state(pfh_ctx* c, const double* u, double* glo, double* ghi);
 void s_residual(pfh_ctx* c, const double* u, const double* u0, double* R, bool u0_ghost_current);
+void s_bilinear_apply(pfh_ctx* c, const double* u, double am, double ak, double* out);  // out = (am M + ak K) u, one field
 void s_jac_setup(pfh_ctx* c, const double* u);
 void s_jac_apply(pfh_ctx* c, const double* x, double* y);
 void s_precond_setup(pfh_ctx* c, const pfh_solver_opts* o);

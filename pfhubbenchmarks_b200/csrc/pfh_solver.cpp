@@ -40,6 +40,10 @@ static FieldRef scalar_ref(pfh_ctx* c, const double* p) {
   return FieldRef{p, c->gS_lo, c->gS_hi};
 }
 
+void s_bilinear_apply(pfh_ctx* c, const double* u, double am, double ak, double* out) {
+  k_lin_apply(c, am, ak, scalar_ref(c, u), 0.0, nullptr, out);
+}
+
 void s_residual(pfh_ctx* c, const double* u, const double* u0, double* R, bool u0_ghost_current) {
   s_exchange_state(c, u, c->gU_lo, c->gU_hi);
   if (!u0_ghost_current) s_exchange_state(c, u0, c->gU0_lo, c->gU0_hi);

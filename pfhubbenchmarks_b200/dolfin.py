@@ -1,0 +1,330 @@
+"""`import pfhubbenchmarks_b200.dolfin as df`: the slice of the legacy-FEniCS namespace the reference drivers touch.
+
+A reference driver (dolfin/bench1.py, bench2.py, bench3.py, bench6.py, b13d.py) is a module-level program: it builds a
+mesh, a mixed P1 space, Functions, a free energy and a weak form in UFL, hands `F, w, bcs, J` to
+`NonlinearVariationalProblem`, configures the SNES parameter tree and time-steps with `solver.solve()` and
+`df.assemble(...)` diagnostics.  With this module (and `pfhubbenchmarks_b200.pfbase` for `from pfbase import *`) the
+same program text runs on libpfh_b200.so: expressions are sympy (forms.py), the weak form is recognised as one of the
+compiled operator families and its coefficients are extracted from it, and every numerical operation -- interpolation of
+the initial condition, Newton-Krylov solve, assembled functionals -- is a call through the C ABI on device vectors.
+
+Nothing here computes on the CPU except evaluating a *user-defined* `UserExpression.eval` at the mesh vertices (the
+reference does that in Python too, pfbase.py:177-193); the shipped InitialConditionsBench* classes run as kernels.
+"""
+import warnings
+
+import numpy as np
+import sympy as sy
+
+from . import engine, forms
+from .api import (DOLFIN_EPS, MPI, BoxMesh, Mesh, NonlinearVariationalSolver as _Solver, Point,  # noqa: F401
+                  RectangleMesh, _IC)
+from .forms import diff, dx, grad, inner, variable  # noqa: F401
+from .io import File  # noqa: F401
+
+# ---- UFL math on expressions (bench3.py:81 uses atan; the rest for user free energies) ----
+atan, sin, cos, exp, sqrt, ln, tanh = sy.atan, sy.sin, sy.cos, sy.exp, sy.sqrt, sy.log, sy.tanh
+
+
+class _Tree(dict):
+    def __missing__(self, k):
+        self[k] = _Tree()
+        return self[k]
+
+
+parameters = _Tree()      # df.parameters["form_compiler"]["quadrature_degree"] = 3  (bench1.py:12-14)
+
+
+class LogLevel:
+    DEBUG, TRACE, PROGRESS, INFO, WARNING, ERROR, CRITICAL = 10, 13, 16, 20, 30, 40, 50
+
+
+_log_level = [LogLevel.INFO]
+
+
+def set_log_level(level):
+    _log_level[0] = level
+
+
+def warning(msg):
+    warnings.warn(msg)
+
+
+def near(a, b, tol=DOLFIN_EPS):
+    return abs(a - b) < tol
+
+
+class SubDomain:
+    def __init__(self, *a, **k):
+        pass
+
+
+class Constant:
+    """df.Constant: a symbol in forms, a float for the time loop (`float(dt)`, `dt.assign(x)`, bench1.py:29,171,180-183)."""
+
+    def __new__(cls, value):
+        if isinstance(value, (tuple, list)):
+            if any(float(v) != 0.0 for v in value):
+                raise NotImplementedError("vector Constants other than zero (pfbase.py:442 only adds f1 = (0, 0))")
+            return forms.VectorZero()
+        return object.__new__(cls)
+
+    def __init__(self, value):
+        self.value = float(value)
+        self.sym = forms.ConstSymbol("k%d" % next(forms._counter), const=self)
+
+    def assign(self, value):
+        self.value = float(value)
+
+    def __float__(self):
+        return self.value
+
+    def __repr__(self):
+        return "Constant(%r)" % self.value
+
+    def _op(self, other, fn):
+        if isinstance(other, (forms.Grad, forms.GradPair, forms.Test, forms.Tested, forms.Mixed, forms.Form, forms.Measure)):
+            return NotImplemented
+        return fn(self.sym, forms._expr(other))
+
+    def __add__(self, o): return self._op(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._op(o, lambda a, b: b + a)
+    def __sub__(self, o): return self._op(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._op(o, lambda a, b: b - a)
+    def __mul__(self, o): return self._op(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._op(o, lambda a, b: b * a)
+    def __truediv__(self, o): return self._op(o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return self._op(o, lambda a, b: b / a)
+    def __pow__(self, o): return self._op(o, lambda a, b: a ** b)
+    def __neg__(self): return -self.sym
+
+
+class _Element:
+    pass
+
+
+def MixedElement(elems):
+    return list(elems)
+
+
+class FunctionSpace:
+    """df.FunctionSpace(mesh, 'P', 1) and df.FunctionSpace(mesh, MixedElement([...]))  (bench1.py:39-41)."""
+
+    def __init__(self, mesh, family, degree=None, constrained_domain=None, _index=None):
+        if constrained_domain is not None:
+            raise NotImplementedError("periodic constrained_domain (commented out in every reference driver)")
+        self.mesh, self.index = mesh, _index
+        if isinstance(family, list):
+            self.nfields = len(family)
+        else:
+            if family not in ("P", "CG", "Lagrange") or degree != 1:
+                raise NotImplementedError("only P1 Lagrange spaces (all the reference drivers use)")
+            self.nfields = 1
+
+    def ufl_element(self):
+        return _Element()
+
+    def split(self):                                   # _, _, Wphi = W.split()  (bench6.py:86)
+        return [FunctionSpace(self.mesh, "P", 1, _index=i) for i in range(self.nfields)]
+
+    def sub(self, i):
+        return self.split()[i]
+
+
+class UserExpression:
+    """Base of user-defined initial conditions: subclasses implement eval(values, x) and value_shape (pfbase.py:177-193)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+
+class Expression:
+    """df.Expression("sin(x[1]/7)", degree=2)  (bench6.py:84): a C-syntax scalar expression of x[0], x[1], x[2]."""
+
+    def __init__(self, code, degree=None, **kw):
+        if isinstance(code, (tuple, list)):
+            raise NotImplementedError("vector-valued Expression")
+        x0, x1, x2 = sy.symbols("x0 x1 x2", real=True)
+        self.code = code
+        self.expr = sy.sympify(code.replace("x[0]", "x0").replace("x[1]", "x1").replace("x[2]", "x2"),
+                               locals={"x0": x0, "x1": x1, "x2": x2})
+
+
+class DirichletBC:
+    """df.DirichletBC(Wphi, value, boundary_fn)  (bench6.py:87-88).  The boundary is identified by probing
+    `boundary_fn(x, on_boundary)` at the four edge midpoints of the rectangle."""
+
+    def __init__(self, space, value, where):
+        if space.index is None:
+            raise NotImplementedError("DirichletBC on the whole mixed space")
+        self.field = space.index
+        self.value_expr = value.expr if isinstance(value, Expression) else sy.Float(float(value)) if float(value) != 0 else sy.Integer(0)
+        lx, ly = space.mesh.length[:2]
+        probes = {"left": (0.0, 0.5 * ly), "right": (lx, 0.5 * ly), "bottom": (0.5 * lx, 0.0), "top": (0.5 * lx, ly)}
+        hit = [k for k, p in probes.items() if where(np.array(p), True)]
+        if where(np.array((0.5 * lx, 0.5 * ly)), False) or len(hit) != 1:
+            raise NotImplementedError("Dirichlet boundary must be exactly one edge of the rectangle")
+        self.side = hit[0]
+
+
+class _FunctionIndex:
+    """w_[i] of a TestFunction / dw[i] of a TrialFunction."""
+
+    def __init__(self, space, test):
+        self.space, self.test = space, test
+
+    def __getitem__(self, i):
+        if not 0 <= i < self.space.nfields:
+            raise IndexError(i)
+        return forms.Test(i) if self.test else None
+
+
+def TestFunction(W):
+    return _FunctionIndex(W, True)
+
+
+def TrialFunction(W):
+    return _FunctionIndex(W, False)
+
+
+class Function:
+    """df.Function(W): symbols in forms; an fp64 device vector [field0 | field1 | ...] once a problem owns it.
+    interpolate()/assign() before the problem exists are replayed when the storage is created."""
+
+    def __init__(self, W):
+        self.W = W
+        k = next(forms._counter)
+        self.symbols = [forms.FieldSymbol("w%d_%d" % (k, i), owner=self, index=i) for i in range(W.nfields)]
+        self._tensor, self._pending, self._problem = None, None, None
+
+    def __getitem__(self, i):
+        return self.symbols[i]
+
+    @property
+    def tensor(self):
+        if self._tensor is None:
+            raise RuntimeError("Function has no storage yet: create the NonlinearVariationalProblem first")
+        return self._tensor
+
+    def _bind(self, problem):
+        self._problem = problem
+        self._tensor = problem.ctx.new_vector()
+        pend, self._pending = self._pending, None
+        if pend is not None:
+            self.interpolate(pend) if not isinstance(pend, Function) else self.assign(pend)
+
+    def interpolate(self, ic):                         # w.interpolate(w_ic)  (bench1.py:134-135)
+        if self._tensor is None:
+            self._pending = ic
+            return
+        ctx = self._problem.ctx
+        if isinstance(ic, _IC):
+            ctx.initial_condition(ic.args, out=self._tensor)
+        elif isinstance(ic, UserExpression):
+            self._tensor.copy_(_eval_user_expression(ic, ctx))
+        else:
+            raise TypeError("cannot interpolate %r" % (ic,))
+
+    def assign(self, other):                           # w0.assign(w), w.assign(w0)  (bench1.py:158,173)
+        if self._tensor is None or other._tensor is None:
+            self._pending = other
+            return
+        self._tensor.copy_(other._tensor)
+
+    def split(self):                                   # c, _ = w.split()  (bench1.py:188)
+        return self._problem.ctx.fields(self.tensor)
+
+    def vector(self):
+        return self.tensor
+
+    def to_numpy(self):
+        return self.tensor.cpu().numpy().reshape(self.W.nfields, -1)
+
+
+def split(w):
+    """c, mu = df.split(w)  (bench1.py:59): the same symbols as w[0], w[1]."""
+    return tuple(w.symbols)
+
+
+def _eval_user_expression(ic, ctx):
+    """Vertex values of a user-defined expression, in the library's vertex order (single rank)."""
+    import torch
+    if ctx.nranks != 1:
+        raise NotImplementedError("user-defined UserExpression on a slab-decomposed mesh")
+    xy = ctx.vertex_coordinates()
+    vals = np.zeros((xy.shape[0], ctx.nf))
+    for i in range(xy.shape[0]):
+        ic.eval(vals[i], xy[i])
+    return torch.from_numpy(np.ascontiguousarray(vals.T).reshape(-1)).to(ctx.new_vector().device)
+
+
+def derivative(F, w, dw):
+    """J = df.derivative(F, w, dw)  (bench1.py:69): the compiled operators carry their exact Gateaux derivative
+    (csrc/pfh_problems.cuh dg), so J is only a marker that the Jacobian of F is wanted."""
+    return ("derivative", F)
+
+
+class NonlinearVariationalProblem:
+    """df.NonlinearVariationalProblem(F, w, bcs, J)  (bench1.py:76).  F is lowered and matched to a compiled operator
+    family (forms.compile_form); the physical coefficients are read out of the form itself."""
+
+    def __init__(self, F, w, bcs=None, J=None, device=0, rank=0, nranks=1, nccl_id=None, krylov_basis=30):
+        if parameters["form_compiler"].get("quadrature_degree", 3) != 3:
+            raise NotImplementedError("the compiled operators integrate with the degree-3 rules the reference sets (bench1.py:14)")
+        if J is not None and not (isinstance(J, tuple) and J[0] == "derivative" and J[1] is F):
+            raise NotImplementedError("J must be df.derivative(F, w, dw)")
+        prev = None
+        for t in F.terms:
+            if t[0] == "src":
+                for s in sy.sympify(t[2]).free_symbols:
+                    if isinstance(s, forms.FieldSymbol) and s.owner is not w:
+                        prev = s.owner
+        if prev is None:
+            raise NotImplementedError("no previous-step Function in the form")
+        name, params, dt = forms.compile_form(F, w.W.nfields, w.symbols, prev.symbols, bcs or ())
+        mesh = w.W.mesh
+        if name == "bench1" and mesh.kind == "kuhn3d":
+            name = "b13d"
+        self.benchmark, self.mesh, self.dt, self.params = name, mesh, dt, params
+        self.ctx = engine.Context(name, mesh.ncell, mesh.length, params=params, device=device, rank=rank, nranks=nranks,
+                                  nccl_id=nccl_id, krylov_basis=krylov_basis)
+        self.w, self.w0 = w, prev
+        w._bind(self)
+        prev._bind(self)
+        self._functionals = {}
+
+
+class NonlinearVariationalSolver(_Solver):
+    pass
+
+
+def assemble(form):
+    """df.assemble of a functional (bench1.py:121-125, bench2.py:184-194, bench3.py:162-170, bench6.py:155-165).
+    The pointwise part must be the benchmark's free-energy density or its second diagnostic (both come out of the
+    fused energy kernel); gradient pieces with other coefficients are corrected with pfh_bilinear_dev."""
+    owner = None
+    for t in form.terms:
+        syms = sy.sympify(t[1]).free_symbols if t[0] == "func" else {t[1], t[2]}
+        for s in syms:
+            if isinstance(s, forms.FieldSymbol):
+                owner = s.owner
+    if owner is None or owner._problem is None:
+        raise RuntimeError("assemble: the functional does not involve the Function of a NonlinearVariationalProblem")
+    pr = owner._problem
+    key = repr(form.terms)
+    plan = pr._functionals.get(key)
+    if plan is None:
+        plan = forms.plan_functional(form, pr.benchmark, pr.ctx.params, owner.symbols)
+        pr._functionals[key] = plan
+    which, scale, corrections = plan
+    val = scale * pr.ctx.energy(owner.tensor)[which] if which is not None else 0.0
+    for field, coef in corrections:
+        val += coef * pr.ctx.bilinear(owner.tensor, field, field, 0.0, 1.0)
+    return val
+
+
+class HDF5File:
+    """bench1.py:116-118 opens an HDF5 checkpoint; h5py / HDF5 are not in this image: use df.File(<name>.pvd)."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("HDF5 output is not available; use File('<name>.pvd') (VTU) instead")

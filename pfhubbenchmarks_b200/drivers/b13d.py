@@ -6,8 +6,9 @@
 import os
 import sys
 
-from .. import api as df
-from .common import parse_args, run_fenics, time_loop
+from .. import dolfin as df
+from ..pfbase import InitialConditionsBench1, cahn_hilliard_weak_form, dx, grad, inner
+from .common import mixed_p1, parse_args, run_fenics, snes_setup, time_loop
 
 
 def main():
@@ -37,26 +38,29 @@ def main():
     Lx = Ly = Lz = 2.0 * n_cells
     mesh = df.BoxMesh(df.Point(0.0, 0.0, 0.0), df.Point(Lx, Ly, Lz), Nx, Ny, Nz)
     dt = df.Constant(1e-1)
-    c_alpha, c_beta, rho_s, kappa, M = 0.3, 0.7, 5.0, 2.0, 5.0
-    w_ic = df.InitialConditionsBench1(0.5, 0.05, degree=2)
-    problem = df.NonlinearVariationalProblem("b13d", mesh, dt, params=[c_alpha, c_beta, rho_s, kappa, M], device=local,
-                                             rank=rank, nranks=world, nccl_id=nccl_id)
+    c_alpha, c_beta, rho_s, kappa, M = (df.Constant(v) for v in (0.3, 0.7, 5.0, 2.0, 5.0))        # b13d.py:35-39
+    W, w, w0, w_, dw = mixed_p1(mesh, 2)
+    w_ic = InitialConditionsBench1(0.5, 0.05, degree=2)
+    c, mu = df.split(w)
+    f_chem = rho_s * (c - c_alpha) ** 2 * (c_beta - c) ** 2
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, M, kappa, df.diff(f_chem, c))
+    # device / rank / nranks / nccl_id place the problem: one z-slab of the box per GPU
+    problem = df.NonlinearVariationalProblem(F, w, [], df.derivative(F, w, dw), device=local, rank=rank, nranks=world,
+                                             nccl_id=nccl_id)
     solver = df.NonlinearVariationalSolver(problem)
-    solver.parameters["nonlinear_solver"] = "snes"
-    nlparams = solver.parameters["snes_solver"]
-    nlparams["line_search"] = "basic"
-    nlparams["report"] = True
-    nlparams["error_on_nonconvergence"] = False
-    nlparams["absolute_tolerance"] = args.atol
-    nlparams["maximum_iterations"] = 10
-    nlparams["linear_solver"] = "gmres"
-    nlparams["preconditioner"] = "sor"
-    nlparams["krylov_solver"]["maximum_iterations"] = int(Nx * Ny * Nz / 10)      # b13d.py:97
-    nlparams["krylov_solver"]["error_on_nonconvergence"] = False
+    snes_setup(solver, args.atol, "basic", int(Nx * Ny * Nz / 10))      # b13d.py:97
+
+    def total_free_energy():
+        return df.assemble(f_chem * dx + kappa / 2.0 * inner(grad(c), grad(c)) * dx)
+
+    def total_solute():
+        return df.assemble(c * dx)
+
     # b13d.py writes results/bench1_out.csv (b13d.py:200)
     return time_loop(problem, solver, w_ic, 1e-1, 1e-2, args.end_time, os.path.join(args.outdir, "bench1_out.csv"),
                      "time,total_free_energy,total_solute", args.max_steps, args.quiet,
-                     save_dir=os.path.join(args.outdir, os.path.basename(__file__)[:-3]) if args.save_solution else None)
+                     save_dir=os.path.join(args.outdir, "b13d") if args.save_solution else None,
+                     functionals=(total_free_energy, total_solute))
 
 
 if __name__ == "__main__":

@@ -12,7 +12,8 @@ import runpy
 import sys
 import time
 
-from .. import api as df
+from .. import api as _api
+from .. import dolfin as df
 
 
 def parse_args(name, end_time):
@@ -38,8 +39,34 @@ def run_fenics(args, script):
     runpy.run_path(os.path.join(args.reference_dir, "dolfin", script), run_name="__main__")
 
 
+def mixed_p1(mesh, nfields):
+    """W, w, w0, w_, dw: the mixed P1 space of `nfields` components and the Functions every driver builds on it
+    (bench1.py:39-56)."""
+    pe = df.FunctionSpace(mesh, 'P', 1).ufl_element()
+    W = df.FunctionSpace(mesh, df.MixedElement([pe] * nfields))
+    return W, df.Function(W), df.Function(W), df.TestFunction(W), df.TrialFunction(W)
+
+
+def snes_setup(solver, atol, line_search, krylov_max_it):
+    """The parameter block every reference driver repeats (bench1.py:82-110)."""
+    solver.parameters['nonlinear_solver'] = 'snes'
+    nl = solver.parameters['snes_solver']
+    nl['report'] = True
+    nl['error_on_nonconvergence'] = False
+    nl['absolute_tolerance'] = atol
+    nl['maximum_iterations'] = 10
+    nl['line_search'] = line_search
+    nl['linear_solver'] = 'gmres'
+    nl['preconditioner'] = 'sor'          # mapped to the Schur/Chebyshev preconditioner (DESIGN.md section 5)
+    nl['krylov_solver']['maximum_iterations'] = krylov_max_it
+    nl['krylov_solver']['error_on_nonconvergence'] = False
+    return nl
+
+
 def time_loop(problem, solver, w_ic, dt0, dt_min, end_time, csv_path, header, max_steps=0, quiet=False, max_retries=20,
-              abort_on_negative_energy=False, save_dir=None, save_fields=(0,)):
+              abort_on_negative_energy=False, save_dir=None, save_fields=(0,), functionals=None):
+    """`functionals`: the driver's own (total_free_energy, total_solute) callables built on df.assemble, as the
+    reference scripts define them (bench1.py:121-125); None uses both values of the fused energy kernel."""
     w, w0, dt = problem.w, problem.w0, problem.dt
     rank0 = df.MPI.rank() == 0
     t = df.Constant(0.0)
@@ -79,7 +106,10 @@ def time_loop(problem, solver, w_ic, dt0, dt_min, end_time, csv_path, header, ma
             dt.assign(2 * float(dt))
         else:
             dt.assign(max(0.5 * float(dt), dt_min))
-        F_total, C_total = df.diagnostics(problem)            # analysis
+        if functionals is None:                               # analysis
+            F_total, C_total = _api.diagnostics(problem)
+        else:
+            F_total, C_total = functionals[0](), functionals[1]()
         benchmark_output.append([float(t), F_total, C_total])
         for k, fh in files.items():
             fh << (w.split()[k].cpu().numpy(), float(t))
@@ -94,5 +124,5 @@ def time_loop(problem, solver, w_ic, dt0, dt_min, end_time, csv_path, header, ma
         if not quiet:
             print("Time spent is %s" % spent)
         os.makedirs(os.path.dirname(os.path.abspath(csv_path)), exist_ok=True)
-        df.write_csv(csv_path, benchmark_output, header)      # post process
+        _api.write_csv(csv_path, benchmark_output, header)      # post process
     return benchmark_output, spent

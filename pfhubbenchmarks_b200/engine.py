@@ -102,6 +102,19 @@ class Context:
         """Per-field views of a state vector (w.split() in the drivers, bench1.py:188)."""
         return [w[i * self.n_owned:(i + 1) * self.n_owned] for i in range(self.nf)]
 
+    def vertex_coordinates(self):
+        """(n_owned, dim) coordinates in the library's vertex order: 2-D corners x-fastest then cell centres
+        (DOLFIN 'crossed' numbering); 3-D x-fastest over this rank's z-planes."""
+        if self.dim == 2:
+            (nx, ny), (lx, ly) = self.ncell, self.length
+            x, y = np.meshgrid(np.linspace(0.0, lx, nx + 1), np.linspace(0.0, ly, ny + 1))
+            xc, yc = np.meshgrid((np.arange(nx) + 0.5) * (lx / nx), (np.arange(ny) + 0.5) * (ly / ny))
+            return np.concatenate([np.stack([x.ravel(), y.ravel()], 1), np.stack([xc.ravel(), yc.ravel()], 1)])
+        (nx, ny, nz), (lx, ly, lz) = self.ncell, self.length
+        zs = np.linspace(0.0, lz, nz + 1)[self.z_range[0]:self.z_range[1]]
+        z, y, x = np.meshgrid(zs, np.linspace(0.0, ly, ny + 1), np.linspace(0.0, lx, nx + 1), indexing="ij")
+        return np.stack([x.ravel(), y.ravel(), z.ravel()], 1)
+
     # ---- scalar state ----
     @property
     def dt(self):
@@ -152,6 +165,12 @@ class Context:
         out = (C.c_double * 4)()
         _lib.check(self.lib.pfh_energy_dev(self._h, _ptr(w), out))
         return float(out[0]), float(out[1])
+
+    def bilinear(self, w, field_a, field_b, am, ak):
+        """u_a^T (am M + ak K) u_b: one piece of a df.assemble functional (bench2.py:190-192)."""
+        out = C.c_double()
+        _lib.check(self.lib.pfh_bilinear_dev(self._h, _ptr(w), int(field_a), int(field_b), float(am), float(ak), C.byref(out)))
+        return float(out.value)
 
     # ---- host-buffer entry points (numpy fp64, C-contiguous) ----
     @staticmethod

@@ -1,0 +1,57 @@
+"""`from pfhubbenchmarks_b200.pfbase import *`: the names a reference driver gets from `from pfbase import *`
+(dolfin/pfbase.py): the initial conditions, the weak-form builders, and -- because the reference module itself does
+`from dolfin import *` -- the UFL vocabulary (`dx`, `inner`, `grad`, `variable`, `MPI`, `HDF5File`, ...).
+
+The builders return forms.Form objects; the strong forms they discretise (backward Euler, integrated by parts,
+natural no-flux boundaries) are
+
+    cahn_hilliard_weak_form   dc/dt = div(M grad mu),  mu = f'(c) - kappa lapl c          (pfbase.py:361-383)
+    allen_cahn_weak_form      deta/dt = -L (f'(eta) - kappa lapl eta) + f                 (pfbase.py:396-408)
+    allen_cahn_RHS_IBP        the right-hand side of the above, un-integrated             (pfbase.py:385-394)
+    poisson_weak_form         div(M grad u) = f                                           (pfbase.py:410-421)
+    diffusion_weak_form       du/dt = L div(D grad u + f1) + f2                           (pfbase.py:435-449)
+    euler_bwd_weak_form       du/dt = f                                                   (pfbase.py:451-462)
+"""
+from .api import (InitialConditionsBench1, InitialConditionsBench2, InitialConditionsBench3,  # noqa: F401
+                  InitialConditionsBench6)
+from .dolfin import *  # noqa: F401,F403
+from .dolfin import MPI, HDF5File, dx, grad, inner  # noqa: F401
+
+
+def _time_derivative(u, u_, u0, dt):
+    return 1 / dt * u_ * (u - u0) * dx
+
+
+def cahn_hilliard_weak_form(c, mu, c_, mu_, c0, dt, M, kappa, dfdc):
+    transport = _time_derivative(c, c_, c0, dt) + inner(grad(c_), M * grad(mu)) * dx
+    potential = mu_ * mu * dx - (mu_ * dfdc * dx + kappa * inner(grad(mu_), grad(c)) * dx)
+    return transport + potential
+
+
+def allen_cahn_RHS_IBP(eta, eta_, L, kappa, dfdeta, f):
+    return -L * (eta_ * dfdeta + kappa * inner(grad(eta_), grad(eta))) + eta_ * f
+
+
+def allen_cahn_weak_form(eta, eta_, eta0, dt, L, kappa, dfdeta, f):
+    return _time_derivative(eta, eta_, eta0, dt) - allen_cahn_RHS_IBP(eta, eta_, L, kappa, dfdeta, f) * dx
+
+
+def poisson_weak_form(u, u_, f, M):
+    return -inner(grad(u_), M * grad(u)) * dx - u_ * f * dx
+
+
+def diffusion_weak_form_RHS(u, u_, L, D, f1, f2):
+    return -inner(grad(L * u_), D * grad(u) + f1) * dx + u_ * f2 * dx
+
+
+def diffusion_weak_form(u, u_, u0, dt, L, D, f1, f2):
+    return _time_derivative(u, u_, u0, dt) - diffusion_weak_form_RHS(u, u_, L, D, f1, f2)
+
+
+def euler_bwd_weak_form(u, u_, u0, dt, f):
+    return _time_derivative(u, u_, u0, dt) - u_ * f * dx
+
+
+def h(u):
+    """Interpolation polynomial u^3 (6u^2 - 15u + 10) of benchmark 2 (bench2.py:83-87)."""
+    return u ** 3 * (6 * u ** 2 - 15 * u + 10)

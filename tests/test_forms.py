@@ -1,0 +1,160 @@
+"""CPU tests of the UFL-style front end (pfhubbenchmarks_b200/forms.py, dolfin.py, pfbase.py): the weak forms the
+reference drivers write (dolfin/bench1.py:59-69, bench2.py:66-116, bench3.py:67-104, bench6.py:60-92) are lowered,
+recognised as the compiled operator family they are, and give back the coefficients the driver put in."""
+import importlib
+import sys
+
+import pytest
+import sympy as sy
+
+import pfhubbenchmarks_b200.dolfin as df
+from pfhubbenchmarks_b200 import engine, forms
+from pfhubbenchmarks_b200.pfbase import (allen_cahn_weak_form, cahn_hilliard_weak_form, dx, grad, inner,
+                                          poisson_weak_form)
+
+
+class _Stop(Exception):
+    pass
+
+
+def _lower(F, w, bcs=()):
+    prev = next(s.owner for t in F.terms if t[0] == "src" for s in sy.sympify(t[2]).free_symbols
+                if isinstance(s, forms.FieldSymbol) and s.owner is not w)
+    return forms.compile_form(F, w.W.nfields, w.symbols, prev.symbols, bcs)
+
+
+@pytest.mark.parametrize("name", ["bench1", "bench2", "bench3", "bench6", "b13d"])
+def test_driver_forms_are_recognised(name, monkeypatch):
+    """Run each driver's main() up to the problem constructor: the form it built maps to its operator family with
+    exactly the coefficients of the reference script (engine.PROBLEMS holds the same numbers for the name-selected API)."""
+    got = {}
+
+    def fake(F, w, bcs=None, J=None, **kw):
+        assert J == ("derivative", F)
+        got["r"] = _lower(F, w, bcs or ())
+        raise _Stop
+
+    monkeypatch.setattr(df, "NonlinearVariationalProblem", fake)
+    monkeypatch.setattr(sys, "argv", [name])
+    mod = importlib.import_module("pfhubbenchmarks_b200.drivers." + name)
+    with pytest.raises(_Stop):
+        mod.main()
+    family, params, dt = got["r"]
+    assert family == ("bench1" if name == "b13d" else name)
+    want = engine.PROBLEMS[name][2]
+    assert len(params) == len(want)
+    for a, b in zip(params, want):
+        assert (a is None and b is None) or abs(a - b) <= 2e-16 * abs(b), (params, want)
+    assert float(dt) == 0.1
+
+
+def _ch(n=2):
+    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(10.0, 10.0), 4, 4, "crossed")
+    pe = df.FunctionSpace(mesh, "P", 1).ufl_element()
+    W = df.FunctionSpace(mesh, df.MixedElement([pe] * n))
+    return W, df.Function(W), df.Function(W), df.TestFunction(W)
+
+
+def test_coefficients_come_from_the_form():
+    W, w, w0, w_ = _ch()
+    dt, M, kappa = df.Constant(0.25), df.Constant(1.5), df.Constant(0.75)
+    c, mu = df.split(w)
+    f = 3.0 * (c - 0.2) ** 2 * (0.9 - c) ** 2
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, M, kappa, df.diff(f, c))
+    family, params, dtc = _lower(F, w)
+    assert family == "bench1" and dtc is dt
+    assert params == pytest.approx([0.2, 0.9, 3.0, 0.75, 1.5], rel=1e-13)
+    # split(w)[i] and w[i] are the same symbols (bench1.py:59 vs :68)
+    assert c is w[0] and mu is w[1]
+
+
+def test_unknown_free_energy_is_refused():
+    W, w, w0, w_ = _ch()
+    dt, one = df.Constant(0.1), df.Constant(1.0)
+    c, mu = df.split(w)
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, one, one, df.diff(c ** 6 - c ** 2, c))
+    with pytest.raises(NotImplementedError, match="compiled operator families"):
+        _lower(F, w)
+    # an Allen-Cahn equation alone is none of the shipped systems either
+    W1, v, v0, v_ = _ch(1)
+    e = v[0]
+    with pytest.raises(NotImplementedError):
+        _lower(allen_cahn_weak_form(e, v_[0], v0[0], dt, one, one, df.diff(e ** 2 * (1 - e) ** 2, e), df.Constant(0)), v)
+
+
+def test_form_algebra_matches_the_weak_forms():
+    """The lowered rows of the Cahn-Hilliard form: (c - c0)/dt and mu - f'(c) pointwise, M and -kappa stiffness couplings."""
+    W, w, w0, w_ = _ch()
+    dt, M, kappa = df.Constant(0.1), df.Constant(5.0), df.Constant(2.0)
+    c, mu = df.split(w)
+    dfdc = df.diff((c - 0.3) ** 2 * (0.7 - c) ** 2, c)
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, M, kappa, dfdc)
+    L = forms.Lowered(F, 2, w.symbols, w0.symbols, dt.sym)
+    assert sy.simplify(L.src[0] - (c - w0[0]) / dt.sym) == 0
+    assert forms._close(L.src[1] - (mu - dfdc), 1e-14)
+    assert L.stiff[0][1] == M.sym and L.stiff[1][0] == -kappa.sym
+    assert L.stiff[0][0] == 0 and L.stiff[1][1] == 0
+    # Poisson row: -int grad v . grad u - int v f
+    Wp, u, u0, u_ = _ch(3)
+    P = poisson_weak_form(u[2], u_[2], -0.5 * u[0], df.Constant(1.0))
+    Lp = forms.Lowered(P, 3, u.symbols, u0.symbols, dt.sym)
+    assert float(Lp.values(Lp.stiff[2][2])) == -1.0 and forms._is_zero(Lp.src[2] - 0.5 * u[0])
+
+
+def test_dirichlet_boundaries():
+    W, w, w0, w_ = _ch(3)
+    sub = W.split()[2]
+    left = df.DirichletBC(sub, df.Constant(0.0), lambda x, on: on and df.near(x[0], 0.0, 1e-12))
+    right = df.DirichletBC(sub, df.Expression("sin(x[1]/7)", degree=2), lambda x, on: on and df.near(x[0], 10.0, 1e-12))
+    assert (left.side, left.field, left.value_expr) == ("left", 2, 0)
+    assert right.side == "right" and str(right.value_expr) == "sin(x1/7)"
+    with pytest.raises(NotImplementedError):
+        df.DirichletBC(sub, df.Constant(0.0), lambda x, on: on)          # the whole boundary
+    with pytest.raises(NotImplementedError):
+        df.DirichletBC(W, df.Constant(0.0), lambda x, on: on and df.near(x[0], 0.0))
+
+
+def test_functional_plans():
+    """df.assemble plans: the fused energy kernel gives the benchmark's two integrals; pieces with other gradient
+    coefficients are corrected by u^T K u terms (bench2.py:187-194 assembles the energy in five pieces)."""
+    W, w, w0, w_ = _ch(6)
+    p = engine.PROBLEMS["bench2"][2]
+    c, mu, *eta = df.split(w)
+    H = sum(e ** 3 * (6 * e ** 2 - 15 * e + 10) for e in eta)
+    Wd = sum(e ** 2 * (1 - e) ** 2 for e in eta) + p[7] * sum(eta[i] ** 2 * eta[j] ** 2 for i in range(4) for j in range(i + 1, 4))
+    f = p[2] * (c - p[0]) ** 2 * (1 - H) + p[2] * (c - p[1]) ** 2 * H + p[6] * Wd
+    kc, ke = df.Constant(p[3]), df.Constant(p[4])
+    which, scale, corr = forms.plan_functional(f * dx + kc / 2.0 * inner(grad(c), grad(c)) * dx, "bench2", p, w.symbols)
+    assert (which, scale) == (0, 1.0) and corr == [(k, pytest.approx(-1.5)) for k in (2, 3, 4, 5)]
+    assert forms.plan_functional(ke / 2.0 * inner(grad(eta[1]), grad(eta[1])) * dx, "bench2", p, w.symbols) == (None, 1.0, [(3, 1.5)])
+    assert forms.plan_functional(c * dx, "bench2", p, w.symbols) == (1, 1.0, [])
+    with pytest.raises(NotImplementedError):
+        forms.plan_functional(c ** 2 * dx, "bench2", p, w.symbols)
+    with pytest.raises(NotImplementedError):
+        forms.plan_functional(inner(grad(c), grad(mu)) * dx, "bench2", p, w.symbols)
+
+
+def test_quadrature_degree_is_checked():
+    W, w, w0, w_ = _ch()
+    dt, one = df.Constant(0.1), df.Constant(1.0)
+    c, mu = df.split(w)
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, one, one, df.diff((c - 0.3) ** 2 * (0.7 - c) ** 2, c))
+    df.parameters["form_compiler"]["quadrature_degree"] = 2
+    try:
+        with pytest.raises(NotImplementedError, match="degree-3"):
+            df.NonlinearVariationalProblem(F, w, [], df.derivative(F, w, df.TrialFunction(W)))
+    finally:
+        df.parameters["form_compiler"]["quadrature_degree"] = 3
+    with pytest.raises(NotImplementedError, match="derivative"):
+        df.NonlinearVariationalProblem(F, w, [], J="something else")
+
+
+def test_function_storage_is_deferred():
+    W, w, w0, w_ = _ch()
+    with pytest.raises(RuntimeError, match="no storage"):
+        w.tensor
+    with pytest.raises(NotImplementedError):
+        df.Constant((1.0, 0.0))
+    assert isinstance(df.Constant((0.0, 0.0)), forms.VectorZero)
+    with pytest.raises(NotImplementedError):
+        df.HDF5File(None, "x.h5", "w")
