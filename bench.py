@@ -184,6 +184,7 @@ def run_b200(args):
     dof = ctx.nf * ctx.n_global
     if world > 1 and os.environ.get("PFH_OVERLAP", "1") == "0":
         ctx.set_option("overlap", 0)
+    ctx.set_option("basis_precision", {"auto": 0, "fp64": 1, "fp32": 2}[args.basis])
     opts = _lib.default_opts(krylov_restart=args.restart, pc_variant=args.pc_variant, pc_sweeps_mass=args.sweeps_mass,
                              pc_sweeps_shifted=args.sweeps_shifted, krylov_maximum_iterations=max(1000, int(n ** 3 / 10)) if args.workload == "b13d" else 1000,
                              line_search=1 if args.workload in ("bench2", "bench6") else 0)
@@ -319,8 +320,9 @@ def run_b200(args):
                 "config": {"workload": ("b13d_kuhn3d_%d" % args.grid) if args.workload == "b13d" else "%s_crossed2d_%d" % (args.workload, args.grid),
                            "grid_vertices": [args.grid] * 3 if args.workload == "b13d" else [args.grid + 1] * 2, "dof": dof,
                            "fields": ",".join(ctx.field_names), "dt_list": dts[args.warmup:], "parallelism": "z-slabs x%d" % world,
-                           "solver": "newton(atol 1e-6, max 10) + GMRES(%d, rtol 1e-5) + Schur/Chebyshev(%d,%d,%s)" % (
-                               args.restart, args.sweeps_mass, args.sweeps_shifted, "upper" if args.pc_variant else "full"),
+                           "solver": "newton(atol 1e-6, max 10) + GMRES(%d, rtol 1e-5, basis stored %s) + Schur/Chebyshev(%d,%d,%s)" % (
+                               args.restart, "fp64" if args.basis == "fp64" else "fp32", args.sweeps_mass, args.sweeps_shifted,
+                               "upper" if args.pc_variant else "full"),
                            "l2_policy": ("inputs_exceed_l2 (every vector is %.0f MB >> 126 MB L2)" % (bytes_vec / 1e6)) if bytes_vec > 2.6e8
                            else "L2-resident working set (%.1f MB per vector): launch-bound regime, no flush" % (bytes_vec / 1e6)},
                 "newton_its": newton, "krylov_its": krylov, "energy": reports[-1]["energy"], "solute": reports[-1]["solute"],
@@ -352,6 +354,8 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=64, help="sample grid of the cpu_baseline leg")
     ap.add_argument("--ref-grid", type=int, default=64, help="sample grid of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--basis", default="auto", choices=["auto", "fp64", "fp32"],
+                    help="Krylov basis storage (auto: fp32 at the default linear tolerance, DESIGN.md section 5)")
     args = ap.parse_args()
     if args.warmup < 3:
         print("warning: timing rules ask for >= 3 warm-up steps", file=sys.stderr)

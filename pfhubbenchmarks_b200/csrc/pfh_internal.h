@@ -178,6 +178,7 @@ struct pfh_ctx {
   // fused two-sweep (temporally blocked) Chebyshev kernels (pfh_cheb2_tma.cu): correct, but shared-memory-bandwidth
   // bound and 1.45x slower per solve than the per-sweep TMA kernel at 512^3 (profiles/README.md), so opt-in only
   bool use_fused = false;
+  int basis_precision = 0;  // Krylov basis storage: 0 = fp32 when krylov_rtol >= 1e-6 else fp64, 1 = fp64, 2 = fp32
   bool use_tma = true;  // 3-D fast path: TMA-staged kernels (pfh_stencil3_tma.cu); false = gather kernels only
 };
 
@@ -252,6 +253,13 @@ void v_multiaxpy(pfh_ctx* c, const double* V, long long stride, int nv, const do
 // out = sum_k y[k] V_k
 void v_combine(pfh_ctx* c, const double* V, long long stride, int nv, const double* y, double* out,
                long long n);
+// the same three with the basis stored in fp32 (compressed-basis GMRES); multiaxpy32 also stores the fp32-rounded
+// result in out32 (may be null), writes that rounded value, widened, to out, and returns its global squared norm
+// in *norm2 (may be null) from the same pass
+void v_multidot32(pfh_ctx* c, const float* V, long long stride, int nv, const double* w, long long n, double* host_out);
+void v_multiaxpy32(pfh_ctx* c, const float* V, long long stride, int nv, const double* h, const double* w, double scale,
+                   double* out, float* out32, long long n, double* norm2);
+void v_combine32(pfh_ctx* c, const float* V, long long stride, int nv, const double* y, double* out, long long n);
 double v_norm2(pfh_ctx* c, const double* x, long long n);  // global ||x||_2^2 on the host
 // finish a two-stage reduction: sums d_partial[nblocks][nvals] -> allreduce -> host; returns h_red
 const double* pfh_reduce_finish(pfh_ctx* c, int nblocks, int nvals);

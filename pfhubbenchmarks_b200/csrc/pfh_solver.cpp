@@ -339,12 +339,16 @@ struct KspResult {
 
 // Solves J x = b. Workspace use: V (basis), W1 (w), W2 (z / precond scratch), R is free for the
 // preconditioner because the Newton loop has already moved -R into `b` (= DX's companion buffer).
+//
+KspResult gmres_compressed(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o, pfh_solve_report* rep);
+
 KspResult gmres(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o, pfh_solve_report* rep) {
   const long long N = c->nf * c->n_owned;
   const long long vs = (N + 31) / 32 * 32;
   const int m = std::max(1, std::min(o.krylov_restart > 0 ? o.krylov_restart : 30, c->cfg.krylov_basis));
   double* V = c->V;
   double* w = c->W1;
+  if (c->basis_precision == 2 || (c->basis_precision == 0 && o.krylov_rtol >= 1e-6)) return gmres_compressed(c, b, x, o, rep);
   std::vector<double> H((m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), h(m + 2);
   auto Hij = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
 
@@ -427,6 +431,103 @@ KspResult gmres(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o
     beta = std::sqrt(v_norm2(c, w, N));
     if (beta <= tol) return {its, beta / bnorm, true};
     v_scale(c, 1.0 / beta, w, V, N);
+  }
+}
+
+// Compressed-basis GMRES.  The orthogonalisation (multi-dot + multi-axpy over the whole basis) is pure HBM
+// streaming and a third of the step, so at the default linear tolerance the basis is STORED in fp32 while all
+// arithmetic stays fp64.  Stored vector u_i is the fp32 rounding of a multiple of the Arnoldi vector, u_i = s_i v_i
+// with s_i = ||u_i|| measured (in the pass that writes it) on the rounded values; the fp64 working copy handed to
+// the preconditioner is that same rounded vector.  With w~ = J P^-1 u_j = s_j A v_j and d_i = u_i . w~:
+//     h_ij = d_i / (s_i s_j),   r~ = w~ - sum_i (d_i / s_i^2) u_i = s_j h_{j+1,j} v_{j+1},
+//     u_{j+1} = round(a r~)  (a = 1 / Pythagoras estimate of ||r~||, only to keep s near 1),   h_{j+1,j} = s_{j+1} / (a s_j).
+// The Arnoldi relation then holds for the stored basis up to the rounding of u_{j+1} (6e-8 relative): no norm is
+// ever taken from the Pythagorean difference, which loses all accuracy against a basis that is orthonormal only to
+// fp32 (measured: +26 % iterations, tests/probe/README.md).  The true residual is recomputed in fp64 at every restart.
+KspResult gmres_compressed(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o, pfh_solve_report* rep) {
+  const long long N = c->nf * c->n_owned;
+  const long long vs = (N + 31) / 32 * 32;
+  const int m = std::max(1, std::min(o.krylov_restart > 0 ? o.krylov_restart : 30, c->cfg.krylov_basis));
+  float* U = reinterpret_cast<float*>(c->V);                            // fp32 basis shares the allocation ...
+  double* ucur = c->V + ((long long)(m + 1) * vs / 2 + 31) / 32 * 32;   // ... and the fp64 working copy sits behind it
+  double* w = c->W1;
+  std::vector<double> H((m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), d(m + 2), sv(m + 1), cf(m + 1);
+  auto Hij = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
+
+  v_zero(c, x, N);
+  const double bnorm = std::sqrt(v_norm2(c, b, N));
+  if (bnorm == 0.0) return {0, 0.0, true};
+  const double tol = std::fmax(o.krylov_rtol * bnorm, o.krylov_atol);
+  double beta = bnorm;
+  const double* r = b;
+  int its = 0;
+  while (true) {
+    double s2 = 0.0;
+    v_multiaxpy32(c, U, vs, 0, nullptr, r, 1.0 / beta, ucur, U, N, &s2);   // u_0 = round(r / beta)
+    sv[0] = std::sqrt(s2);
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta * sv[0];                                                   // r = beta u_0 = beta s_0 v_0
+    int jd = 0;
+    bool done = false;
+    for (int j = 0; j < m; ++j) {
+      s_precond_apply(c, ucur, c->DX2);
+      rep->pc_applies++;
+      s_jac_apply(c, c->DX2, w);
+      rep->jac_applies++;
+      v_multidot32(c, U, vs, j + 1, w, N, d.data());
+      const double ww = d[j + 1];
+      double est = ww;
+      for (int i = 0; i <= j; ++i) {
+        cf[i] = d[i] / (sv[i] * sv[i]);
+        est -= d[i] * d[i] / (sv[i] * sv[i]);
+      }
+      const double a = ww > 0.0 ? 1.0 / std::sqrt(std::fmax(est, 1e-8 * ww)) : 1.0;
+      v_multiaxpy32(c, U, vs, j + 1, cf.data(), w, a, ucur, U + (long long)(j + 1) * vs, N, &s2);
+      sv[j + 1] = std::sqrt(s2);
+      const double hn = sv[j + 1] / (a * sv[j]);
+      for (int i = 0; i <= j; ++i) Hij(i, j) = d[i] / (sv[i] * sv[j]);
+      Hij(j + 1, j) = hn;
+      for (int i = 0; i < j; ++i) {
+        const double t = cs[i] * Hij(i, j) + sn[i] * Hij(i + 1, j);
+        Hij(i + 1, j) = -sn[i] * Hij(i, j) + cs[i] * Hij(i + 1, j);
+        Hij(i, j) = t;
+      }
+      const double den = std::hypot(Hij(j, j), Hij(j + 1, j));
+      cs[j] = Hij(j, j) / den;
+      sn[j] = Hij(j + 1, j) / den;
+      Hij(j, j) = den;
+      Hij(j + 1, j) = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      ++its;
+      jd = j + 1;
+      if (o.verbose > 1) fprintf(stderr, "      gmres it %3d  |r|/|b| = %.3e\n", its, std::fabs(g[j + 1]) / bnorm);
+      if (!(std::fabs(g[j + 1]) == std::fabs(g[j + 1]))) return {its, NAN, false};
+      if (std::fabs(g[j + 1]) <= tol || its >= o.krylov_maximum_iterations || !(sv[j + 1] > 0.0)) {
+        done = true;
+        break;
+      }
+    }
+    // y = H^-1 g ; x += P^-1 (sum_j (y_j / s_j) u_j)
+    for (int i = jd - 1; i >= 0; --i) {
+      double s = g[i];
+      for (int k = i + 1; k < jd; ++k) s -= Hij(i, k) * y[k];
+      y[i] = s / Hij(i, i);
+    }
+    for (int i = 0; i < jd; ++i) cf[i] = y[i] / sv[i];
+    v_combine32(c, U, vs, jd, cf.data(), w, N);
+    s_precond_apply(c, w, c->DX2);
+    rep->pc_applies++;
+    v_axpy(c, 1.0, c->DX2, x, N);
+    const double estr = std::fabs(g[jd]);
+    if (done) return {its, estr / bnorm, estr <= tol};
+    // restart: true residual r = b - J x
+    s_jac_apply(c, x, w);
+    rep->jac_applies++;
+    v_axpby(c, 1.0, b, -1.0, w, w, N);
+    beta = std::sqrt(v_norm2(c, w, N));
+    if (beta <= tol) return {its, beta / bnorm, true};
+    r = w;
   }
 }
 

@@ -24,32 +24,68 @@ struct Coef {
   double v[MD];
 };
 
+// Basis vectors are stored in fp64 or, for the compressed-basis GMRES (pfh_solver.cpp), in fp32; arithmetic is fp64.
+// Every thread moves 16-byte chunks of each basis vector: 2 doubles or 4 floats (same bytes in flight either way).
+template <class TV>
+struct Chunk;
+template <>
+struct Chunk<double> {
+  static constexpr int E = 2;
+  static __device__ __forceinline__ void load(const double* p, long long i, double (&v)[2]) {
+    const double2 t = reinterpret_cast<const double2*>(p)[i];
+    v[0] = t.x; v[1] = t.y;
+  }
+};
+template <>
+struct Chunk<float> {
+  static constexpr int E = 4;
+  static __device__ __forceinline__ void load(const float* p, long long i, double (&v)[4]) {
+    const float4 t = reinterpret_cast<const float4*>(p)[i];
+    v[0] = (double)t.x; v[1] = (double)t.y; v[2] = (double)t.z; v[3] = (double)t.w;
+  }
+};
+template <int E>
+__device__ __forceinline__ void load_w(const double* p, long long i, double (&v)[E]) {
+#pragma unroll
+  for (int q = 0; q < E / 2; ++q) {
+    const double2 t = reinterpret_cast<const double2*>(p)[i * (E / 2) + q];
+    v[2 * q] = t.x; v[2 * q + 1] = t.y;
+  }
+}
+
 // partial[block][k0 + k] = sum_i V_{k0+k}[i] w[i] (k < nb); if WW also partial[block][ww_slot] = sum w^2
-template <bool WW>
-__global__ void __launch_bounds__(TPB) k_multidot(const double* __restrict__ V, long long stride, int nb, int k0, int ww_slot,
+template <bool WW, class TV>
+__global__ void __launch_bounds__(TPB) k_multidot(const TV* __restrict__ V, long long stride, int nb, int k0, int ww_slot,
                                                   const double* __restrict__ w, long long n, double* __restrict__ partial) {
+  constexpr int E = Chunk<TV>::E;
   double acc[MD + 1];
 #pragma unroll
   for (int k = 0; k <= MD; ++k) acc[k] = 0.0;
-  const long long n2 = n >> 1;
-  const double2* w2 = reinterpret_cast<const double2*>(w);
-  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n2; i += (long long)gridDim.x * TPB) {
-    const double2 wi = w2[i];
+  const long long nc = n / E;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < nc; i += (long long)gridDim.x * TPB) {
+    double wi[E];
+    load_w<E>(w, i, wi);
 #pragma unroll
     for (int k = 0; k < MD; ++k)
       if (k < nb) {
-        const double2 vi = reinterpret_cast<const double2*>(V + (long long)k * stride)[i];
-        acc[k] += vi.x * wi.x + vi.y * wi.y;
-      }
-    if (WW) acc[MD] += wi.x * wi.x + wi.y * wi.y;
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const double wi = w[n - 1];
+        double vi[E];
+        Chunk<TV>::load(V + (long long)k * stride, i, vi);
 #pragma unroll
-    for (int k = 0; k < MD; ++k)
-      if (k < nb) acc[k] += V[(long long)k * stride + n - 1] * wi;
-    if (WW) acc[MD] += wi * wi;
+        for (int e = 0; e < E; ++e) acc[k] += vi[e] * wi[e];
+      }
+    if (WW) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[MD] += wi[e] * wi[e];
+    }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long t = nc * E; t < n; ++t) {
+      const double wi = w[t];
+#pragma unroll
+      for (int k = 0; k < MD; ++k)
+        if (k < nb) acc[k] += (double)V[(long long)k * stride + t] * wi;
+      if (WW) acc[MD] += wi * wi;
+    }
   __shared__ double sh[MD + 1][TPB / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -68,32 +104,74 @@ __global__ void __launch_bounds__(TPB) k_multidot(const double* __restrict__ V, 
 }
 
 // out = wscale * w - sum_k h[k] V_k   (HAS_W false: out = - sum_k h[k] V_k)
-template <bool HAS_W>
-__global__ void __launch_bounds__(TPB) k_multiaxpy(const double* __restrict__ V, long long stride, int nb, Coef h,
-                                                   const double* w, double wscale, double* out, long long n) {
-  const long long n2 = n >> 1;
-  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < n2; i += (long long)gridDim.x * TPB) {
-    double2 r = make_double2(0.0, 0.0);
+// out32 != nullptr: the result is rounded to fp32 and stored there (the next compressed basis vector); `out` then
+// receives that rounded value, so the fp64 working copy and the stored basis vector are the same vector.
+// NORM: partial[block][0] = sum over this block's elements of (stored result)^2, for the norm of the new basis vector
+template <bool HAS_W, class TV, bool NORM>
+__global__ void __launch_bounds__(TPB) k_multiaxpy(const TV* __restrict__ V, long long stride, int nb, Coef h,
+                                                   const double* w, double wscale, double* out, float* out32, long long n,
+                                                   double* __restrict__ partial) {
+  constexpr int E = Chunk<TV>::E;
+  double nacc = 0.0;
+  const long long nc = n / E;
+  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < nc; i += (long long)gridDim.x * TPB) {
+    double r[E];
     if (HAS_W) {
-      r = reinterpret_cast<const double2*>(w)[i];
-      r.x *= wscale;
-      r.y *= wscale;
+      load_w<E>(w, i, r);
+#pragma unroll
+      for (int e = 0; e < E; ++e) r[e] *= wscale;
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) r[e] = 0.0;
     }
 #pragma unroll
     for (int k = 0; k < MD; ++k)
       if (k < nb) {
-        const double2 vi = reinterpret_cast<const double2*>(V + (long long)k * stride)[i];
-        r.x -= h.v[k] * vi.x;
-        r.y -= h.v[k] * vi.y;
-      }
-    reinterpret_cast<double2*>(out)[i] = r;
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    double r = HAS_W ? w[n - 1] * wscale : 0.0;
+        double vi[E];
+        Chunk<TV>::load(V + (long long)k * stride, i, vi);
 #pragma unroll
-    for (int k = 0; k < MD; ++k)
-      if (k < nb) r -= h.v[k] * V[(long long)k * stride + n - 1];
-    out[n - 1] = r;
+        for (int e = 0; e < E; ++e) r[e] -= h.v[k] * vi[e];
+      }
+    if (out32) {
+#pragma unroll
+      for (int q = 0; q < E / 2; ++q) {
+        const float2 f = make_float2((float)r[2 * q], (float)r[2 * q + 1]);
+        reinterpret_cast<float2*>(out32)[i * (E / 2) + q] = f;
+        r[2 * q] = (double)f.x;
+        r[2 * q + 1] = (double)f.y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < E / 2; ++q) {
+      if (NORM) nacc += r[2 * q] * r[2 * q] + r[2 * q + 1] * r[2 * q + 1];
+      reinterpret_cast<double2*>(out)[i * (E / 2) + q] = make_double2(r[2 * q], r[2 * q + 1]);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long t = nc * E; t < n; ++t) {
+      double r = HAS_W ? w[t] * wscale : 0.0;
+#pragma unroll
+      for (int k = 0; k < MD; ++k)
+        if (k < nb) r -= h.v[k] * (double)V[(long long)k * stride + t];
+      if (out32) {
+        out32[t] = (float)r;
+        r = (double)out32[t];
+      }
+      if (NORM) nacc += r * r;
+      out[t] = r;
+    }
+  if (NORM) {
+    __shared__ double sh[TPB / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    nacc = warp_sum(nacc);
+    if (lane == 0) sh[wid] = nacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < TPB / 32; ++q) t += sh[q];
+      partial[blockIdx.x * PFH_RED_MAXVALS] = t;
+    }
   }
 }
 
@@ -171,20 +249,21 @@ void v_axpby(pfh_ctx* c, double a, const double* x, double b, const double* y, d
 void v_axpy(pfh_ctx* c, double a, const double* x, double* y, long long n) { v_axpby(c, a, x, 1.0, y, y, n); }
 void v_scale(pfh_ctx* c, double a, const double* x, double* out, long long n) { v_axpby(c, a, x, 0.0, nullptr, out, n); }
 
-void v_multidot(pfh_ctx* c, const double* V, long long stride, int nv, const double* w, long long n, double* host_out) {
+template <class TV>
+static void multidot_t(pfh_ctx* c, const TV* V, long long stride, int nv, const double* w, long long n, double* host_out) {
   PFH_CHECK(nv + 1 <= PFH_RED_MAXVALS, "too many basis vectors for the reduction scratch");
-  PFH_CHECK((stride & 1) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+  PFH_CHECK((stride & 3) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
             "multidot operands must be 16-byte aligned");
   const int nb = grid_stream(n);
   int k0 = 0;
   do {
     const int cnt = nv - k0 < MD ? nv - k0 : MD;
     const bool last = k0 + cnt >= nv;
-    ProfScope ps(c, T_MULTIDOT, 8.0 * (cnt + 1) * n);
+    ProfScope ps(c, T_MULTIDOT, ((double)sizeof(TV) * cnt + 8.0) * n);
     if (last)
-      k_multidot<true><<<nb, TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, k0, nv, w, n, c->d_partial);
+      k_multidot<true, TV><<<nb, TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, k0, nv, w, n, c->d_partial);
     else
-      k_multidot<false><<<nb, TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, k0, nv, w, n, c->d_partial);
+      k_multidot<false, TV><<<nb, TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, k0, nv, w, n, c->d_partial);
     PFH_CUDA(cudaGetLastError());
     k0 += cnt;
   } while (k0 < nv);
@@ -192,11 +271,13 @@ void v_multidot(pfh_ctx* c, const double* V, long long stride, int nv, const dou
   for (int k = 0; k <= nv; ++k) host_out[k] = h[k];
 }
 
-// out = wscale * w - sum_k coef_k V_k, MD basis vectors per pass (w == nullptr: no w term)
-static void multiaxpy_raw(pfh_ctx* c, const double* V, long long stride, int nv, const double* coef, const double* w,
-                          double wscale, double* out, long long n) {
-  PFH_CHECK((stride & 1) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+// out = wscale * w - sum_k coef_k V_k, MD basis vectors per pass (w == nullptr: no w term); the last pass also
+// writes the fp32-rounded result to out32 when given
+template <class TV>
+static void multiaxpy_raw(pfh_ctx* c, const TV* V, long long stride, int nv, const double* coef, const double* w,
+                          double wscale, double* out, float* out32, long long n, double* norm2 = nullptr) {
+  PFH_CHECK((stride & 3) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(out32) & 7) == 0,
             "multiaxpy operands must be 16-byte aligned");
   int k0 = 0;
   bool first = true;
@@ -205,29 +286,55 @@ static void multiaxpy_raw(pfh_ctx* c, const double* V, long long stride, int nv,
     Coef cf;
     for (int k = 0; k < MD; ++k) cf.v[k] = k < cnt ? coef[k0 + k] : 0.0;
     const double* win = first ? w : out;
-    ProfScope ps(c, T_MULTIAXPY, 8.0 * (cnt + (win ? 2 : 1)) * n);
-    if (win)
-      k_multiaxpy<true><<<grid_stream(n), TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, cf, win,
-                                                              first ? wscale : 1.0, out, n);
-    else
-      k_multiaxpy<false><<<grid_stream(n), TPB, 0, c->stream>>>(V + (long long)k0 * stride, stride, cnt, cf, nullptr, 0.0, out, n);
+    const bool last = k0 + cnt >= nv;
+    float* o32 = last ? out32 : nullptr;
+    ProfScope ps(c, T_MULTIAXPY, ((double)sizeof(TV) * cnt + 8.0 * (win ? 2 : 1) + (o32 ? 4.0 : 0.0)) * n);
+    const int nb = grid_stream(n);
+    const TV* Vk = V + (long long)k0 * stride;
+    if (last && norm2) {
+      PFH_CHECK(win != nullptr, "multiaxpy: norm needs a w term");
+      k_multiaxpy<true, TV, true><<<nb, TPB, 0, c->stream>>>(Vk, stride, cnt, cf, win, first ? wscale : 1.0, out, o32, n, c->d_partial);
+    } else if (win) {
+      k_multiaxpy<true, TV, false><<<nb, TPB, 0, c->stream>>>(Vk, stride, cnt, cf, win, first ? wscale : 1.0, out, o32, n, nullptr);
+    } else {
+      k_multiaxpy<false, TV, false><<<nb, TPB, 0, c->stream>>>(Vk, stride, cnt, cf, nullptr, 0.0, out, o32, n, nullptr);
+    }
     PFH_CUDA(cudaGetLastError());
     first = false;
     k0 += cnt;
   } while (k0 < nv);
+  if (norm2) *norm2 = pfh_reduce_finish(c, grid_stream(n), 1)[0];
+}
+
+void v_multidot(pfh_ctx* c, const double* V, long long stride, int nv, const double* w, long long n, double* host_out) {
+  multidot_t(c, V, stride, nv, w, n, host_out);
+}
+void v_multidot32(pfh_ctx* c, const float* V, long long stride, int nv, const double* w, long long n, double* host_out) {
+  multidot_t(c, V, stride, nv, w, n, host_out);
 }
 
 void v_multiaxpy(pfh_ctx* c, const double* V, long long stride, int nv, const double* h, const double* w, double scale,
                  double* out, long long n) {
   std::vector<double> cf(nv);
   for (int k = 0; k < nv; ++k) cf[k] = scale * h[k];
-  multiaxpy_raw(c, V, stride, nv, cf.data(), w, scale, out, n);
+  multiaxpy_raw(c, V, stride, nv, cf.data(), w, scale, out, nullptr, n);
+}
+void v_multiaxpy32(pfh_ctx* c, const float* V, long long stride, int nv, const double* h, const double* w, double scale,
+                   double* out, float* out32, long long n, double* norm2) {
+  std::vector<double> cf(nv);
+  for (int k = 0; k < nv; ++k) cf[k] = scale * h[k];
+  multiaxpy_raw(c, V, stride, nv, cf.data(), w, scale, out, out32, n, norm2);
 }
 
 void v_combine(pfh_ctx* c, const double* V, long long stride, int nv, const double* y, double* out, long long n) {
   std::vector<double> cf(nv);
   for (int k = 0; k < nv; ++k) cf[k] = -y[k];
-  multiaxpy_raw(c, V, stride, nv, cf.data(), nullptr, 0.0, out, n);
+  multiaxpy_raw(c, V, stride, nv, cf.data(), nullptr, 0.0, out, nullptr, n);
+}
+void v_combine32(pfh_ctx* c, const float* V, long long stride, int nv, const double* y, double* out, long long n) {
+  std::vector<double> cf(nv);
+  for (int k = 0; k < nv; ++k) cf[k] = -y[k];
+  multiaxpy_raw(c, V, stride, nv, cf.data(), nullptr, 0.0, out, nullptr, n);
 }
 
 double v_norm2(pfh_ctx* c, const double* x, long long n) {

@@ -339,3 +339,43 @@ def test_snes_callback_boundary_drives_the_same_operators():
     assert rep["converged"]
     assert rel_l2(x.cpu().numpy(), w.cpu().numpy()) < 1e-10
     ctx.close()
+
+
+def test_compressed_krylov_basis():
+    """The GMRES basis is stored in fp32 at the default linear tolerance (fp64 arithmetic): the
+    Newton solve converges to the same solution as with the fp64 basis (both to the nonlinear tolerance), with
+    essentially the same Krylov iteration count; a tight linear tolerance selects the fp64 basis by itself."""
+    from pfhubbenchmarks_b200 import engine
+    out = {}
+    for mode in (1, 2, 0):
+        ctx = engine.Context("b13d", (48, 40, 36), (96.0, 80.0, 72.0))
+        ctx.set_option("basis_precision", mode)
+        w0 = ctx.initial_condition()
+        w = w0.clone()
+        its = 0
+        for dt in (0.1, 0.2, 0.4):
+            ctx.dt = dt
+            w0.copy_(w)
+            rep = ctx.newton_solve(w, w0, absolute_tolerance=1e-9)
+            assert rep["converged"], rep
+            its += rep["krylov_its"]
+        out[mode] = (w.cpu().numpy().reshape(2, -1), its, ctx.energy(w))
+        ctx.close()
+    c64, i64, e64 = out[1]
+    c32, i32, e32 = out[2]
+    assert rel_l2(c32[0], c64[0]) < 1e-9 and abs(e32[0] / e64[0] - 1) < 1e-10
+    assert abs(i32 - i64) <= max(2, i64 // 20), (i32, i64)
+    assert np.array_equal(out[0][0], c32) and out[0][1] == i32          # auto = fp32 at krylov_rtol 1e-5
+    # tight linear tolerance: auto falls back to the fp64 basis
+    res = {}
+    for mode in (1, 0):
+        ctx = engine.Context("b13d", (24, 20, 18), (48.0, 40.0, 36.0))
+        ctx.set_option("basis_precision", mode)
+        w0 = ctx.initial_condition()
+        w = w0.clone()
+        ctx.dt = 0.1
+        rep = ctx.newton_solve(w, w0, absolute_tolerance=1e-10, krylov_rtol=1e-9, maximum_iterations=25)
+        assert rep["converged"]
+        res[mode] = w.cpu().numpy()
+        ctx.close()
+    assert np.array_equal(res[0], res[1])
