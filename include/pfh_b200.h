@@ -137,6 +137,12 @@ int pfh_energy_dev(pfh_ctx* ctx, const double* w, double out[4]);
  * parameter: that is ak = kappa_eta/2, a = b = 2+i.  am = 1, ak = 0 gives int u_a u_b dx. */
 int pfh_bilinear_dev(pfh_ctx* ctx, const double* w, int field_a, int field_b, double am, double ak, double* out);
 
+/* f(x) of the reference's peval / sample (dolfin/pfbase.py:50-94): the P1 interpolant of field `field` of w at
+ * npts points (pts: npts x dim, row-major; pts and out are DEVICE pointers).  Points outside the mesh give +inf
+ * (peval's fill value for points a rank cannot evaluate).  Slab-decomposed meshes: every rank passes the same points
+ * and receives all values. */
+int pfh_eval_points_dev(pfh_ctx* ctx, const double* w, int field, const double* pts, long long npts, double* out);
+
 /* Host-buffer entry points (reference-facing plugin call; copies inside): one full
  * backward-Euler step w0 -> w at the given dt, plus the step's diagnostics. */
 int pfh_step_host(pfh_ctx* ctx, double* w_host /* in: guess, out: solution */, const double* w0_host,

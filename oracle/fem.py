@@ -78,3 +78,23 @@ class P1Space:
 
     def integrate(self, eq):
         return float(np.dot(eq, self.qw))
+
+
+def eval_points(mesh, u, pts, tol=1e-10):
+    """f(x) of the reference's peval/sample (dolfin/pfbase.py:50-94): value of the P1 function with vertex values `u`
+    at each point, by searching ALL cells for one whose barycentric coordinates are >= -tol (no use of the mesh
+    structure; O(ncells * npts), small cases only).  Points in no cell give +inf, as peval's fill value."""
+    X, C = mesh.coords, mesh.cells
+    d = mesh.dim
+    P = X[C]                                                       # (nc, d+1, d)
+    T = np.transpose(P[:, 1:, :] - P[:, :1, :], (0, 2, 1))         # columns = edge vectors
+    Tinv = np.linalg.inv(T)
+    out = np.full(len(pts), np.inf)
+    for k, x in enumerate(np.asarray(pts, dtype=float)):
+        lam = np.einsum("cij,cj->ci", Tinv, x[None, :] - P[:, 0, :])          # lambda_1..d
+        lam0 = 1.0 - lam.sum(axis=1)
+        ok = np.where((lam.min(axis=1) >= -tol) & (lam0 >= -tol))[0]
+        if ok.size:
+            c = ok[0]
+            out[k] = lam0[c] * u[C[c, 0]] + lam[c] @ u[C[c, 1:]]
+    return out

@@ -60,6 +60,7 @@ SIGNATURES = {
     "pfh_precond_apply_dev": (C.c_int, [_P, _P, _P]),
     "pfh_newton_solve_dev": (C.c_int, [_P, _P, _P, C.POINTER(SolverOpts), C.POINTER(SolveReport)]),
     "pfh_energy_dev": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
+    "pfh_eval_points_dev": (C.c_int, [_P, _P, C.c_int, _P, C.c_longlong, _P]),
     "pfh_bilinear_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     "pfh_step_host": (C.c_int, [_P, _P, _P, C.c_double, C.POINTER(SolverOpts), C.POINTER(SolveReport),
                                 C.POINTER(C.c_double)]),

@@ -321,6 +321,17 @@ int pfh_bilinear_dev(pfh_ctx* c, const double* w, int fa, int fb, double am, dou
   PFH_API_END
 }
 
+int pfh_eval_points_dev(pfh_ctx* c, const double* w, int field, const double* pts, long long npts, double* out) {
+  PFH_API_BEGIN
+  PFH_CHECK(c && w && (npts == 0 || (pts && out)), "null argument");
+  PFH_CHECK(field >= 0 && field < c->nf && npts >= 0, "field index out of range");
+  PFH_CHECK(npts < (1LL << 31), "too many points for one call");
+  PFH_CUDA(cudaSetDevice(c->cfg.device));
+  k_eval_points(c, s_field_ref(c, w + (long long)field * c->n_owned), pts, npts, out);
+  if (c->cfg.nranks > 1 && npts > 0) comm_allreduce_sum(c, out, (int)npts);
+  PFH_API_END
+}
+
 static void stage(pfh_ctx* c) {
   const long long N = c->nf * c->n_owned;
   if (!c->U) {

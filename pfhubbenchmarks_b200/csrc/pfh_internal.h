@@ -219,6 +219,7 @@ void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const do
                   double* zprev, bool zprev_is_zero);  // zprev_is_zero: zprev is write-only (z_{k-1} = 0)
 // point-Jacobi on the Jacobian diagonal blocks: z_a = r_a / diag_a
 void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z);
+void k_eval_points(pfh_ctx* c, FieldRef f, const double* pts, long long npts, double* out);  // pfh_sample.cu
 void k_energy(pfh_ctx* c, const double* u, double out[4]);  // includes final reduction + allreduce + D2H
 void k_initial_condition(pfh_ctx* c, const double* icp, int n, double* w);
 void k_dirichlet_fix(pfh_ctx* c, double* w);  // impose Dirichlet values on the iterate (bench6)
@@ -278,6 +279,7 @@ int comm_unique_id(void* out);
 // ---- solver (pfh_solver.cpp) ----
 void s_exchange_state(pfh_ctx* c, const double* u, double* glo, double* ghi);
 void s_residual(pfh_ctx* c, const double* u, const double* u0, double* R, bool u0_ghost_current);
+FieldRef s_field_ref(pfh_ctx* c, const double* u);  // one field + its freshly exchanged ghost planes
 void s_bilinear_apply(pfh_ctx* c, const double* u, double am, double ak, double* out);  // out = (am M + ak K) u, one field
 void s_jac_setup(pfh_ctx* c, const double* u);
 void s_jac_apply(pfh_ctx* c, const double* x, double* y);

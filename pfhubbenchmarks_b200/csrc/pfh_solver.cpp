@@ -40,6 +40,8 @@ static FieldRef scalar_ref(pfh_ctx* c, const double* p) {
   return FieldRef{p, c->gS_lo, c->gS_hi};
 }
 
+FieldRef s_field_ref(pfh_ctx* c, const double* u) { return scalar_ref(c, u); }
+
 void s_bilinear_apply(pfh_ctx* c, const double* u, double am, double ak, double* out) {
   k_lin_apply(c, am, ak, scalar_ref(c, u), 0.0, nullptr, out);
 }

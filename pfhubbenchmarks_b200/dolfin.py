@@ -234,11 +234,38 @@ class Function:
     def split(self):                                   # c, _ = w.split()  (bench1.py:188)
         return self._problem.ctx.fields(self.tensor)
 
+    def sub(self, i):                                  # w.sub(0): a scalar component that can be evaluated, f(x)
+        return SubFunction(self, i)
+
     def vector(self):
         return self.tensor
 
     def to_numpy(self):
         return self.tensor.cpu().numpy().reshape(self.W.nfields, -1)
+
+
+class SubFunction:
+    """One component of a mixed Function: `f(x)` evaluates its P1 interpolant at a point (what pfbase.peval calls,
+    pfbase.py:50-62); `f.at(points)` does many points in one kernel launch."""
+
+    def __init__(self, owner, index):
+        self.owner, self.index = owner, index
+
+    def at(self, points):
+        return self.owner._problem.ctx.eval_points(self.owner.tensor, self.index, points)
+
+    def __call__(self, x):
+        v = float(self.at(np.asarray(x, dtype=float)[None, :])[0])
+        if not np.isfinite(v):
+            raise RuntimeError("point %r is outside the mesh" % (tuple(x),))     # dolfin raises the same way
+        return v
+
+    def value_shape(self):
+        return ()
+
+    @property
+    def tensor(self):
+        return self.owner.split()[self.index]
 
 
 def split(w):

@@ -166,6 +166,18 @@ class Context:
         _lib.check(self.lib.pfh_energy_dev(self._h, _ptr(w), out))
         return float(out[0]), float(out[1])
 
+    def eval_points(self, w, field, points):
+        """P1 interpolant of one field at `points` ((npts, dim) array): f(x) of pfbase.py:50-94; +inf outside the mesh."""
+        import torch
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
+        dev = torch.device("cuda", self.device)
+        d_pts = torch.from_numpy(pts).to(dev)
+        out = torch.empty(len(pts), dtype=torch.float64, device=dev)
+        if len(pts):
+            _lib.check(self.lib.pfh_eval_points_dev(self._h, _ptr(w), int(field), _ptr(d_pts.reshape(-1)), len(pts), _ptr(out)))
+            self.synchronize()               # the library ran on its own stream
+        return out.cpu().numpy()
+
     def bilinear(self, w, field_a, field_b, am, ak):
         """u_a^T (am M + ak K) u_b: one piece of a df.assemble functional (bench2.py:190-192)."""
         out = C.c_double()

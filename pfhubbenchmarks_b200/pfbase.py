@@ -12,10 +12,27 @@ natural no-flux boundaries) are
     diffusion_weak_form       du/dt = L div(D grad u + f1) + f2                           (pfbase.py:435-449)
     euler_bwd_weak_form       du/dt = f                                                   (pfbase.py:451-462)
 """
+import numpy as np
+
 from .api import (InitialConditionsBench1, InitialConditionsBench2, InitialConditionsBench3,  # noqa: F401
                   InitialConditionsBench6)
 from .dolfin import *  # noqa: F401,F403
 from .dolfin import MPI, HDF5File, dx, grad, inner  # noqa: F401
+
+
+def peval(f, x):
+    """Parallel-safe f(x) (pfbase.py:50-62): the value, or +inf where the point is outside the mesh.  `f` is a scalar
+    component, `w.sub(i)`.  On a slab-decomposed mesh the library already returns the value on every rank."""
+    return np.array([f.at(np.asarray(x, dtype=float)[None, :])[0]])
+
+
+def sample(u, Nx, Ny, Lx, Ly):
+    """xs, ys, us[Nx, Ny] on a regular lattice of the rectangle (pfbase.py:68-94) -- all Nx*Ny points in one launch."""
+    xs = np.linspace(0, Lx, Nx)
+    ys = np.linspace(0, Ly, Ny)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    us = u.at(np.stack([X.ravel(), Y.ravel()], axis=1)).reshape(Nx, Ny)
+    return xs, ys, us
 
 
 def _time_derivative(u, u_, u0, dt):

@@ -10,7 +10,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "libpfh_emul.so")
 _SRC = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_tables.cpp")]
 _DEPS = _SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", f)
-                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h")]
+                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh")]
 
 
 def build():
@@ -53,4 +53,19 @@ def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=
         return out.reshape(2, n)
     if mode in (5, 6):
         return out
+    return out
+
+
+def sample(mesh_kind, ncell, length, u, pts, z0=0, nzl=-1, glo=None, ghi=None):
+    """csrc/pfh_sample.cuh on the CPU: values at pts ((npts, dim)); +inf outside the mesh, NaN where a slab does not own the cube."""
+    lib = ctypes.CDLL(build())
+    nc = (ctypes.c_int * 3)(*(list(ncell) + [1] * (3 - len(ncell))))
+    ln = (ctypes.c_double * 3)(*(list(length) + [1.0] * (3 - len(length))))
+    arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (u, glo, ghi)]
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    out = np.zeros(len(pts))
+    lib.emul_sample.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P,
+                                ctypes.c_longlong, _P]
+    rc = lib.emul_sample(mesh_kind, nc, ln, z0, nzl, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(pts), len(pts), _p(out))
+    assert rc == 0, rc
     return out

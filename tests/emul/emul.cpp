@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../pfhubbenchmarks_b200/csrc/pfh_vertex.cuh"
+#include "../../pfhubbenchmarks_b200/csrc/pfh_sample.cuh"
 
 void pfh_set_error(const std::string&) {}
 
@@ -156,6 +157,29 @@ int run(const Setup& S, const ProblemParams& pp, double dt, int mode, const doub
   return 0;
 }
 }  // namespace
+
+// point evaluation (csrc/pfh_sample.cuh) on the CPU: out[i] = value, +inf outside; 3-D slabs: NaN where not owned
+extern "C" int emul_sample(int mesh_kind, const int* ncell, const double* length, int z0, int nzl, const double* u,
+                           const double* glo, const double* ghi, const double* pts, long long npts, double* out) {
+  try {
+    Setup S;
+    setup(S, mesh_kind, ncell, length, z0, nzl);
+    for (long long i = 0; i < npts; ++i) {
+      double v = 0.0;
+      if (mesh_kind == 3) {
+        bool inside, owned;
+        smp::eval3(S.m3, FieldRef{u, glo, ghi}, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], inside, owned, v);
+        out[i] = !inside ? INFINITY : (owned ? v : NAN);
+      } else {
+        out[i] = smp::eval2(S.m2, u, pts[2 * i], pts[2 * i + 1], v) ? v : INFINITY;
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "emul: %s\n", e.what());
+    return -1;
+  }
+}
 
 extern "C" int emul_run(int mesh_kind, int problem, const int* ncell, const double* length, const double* params, int nparams,
                         double dt, int mode, int z0, int nzl, const double* U, const double* X, const double* U0,

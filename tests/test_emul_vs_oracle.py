@@ -107,3 +107,52 @@ def test_low_flop_cube_residual_routine():
     got = emul.run(3, 1, list(ncell), list(length), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, 6, U=U, nf=2)
     ref = D.V.load(D.prob.g(D.V.at_quad(U)))[1]
     assert rel_max(got, ref) < 1e-13
+
+
+def _probe_points(rng, lengths, n):
+    """Random interior points plus the awkward ones: vertices, cell centres, points on faces/diagonals, the far corner."""
+    L = np.asarray(lengths, dtype=float)
+    pts = [rng.random((n, len(L))) * L, np.zeros((1, len(L))), L[None, :], 0.5 * L[None, :]]
+    return np.concatenate(pts)
+
+
+def test_point_evaluation_matches_cell_search():
+    """csrc/pfh_sample.cuh (cell index + ordering of local coordinates) against the oracle's brute-force search over
+    all simplices of the same mesh: f(x) of the reference's peval/sample (pfbase.py:50-94)."""
+    from oracle import fem
+    rng = np.random.default_rng(5)
+    for ncell, length in [((7, 5), (14.0, 10.0)), ((4, 6), (3.0, 9.0))]:
+        m = omesh.crossed2d(*ncell, *length)
+        u = rng.standard_normal(m.nv)
+        pts = _probe_points(rng, length, 300)
+        hx, hy = length[0] / ncell[0], length[1] / ncell[1]
+        pts = np.concatenate([pts, [[2 * hx, 3 * hy], [2.5 * hx, 1.5 * hy], [2.25 * hx, 1.25 * hy], [2.75 * hx, 1.25 * hy], [hx, 0.3 * hy]]])
+        got = emul.sample(2, ncell, length, u, pts)
+        want = fem.eval_points(m, u, pts)
+        assert np.all(np.isfinite(want)) and np.max(np.abs(got - want)) < 1e-12
+        # a linear function is reproduced exactly; outside points give +inf
+        lin = 0.3 + 1.7 * m.coords[:, 0] - 0.6 * m.coords[:, 1]
+        assert np.max(np.abs(emul.sample(2, ncell, length, lin, pts) - (0.3 + 1.7 * pts[:, 0] - 0.6 * pts[:, 1]))) < 1e-12
+        out = emul.sample(2, ncell, length, u, [[-0.1, 1.0], [1.0, length[1] + 0.1]])
+        assert np.all(np.isinf(out)) and np.all(np.isinf(fem.eval_points(m, u, [[-0.1, 1.0], [1.0, length[1] + 0.1]])))
+    for ncell, length in [((5, 4, 3), (10.0, 8.0, 6.0)), ((3, 4, 5), (4.0, 8.0, 7.0))]:
+        m = omesh.kuhn3d(*ncell, *length)
+        u = rng.standard_normal(m.nv)
+        pts = _probe_points(rng, length, 300)
+        h = np.asarray(length) / np.asarray(ncell)
+        pts = np.concatenate([pts, [h * [1, 2, 1], h * [1.5, 1.5, 1.5], h * [1.25, 1.25, 1.7], h * [2.0, 1.3, 1.3]]])
+        got = emul.sample(3, ncell, length, u, pts)
+        want = fem.eval_points(m, u, pts)
+        assert np.all(np.isfinite(want)) and np.max(np.abs(got - want)) < 1e-12
+        # slabs: every point is owned by exactly one slab (the one holding its cube's lower plane) with the same value
+        nzv, nxy = ncell[2] + 1, (ncell[0] + 1) * (ncell[1] + 1)
+        U = u.reshape(nzv, nxy)
+        owners = np.zeros(len(pts), dtype=int)
+        for z0, z1 in [(0, 2), (2, 3), (3, nzv)]:
+            glo = U[z0 - 1] if z0 > 0 else None
+            ghi = U[z1] if z1 < nzv else None
+            part = emul.sample(3, ncell, length, U[z0:z1].ravel(), pts, z0=z0, nzl=z1 - z0, glo=glo, ghi=ghi)
+            mine = ~np.isnan(part)
+            owners += mine
+            assert not mine.any() or np.max(np.abs(part[mine] - want[mine])) < 1e-12     # the top plane alone owns no cube
+        assert np.all(owners == 1)

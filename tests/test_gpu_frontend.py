@@ -141,3 +141,35 @@ def test_user_expression_interpolates_like_the_kernel():
     w0.interpolate(InitialConditionsBench1(0.5, 0.05, degree=2))
     assert float((w.tensor - w0.tensor).abs().max()) < 1e-14
     problem.ctx.close()
+
+
+def test_peval_and_sample():
+    """pfbase.peval / sample (pfbase.py:50-94) through pfh_eval_points_dev: vertex values are reproduced, a lattice
+    sample equals the oracle's cell search, outside points are +inf (peval) or raise (f(x))."""
+    from oracle import fem, mesh as omesh
+    from pfhubbenchmarks_b200.pfbase import InitialConditionsBench1, peval, sample
+    df, mesh, w, w0, dt, f_chem, kappa, F, dw = _bench1(n=24, length=48.0)
+    problem = df.NonlinearVariationalProblem(F, w, [], df.derivative(F, w, dw))
+    w.interpolate(InitialConditionsBench1(0.5, 0.05, degree=2))
+    c = w.sub(0)
+    u = w.to_numpy()[0]
+    m = omesh.crossed2d(24, 24, 48.0, 48.0)
+    assert np.max(np.abs(c.at(m.coords) - u)) < 1e-14                       # all vertices (corners and centres)
+    xs, ys, us = sample(c, 31, 17, 48.0, 48.0)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    want = fem.eval_points(m, u, np.stack([X.ravel(), Y.ravel()], 1)).reshape(31, 17)
+    assert us.shape == (31, 17) and np.max(np.abs(us - want)) < 1e-13
+    assert abs(c(np.array([10.3, 7.9])) - fem.eval_points(m, u, [[10.3, 7.9]])[0]) < 1e-14
+    assert np.isinf(peval(c, np.array([50.0, 1.0]))[0])
+    with pytest.raises(RuntimeError):
+        c(np.array([-1.0, 1.0]))
+    problem.ctx.close()
+    # 3-D: the Kuhn tets
+    from pfhubbenchmarks_b200 import engine
+    ctx = engine.Context("b13d", (9, 7, 6), (18.0, 14.0, 12.0))
+    w3 = ctx.initial_condition()
+    m3 = omesh.kuhn3d(9, 7, 6, 18.0, 14.0, 12.0)
+    pts = np.random.default_rng(3).random((400, 3)) * [18.0, 14.0, 12.0]
+    got = ctx.eval_points(w3, 0, pts)
+    assert np.max(np.abs(got - fem.eval_points(m3, w3.cpu().numpy()[:m3.nv], pts))) < 1e-13
+    ctx.close()
