@@ -1,5 +1,5 @@
 // pfh_eval_points_dev: P1 point evaluation of one field at a list of points (dolfin/pfbase.py:50-94, peval / sample).
-#include <limits>
+#include <math_constants.h>
 
 #include "pfh_internal.h"
 #include "pfh_sample.cuh"
