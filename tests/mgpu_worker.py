@@ -40,6 +40,16 @@ def main():
     # gather slabs on rank 0
     parts = [None] * world
     dist.all_gather_object(parts, (ctx.z_range, w.cpu().numpy()))
+    # point evaluation and an assembled bilinear functional across slabs (every rank gets the global answer)
+    pts = np.random.default_rng(11).random((257, 3)) * np.asarray(length)
+    vals = ctx.eval_points(w, 0, pts)
+    quad = ctx.bilinear(w, 0, 1, 0.5, 2.0)
+    # one more step at the drivers' default tolerances: the compressed (fp32-stored) Krylov basis with its allreduced norms
+    w0 = w.clone()
+    ctx.dt = 0.4
+    rep_c = ctx.newton_solve(w, w0)
+    assert rep_c["converged"], rep_c
+    e_c = ctx.energy(w)
     ctx.close()
     ok = True
     if rank == 0:
@@ -64,6 +74,17 @@ def main():
         print("mgpu world=%d grid=%d  rel L2 (c, mu) = %.2e %.2e  dE %.1e dM %.1e  its %s vs %s" % (
             world, grid, err[0], err[1], de, dm, hist, ref_hist), flush=True)
         ok = err[0] < 1e-10 and err[1] < 1e-8 and de < 1e-11 and dm < 1e-13
+        dv = float(np.max(np.abs(vals - one.eval_points(v, 0, pts))))
+        q1 = one.bilinear(v, 0, 1, 0.5, 2.0)
+        v0 = v.clone()
+        one.dt = 0.4
+        rep_1 = one.newton_solve(v, v0)
+        e_1 = one.energy(v)
+        print("mgpu eval_points max diff %.1e  bilinear rel diff %.1e  default-tolerance step: its %s vs %s, dE %.1e" % (
+            dv, abs(quad / q1 - 1), (rep_c["niters"], rep_c["krylov_its"]), (rep_1["niters"], rep_1["krylov_its"]),
+            abs(e_c[0] / e_1[0] - 1)), flush=True)
+        ok = ok and dv < 1e-9 and abs(quad / q1 - 1) < 1e-9 and rep_1["converged"] and abs(e_c[0] / e_1[0] - 1) < 1e-8 \
+            and abs(rep_c["krylov_its"] - rep_1["krylov_its"]) <= 2
         one.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
