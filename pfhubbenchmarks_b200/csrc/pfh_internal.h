@@ -178,6 +178,8 @@ struct pfh_ctx {
   // fused two-sweep (temporally blocked) Chebyshev kernels (pfh_cheb2_tma.cu): correct, but shared-memory-bandwidth
   // bound and 1.45x slower per solve than the per-sweep TMA kernel at 512^3 (profiles/README.md), so opt-in only
   bool use_fused = false;
+  std::vector<double> h_mT3, h_kT3;  // host copies of the 3-D type tables (inverse diagonals for k_cheb_first2)
+  bool use_first2 = true;  // 3-D: first two Chebyshev iterates in one pass over r (k_cheb_first2)
   int basis_precision = 0;  // Krylov basis storage: 0 = fp32 when krylov_rtol >= 1e-6 else fp64, 1 = fp64, 2 = fp32
   bool use_tma = true;  // 3-D fast path: TMA-staged kernels (pfh_stencil3_tma.cu); false = gather kernels only
 };
@@ -214,6 +216,8 @@ void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y);
 void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out);
 // z = b * Dinv r,  D = diag(am M + ak K)
 void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z);
+// first two Chebyshev iterates from r alone (3-D TMA path): z1 = b0 D^-1 r, z2 = z1 + a1 z1 + b1 D^-1 (r - A z1); false = not available
+bool k_cheb_first2(pfh_ctx* c, double am, double ak, double b0, double a1, double b1, FieldRef r, double* z1, double* z2);
 // zprev <- z + a (z - zprev) + b Dinv (r - (am M + ak K) z)
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z,
                   double* zprev, bool zprev_is_zero);  // zprev_is_zero: zprev is write-only (z_{k-1} = 0)
@@ -235,6 +239,7 @@ bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const 
 bool k3_cheb2_launch(pfh_ctx* c, bool first, double am, double ak, double b0, double aX, double bX, double aY, double bY,
                      const double* zk, const double* zkm1, const double* r, double* outX, double* outY);
 bool k3_res_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* u, const double* u0, double* R);
+bool k3_cheb_first2_tma_launch(pfh_ctx* c, double am, double ak, double b0, double a1, double b1, FieldRef r, double* z1, double* z2);
 bool k3_ch_crow_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, FieldRef xc, double* out);
 // out = [J(ulin) (xc, 0)]_mu for Cahn-Hilliard (scalar in, scalar out); false if no fast path applies
 bool k_ch_crow(pfh_ctx* c, const double* ulin, FieldRef xc, double* out);

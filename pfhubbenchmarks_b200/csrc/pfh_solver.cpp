@@ -144,12 +144,63 @@ void cheb_solve(pfh_ctx* c, double am, double ak, double lmin, double lmax, int 
   double* cur = ((nsweeps - 1) % 2 == 0) ? target : tmp;
   double* prev = (cur == target) ? tmp : target;
   const bool ov = c->cfg.nranks > 1 && c->overlap && c->comm_stream && c->dim == 3 && c->m3.nzl >= 4;
+  // 3-D fast path: the first two iterates come out of one pass over r (k_cheb_first2), the loop then starts at k = 2
+  const bool first2 = nsweeps >= 2 && c->use_first2 && c->dim == 3 && pfh_tma_ok(c) && c->scalar_variant == 0;
   if (!ov) {
-    k_cheb_first(c, am, ak, cf[0].b, r, cur);
-    for (int k = 1; k < nsweeps; ++k) {
+    int k0 = 1;
+    if (first2 && k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, scalar_ref(c, r), cur, prev)) {
+      std::swap(cur, prev);
+      k0 = 2;
+    } else {
+      k_cheb_first(c, am, ak, cf[0].b, r, cur);
+    }
+    for (int k = k0; k < nsweeps; ++k) {
       k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev, k == 1);
       std::swap(cur, prev);
     }
+  } else if (first2) {
+    // as below, but the first launch pair reads r's ghost planes: they travel under the interior launch
+    if (c->gS_prefetched != r) {
+      PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+      PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+      comm_halo(c, r, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
+      PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+    }
+    c->gS_prefetched = nullptr;
+    const FieldRef rref{r, c->gS_lo, c->gS_hi};
+    c->zpart = 2;
+    PFH_CHECK(k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, rref, cur, prev), "internal: fused first sweeps unavailable");
+    PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+    c->zpart = 1;
+    k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, rref, cur, prev);
+    PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+    std::swap(cur, prev);
+    if (nsweeps == 2 && consumer_needs_ghosts) {
+      PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+      comm_halo(c, cur, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
+      PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+      c->gS_prefetched = cur;
+    }
+    for (int k = 2; k < nsweeps; ++k) {
+      PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+      comm_halo(c, cur, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
+      PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+      PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+      const FieldRef ref{cur, c->gS_lo, c->gS_hi};
+      c->zpart = 1;
+      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, false);
+      PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+      if (k == nsweeps - 1 && consumer_needs_ghosts) {
+        PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+        comm_halo(c, prev, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
+        PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+        c->gS_prefetched = prev;
+      }
+      c->zpart = 2;
+      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, false);
+      std::swap(cur, prev);
+    }
+    c->zpart = 0;
   } else {
     // Halo/compute overlap: every producer writes its two slab-boundary planes first and signals ev_bnd; the ghost
     // exchange of those planes runs on comm_stream while the interior planes are computed on the ctx stream; the

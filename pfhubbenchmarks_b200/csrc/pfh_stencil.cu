@@ -475,6 +475,12 @@ void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, d
   PFH_CUDA(cudaGetLastError());
 }
 
+bool k_cheb_first2(pfh_ctx* c, double am, double ak, double b0, double a1, double b1, FieldRef r, double* z1, double* z2) {
+  if (c->dim != 3 || !pfh_tma_ok(c) || c->scalar_variant != 0) return false;
+  ProfScope ps(c, T_CHEB_FIRST, 24.0 * c->n_owned * zfrac(c));
+  return k3_cheb_first2_tma_launch(c, am, ak, b0, a1, b1, r, z1, z2);
+}
+
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev,
                   bool zprev_is_zero) {
   ProfScope ps(c, T_CHEB_SWEEP, (zprev_is_zero ? 24.0 : 32.0) * c->n_owned * zfrac(c));

@@ -10,6 +10,8 @@
 //  k3_scalar_tma : A = am M + ak K on a scalar field (15-point P1 stencil):
 //                  MODE 0  out = s*add + A in                      (lin_apply)
 //                  MODE 2  zprev <- z + a (z - zprev) + b D^-1 (r - A z)   (Jacobi-Chebyshev sweep)
+//                  MODE 3  z1 = b0 D^-1 r ; z2 = z1 + a z1 + b D^-1 (r - A z1)   (first two Chebyshev iterates from r alone:
+//                          the stencil operand is r, scaled on the fly by b0 / diag of each neighbour's row) 24 B/vertex
 //                  algorithmic traffic 32 B/vertex (MODE 2), 16-24 B/vertex (MODE 0).
 //  k3_jac_tma    : y = J(u) x for the mixed system.  The nonlinear block int phi_i g'(u_h) x_h is
 //                  evaluated ONCE per tetrahedron (cube-centric, 5-point Zienkiewicz-Taylor rule,
@@ -32,13 +34,17 @@ using namespace tma;
 struct Coef15 {
   double c[PFH_NOFF3];
 };
+struct InvDiag27 {
+  double v[27];  // 1 / diagonal of (am M + ak K) by boundary type
+};
 
 template <int MODE, int TX, int TY, int RY, int NS>
 __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
     k3_scalar_tma(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_lo,
                   const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_r,
                   const __grid_constant__ CUtensorMap tm_o, Mesh3 m, int has_lo, int has_hi, int has_r, int has_o, int zchunk,
-                  int zpart, double am, double ak, Coef15 cI, double a, double b, double bdI, double* __restrict__ out) {
+                  int zpart, double am, double ak, Coef15 cI, double a, double b, double bdI, double* __restrict__ out,
+                  double b0, double* __restrict__ out1, const __grid_constant__ InvDiag27 invd) {
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2: the TMA box start (x0-2) must be 16-byte aligned
   constexpr int ZT_BYTES = W * H * 8, PT_BYTES = TX * TY * 8;
   constexpr int ZT_STRIDE = round_up(ZT_BYTES, 128);
@@ -153,6 +159,27 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
       v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
       const int type = tzt * 9 + txy[rr];
       double Av, bd;
+      double rc = 0.0, s1 = 0.0;  // MODE 3: r at this vertex; uniform operand scale b0 / diag when every neighbour is an interior row
+      if (MODE == 3) {
+        rc = v[0];
+        const int iy = y0 + ly;
+        const bool deep = ix >= 2 && ix <= m.nxv - 3 && iy >= 2 && iy <= m.nyv - 3 && gz >= 2 && gz <= m.nzv - 3;
+        if (deep) {
+          s1 = b0 * invd.v[13];
+        } else {
+          // next to the boundary the neighbours' rows differ: scale operand by operand (out-of-domain operands are the
+          // zeros TMA filled in, whatever scale they get)
+          constexpr int DX[PFH_NOFF3] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1};
+          constexpr int DY[PFH_NOFF3] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1};
+          constexpr int DZ[PFH_NOFF3] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1};
+#pragma unroll
+          for (int o = 0; o < PFH_NOFF3; ++o) {
+            const int tn = vtx::type3(m, ix + DX[o], iy + DY[o], gz + DZ[o]);
+            v[o] *= b0 * invd.v[tn];
+          }
+          s1 = 1.0;
+        }
+      }
       if (type == 13) {
         // four independent partial sums: the 15 fused multiply-adds are not one dependent chain
         double s0 = cI.c[0] * v[0], s1 = cI.c[1] * v[1], s2 = cI.c[2] * v[2], s3 = cI.c[3] * v[3];
@@ -167,10 +194,15 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
         double Ms, Ks;
         vtx::mk_sums3(row, v, Ms, Ks);
         Av = am * Ms + ak * Ks;
-        bd = MODE == 2 ? b / (am * row.m[0] + ak * row.k[0]) : 0.0;
+        bd = MODE >= 2 ? b / (am * row.m[0] + ak * row.k[0]) : 0.0;
       }
       if (MODE == 0) out[idx[rr]] = a * rv + Av;
-      else out[idx[rr]] = v[0] + a * (v[0] - ov) + bd * (rv - Av);
+      else if (MODE == 2) out[idx[rr]] = v[0] + a * (v[0] - ov) + bd * (rv - Av);
+      else {
+        const double z1 = s1 * v[0];
+        out1[idx[rr]] = z1;
+        out[idx[rr]] = z1 + a * z1 + bd * (rc - s1 * Av);
+      }
     }
 #pragma unroll
     for (int rr = 0; rr < RY; ++rr) idx[rr] += m.nxy;
@@ -404,6 +436,9 @@ struct ScalarArgs {
   const double* r;
   double* out;
   int mode;
+  double b0 = 0.0;       // MODE 3
+  double* out1 = nullptr;
+  InvDiag27 invd = {};
 };
 
 template <int TX, int TY, int RY, int NS, int ZCH>
@@ -424,14 +459,18 @@ bool scalar_launch(pfh_ctx* c, ScalarArgs& A) {
   if (!attr_set) {
     PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<0, TX, TY, RY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<2, TX, TY, RY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFH_CUDA(cudaFuncSetAttribute(k3_scalar_tma<3, TX, TY, RY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   if (A.mode == 0)
     k3_scalar_tma<0, TX, TY, RY, NS><<<grid, block, smem, c->stream>>>(A.tm, A.tl, A.th, A.tr, A.to, m, A.lo, A.hi, A.has_r, 0, ZCH, zp, A.am,
-                                                                      A.ak, A.cI, A.a, A.b, 0.0, A.out);
-  else
+                                                                      A.ak, A.cI, A.a, A.b, 0.0, A.out, 0.0, nullptr, A.invd);
+  else if (A.mode == 2)
     k3_scalar_tma<2, TX, TY, RY, NS><<<grid, block, smem, c->stream>>>(A.tm, A.tl, A.th, A.tr, A.to, m, A.lo, A.hi, A.has_r, A.has_o, ZCH, zp,
-                                                                      A.am, A.ak, A.cI, A.a, A.b, A.bdI, A.out);
+                                                                      A.am, A.ak, A.cI, A.a, A.b, A.bdI, A.out, 0.0, nullptr, A.invd);
+  else
+    k3_scalar_tma<3, TX, TY, RY, NS><<<grid, block, smem, c->stream>>>(A.tm, A.tl, A.th, A.tr, A.to, m, A.lo, A.hi, 0, 0, ZCH, zp, A.am, A.ak,
+                                                                      A.cI, A.a, A.b, A.bdI, A.out, A.b0, A.out1, A.invd);
   PFH_CUDA(cudaGetLastError());
   return true;
 }
@@ -461,6 +500,26 @@ bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, 
     case 7: return scalar_launch<64, 7, 1, 4, 32>(c, A);
     default: return scalar_launch<S_TX, S_TY, S_RY, S_NS, S_ZCH>(c, A);
   }
+}
+
+// z1 = b0 D^-1 r and z2 = z1 + a1 z1 + b1 D^-1 (r - A z1) in one pass over r (MODE 3): replaces the pointwise first
+// Chebyshev step and the first sweep (40 B/vertex together) by 24 B/vertex
+bool k3_cheb_first2_tma_launch(pfh_ctx* c, double am, double ak, double b0, double a1, double b1, FieldRef r, double* z1, double* z2) {
+  if (!pfh_tma_ok(c) || !aligned16(r.p) || !aligned16(z1) || !aligned16(z2)) return false;
+  const Mesh3& m = c->m3;
+  const bool lo = r.glo != nullptr && c->cfg.rank > 0, hi = r.ghi != nullptr && c->cfg.rank < c->cfg.nranks - 1;
+  if ((lo && !aligned16(r.glo)) || (hi && !aligned16(r.ghi))) return false;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  Coef15 cI;
+  for (int o = 0; o < PFH_NOFF3; ++o) cI.c[o] = am * m.mI[o] + (o < PFH_NKOFF3 ? ak * m.kI[o] : 0.0);
+  ScalarArgs A{tm, tm, tm, tm, tm, m, lo, hi, false, false, c->zpart, am, ak, cI, a1, b1, b1 / cI.c[0], r, nullptr, z2, 3, b0, z1};
+  if (c->h_mT3.empty()) {  // host copy of the type tables, for the inverse diagonals
+    Mesh3 mm = m;
+    pfh_build_tables3(mm, c->h_mT3, c->h_kT3);
+  }
+  for (int t = 0; t < 27; ++t) A.invd.v[t] = 1.0 / (am * c->h_mT3[t * PFH_NOFF3] + ak * c->h_kT3[t * PFH_NKOFF3]);
+  return scalar_launch<S_TX, S_TY, S_RY, S_NS, S_ZCH>(c, A);
 }
 
 // y = J(ulin) x for Cahn-Hilliard on the Kuhn mesh; ghosts: gX_* for x, gU_* for ulin
