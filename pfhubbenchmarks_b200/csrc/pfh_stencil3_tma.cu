@@ -172,11 +172,16 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
           constexpr int DX[PFH_NOFF3] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1};
           constexpr int DY[PFH_NOFF3] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1};
           constexpr int DZ[PFH_NOFF3] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1};
+          auto cls = [](int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); };
+          int tX[3], tY[3], tZ[3];
 #pragma unroll
-          for (int o = 0; o < PFH_NOFF3; ++o) {
-            const int tn = vtx::type3(m, ix + DX[o], iy + DY[o], gz + DZ[o]);
-            v[o] *= b0 * invd.v[tn];
+          for (int d = 0; d < 3; ++d) {
+            tX[d] = cls(ix + d - 1, m.nxv);
+            tY[d] = 3 * cls(iy + d - 1, m.nyv);
+            tZ[d] = 9 * cls(gz + d - 1, m.nzv);
           }
+#pragma unroll
+          for (int o = 0; o < PFH_NOFF3; ++o) v[o] *= b0 * invd.v[tZ[DZ[o] + 1] + tY[DY[o] + 1] + tX[DX[o] + 1]];
           s1 = 1.0;
         }
       }
