@@ -231,10 +231,10 @@ class Function:
             return
         self._tensor.copy_(other._tensor)
 
-    def split(self):                                   # c, _ = w.split()  (bench1.py:188)
-        return self._problem.ctx.fields(self.tensor)
+    def split(self):                                   # c, _ = w.split()  (bench1.py:188): components to write / evaluate
+        return [SubFunction(self, i) for i in range(self.W.nfields)]
 
-    def sub(self, i):                                  # w.sub(0): a scalar component that can be evaluated, f(x)
+    def sub(self, i):                                  # w.sub(0)
         return SubFunction(self, i)
 
     def vector(self):
@@ -264,8 +264,14 @@ class SubFunction:
         return ()
 
     @property
-    def tensor(self):
-        return self.owner.split()[self.index]
+    def tensor(self):                                  # view of the component inside the owner's device vector
+        return self.owner._problem.ctx.fields(self.owner.tensor)[self.index]
+
+    def cpu(self):
+        return self.tensor.cpu()
+
+    def function_space(self):
+        return self.owner.W.split()[self.index]
 
 
 def split(w):

@@ -112,7 +112,7 @@ def time_loop(problem, solver, w_ic, dt0, dt_min, end_time, csv_path, header, ma
             F_total, C_total = functionals[0](), functionals[1]()
         benchmark_output.append([float(t), F_total, C_total])
         for k, fh in files.items():
-            fh << (w.split()[k].cpu().numpy(), float(t))
+            fh << (w.split()[k], float(t))
         if rank0 and not quiet:
             print("Converged in %d Newton iterations; C_total: %r TFE: %r" % (niters, C_total, F_total))
         if abort_on_negative_energy and F_total < 0.0:        # bench3.py:254-258

@@ -116,6 +116,14 @@ class File:
             f.write("  </Collection>\n</VTKFile>\n")
 
     def __lshift__(self, pair):
+        """`file << (c, t)` with c a component of a Function (`c, _ = w.split()`, bench2.py:269-274), a device tensor or
+        a numpy array; the mesh is taken from the Function when the File was opened without one, as in the reference."""
         values, t = pair
+        if hasattr(values, "owner"):                      # dolfin.SubFunction
+            if self.mesh is None:
+                self.mesh = values.owner.W.mesh
+            values = values.tensor
+        if hasattr(values, "detach"):                     # torch tensor
+            values = values.detach().cpu().numpy()
         self.write(values, float(t))
         return self

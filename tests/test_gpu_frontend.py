@@ -161,6 +161,15 @@ def test_peval_and_sample():
     assert us.shape == (31, 17) and np.max(np.abs(us - want)) < 1e-13
     assert abs(c(np.array([10.3, 7.9])) - fem.eval_points(m, u, [[10.3, 7.9]])[0]) < 1e-14
     assert np.isinf(peval(c, np.array([50.0, 1.0]))[0])
+    # `c, _ = w.split(); cfile << (c, t)` with a File opened without a mesh, as the reference does (bench2.py:180,269)
+    import tempfile
+    from oracle import golden_io
+    with tempfile.TemporaryDirectory() as tmp:
+        cfile = df.File(tmp + "/conc.pvd", "compressed")
+        c_split, _ = w.split()
+        cfile << (c_split, 0.5)
+        (t0, fn), = golden_io.read_pvd(tmp + "/conc.pvd")
+        assert t0 == 0.5 and np.array_equal(golden_io.read_vtu_scalar(tmp + "/" + fn), u)
     with pytest.raises(RuntimeError):
         c(np.array([-1.0, 1.0]))
     problem.ctx.close()
