@@ -154,6 +154,12 @@ int pfh_energy_host(pfh_ctx* ctx, const double* w_host, double out[4]);
 /* Instrumentation: kernels launched by this ctx since creation / last reset; and device
  * time (ms, CUDA events on the ctx stream) accumulated per kernel family when profiling is on. */
 long long pfh_launch_count(const pfh_ctx* ctx);
+/* Options (key, value): "profiling" 0/1 per-family event timers; "reset_launch_count"; "overlap" 0/1 halo/compute
+ * overlap on slab-decomposed meshes (default 1); "use_tma" 0/1 TMA-staged 3-D kernels (default 1; 0 = gather kernels);
+ * "use_first2" 0/1 first two Chebyshev iterates in one pass (default 1); "use_fused" 0/1 temporally blocked sweeps
+ * (default 0, slower); "scalar_variant" tile-shape variants of the 3-D scalar kernel (tuning); "basis_precision" storage
+ * of the GMRES basis: 0 = fp32 when krylov_rtol >= 1e-6 else fp64 (default), 1 = fp64, 2 = fp32 (arithmetic is fp64
+ * in all cases).  Unknown keys are an error. */
 int pfh_set_option(pfh_ctx* ctx, const char* key, double value);
 #define PFH_N_TIMERS 16
 int pfh_timers(pfh_ctx* ctx, double ms[PFH_N_TIMERS], long long launches[PFH_N_TIMERS],
