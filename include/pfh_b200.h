@@ -40,7 +40,10 @@ enum {
   PFH_PROBLEM_CH = 1,     /* bench1.py / b13d.py : fields (c, mu);  params = {c_alpha, c_beta, rho_s, kappa, M} */
   PFH_PROBLEM_BENCH2 = 2, /* bench2.py : (c, mu, eta1..4); params = {c_alpha, c_beta, rho^2, kappa_c, kappa_eta, M, w, alpha, L} */
   PFH_PROBLEM_BENCH3 = 3, /* bench3.py : (U, phi); params = {W0, tau0, D, lambda, Lx*Ly} */
-  PFH_PROBLEM_BENCH6 = 6  /* bench6.py : (c, mu, phi); params = {c_alpha, c_beta, rho, kappa, M, k, epsilon} */
+  PFH_PROBLEM_BENCH6 = 6, /* bench6.py : (c, mu, phi); params = {c_alpha, c_beta, rho, kappa, M, k, epsilon} */
+  /* A model generated from the driver's own weak form (pfhubbenchmarks_b200/codegen.py: sympy -> functor) and compiled
+   * into its own copy of this library; only that copy accepts it.  No params: the coefficients are in the code. */
+  PFH_PROBLEM_USER = 100
 };
 
 #define PFH_MAX_PARAMS 16

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpfh_b200.so")
 
 MESH_CROSSED2D, MESH_KUHN3D = 2, 3
-PROBLEM_CH, PROBLEM_BENCH2, PROBLEM_BENCH3, PROBLEM_BENCH6 = 1, 2, 3, 6
+PROBLEM_CH, PROBLEM_BENCH2, PROBLEM_BENCH3, PROBLEM_BENCH6, PROBLEM_USER = 1, 2, 3, 6, 100
 MAX_PARAMS, NCCL_ID_BYTES, N_TIMERS = 16, 128, 16
 
 
@@ -101,9 +101,28 @@ def load():
     return lib
 
 
-def check(rc):
+_user_libs = {}
+
+
+def load_user(path):
+    """Load the copy of the library built for one generated model (build.build_user); same ABI, same checks."""
+    if path in _user_libs:
+        return _user_libs[path]
+    if not os.path.exists(path):
+        raise PfhError("generated library %s is missing; there is no CPU fallback" % path)
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.pfh_abi_version() != 1:
+        raise PfhError("ABI version mismatch")
+    _user_libs[path] = lib
+    return lib
+
+
+def check(rc, lib=None):
     if rc != 0:
-        raise PfhError(load().pfh_last_error().decode())
+        raise PfhError((lib or load()).pfh_last_error().decode())
 
 
 def default_opts(**kw):

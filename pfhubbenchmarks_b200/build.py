@@ -32,9 +32,30 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    return _compile_all(os.path.join(HERE, "build"), LIB, [], verbose)
+
+
+def build_user(source, tag, force=False):
+    """Compile a copy of the library for one generated model (codegen.UserModel): _jit/pfh_user_<tag>.cuh is written and
+    compiled in through -DPFH_USER_PROBLEM_HEADER; the result is _jit/libpfh_b200_<tag>.so (cached by content hash and by
+    the mtimes of the library sources).  -Bsymbolic keeps its internal calls inside this copy when the stock library is
+    loaded in the same process."""
+    jit = os.path.join(HERE, "_jit")
+    os.makedirs(jit, exist_ok=True)
+    hdr = os.path.join(jit, "pfh_user_%s.cuh" % tag)
+    lib = os.path.join(jit, "libpfh_b200_%s.so" % tag)
+    if not os.path.exists(hdr) or open(hdr).read() != source:
+        with open(hdr, "w") as f:
+            f.write(source)
+    if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in _deps() + [hdr]):
+        return lib
+    return _compile_all(os.path.join(jit, "build_" + tag), lib,
+                        ['-DPFH_USER_PROBLEM_HEADER="%s"' % hdr, "-DPFH_ONLY_USER"], False, ["-Xlinker", "-Bsymbolic"])
+
+
+def _compile_all(objdir, lib, defines, verbose, link_flags=()):
     os.makedirs(objdir, exist_ok=True)
-    flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH
+    flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH + list(defines)
     if verbose:
         flags += ["-Xptxas", "-v"]
 
@@ -50,11 +71,11 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"]
+    cmd = [_nvcc()] + ARCH + ["-shared", "-o", lib] + objs + ["-ldl"] + list(link_flags)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -5,6 +5,9 @@
 #include <mutex>
 
 #include "pfh_internal.h"
+#ifdef PFH_USER_PROBLEM_HEADER
+#include "pfh_problems.cuh"  // ProbUser: the generated model this copy of the library is built for
+#endif
 
 static thread_local std::string g_err;
 void pfh_set_error(const std::string& m) { g_err = m; }
@@ -112,12 +115,16 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
       case PFH_PROBLEM_BENCH2: c->nf = 6; need = 9; break;
       case PFH_PROBLEM_BENCH3: c->nf = 2; need = 5; break;
       case PFH_PROBLEM_BENCH6: c->nf = 3; need = 7; break;
-      default: throw PfhError("unknown problem id");
+#ifdef PFH_USER_PROBLEM_HEADER
+      case PFH_PROBLEM_USER: c->nf = ProbUser::NF; need = 0; break;
+#endif
+      default: throw PfhError("unknown problem id (a generated model needs the library built for it)");
     }
     PFH_CHECK(cfg->n_params >= need && cfg->n_params <= PFH_MAX_PARAMS, "wrong number of problem parameters");
     c->prob.nf = c->nf;
     for (int i = 0; i < cfg->n_params; ++i) c->prob.p[i] = cfg->params[i];
-    PFH_CHECK(c->dim == 2 || cfg->problem == PFH_PROBLEM_CH, "3-D meshes support PFH_PROBLEM_CH only (b13d)");
+    PFH_CHECK(c->dim == 2 || cfg->problem == PFH_PROBLEM_CH || cfg->problem == PFH_PROBLEM_USER,
+              "3-D meshes support PFH_PROBLEM_CH (b13d) and generated models only");
     PFH_CHECK(cfg->nranks >= 1 && cfg->rank >= 0 && cfg->rank < cfg->nranks, "bad rank/nranks");
     PFH_CHECK(c->dim == 3 || cfg->nranks == 1, "2-D problems do not shard (replicas only)");
 
@@ -166,7 +173,7 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     c->W1 = pfh_alloc(c, vs); c->W2 = pfh_alloc(c, vs);
     c->V = pfh_alloc(c, (size_t)vs * (c->cfg.krylov_basis + 1));
     for (int i = 0; i < 5; ++i) c->S[i] = pfh_alloc(c, c->n_owned + 32);
-    if (c->dim == 2 && (cfg->problem == PFH_PROBLEM_BENCH2 || cfg->problem == PFH_PROBLEM_BENCH3))
+    if (c->dim == 2 && (cfg->problem == PFH_PROBLEM_BENCH2 || cfg->problem == PFH_PROBLEM_BENCH3 || cfg->problem == PFH_PROBLEM_USER))
       for (int i = 0; i < 4; ++i) c->SIG[i] = pfh_alloc(c, c->n_owned + 32);
     if (c->nplane) {
       const size_t g = (size_t)c->nf * c->nplane;

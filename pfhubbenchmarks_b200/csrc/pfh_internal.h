@@ -77,6 +77,17 @@ struct Mesh2 {
 void pfh_build_tables3(Mesh3& m, std::vector<double>& mT, std::vector<double>& kT);
 void pfh_build_tables2(Mesh2& m, std::vector<double>& mT, std::vector<double>& kT);
 
+// Block structure the Schur/Chebyshev preconditioner works on (pfh_solver.cpp): fields (0, 1) as a Cahn-Hilliard
+// (c, mu) pair, up to four further fields with an SPD parabolic diagonal block am M + ak K, or plain Jacobi.
+struct PfhPcLayout {
+  bool has_ch = false;
+  double Mob = 0, kappa = 0;
+  int n_spd = 0;
+  int spd_field[4] = {0, 0, 0, 0};
+  double spd_am[4] = {0, 0, 0, 0}, spd_ak[4] = {0, 0, 0, 0}, spd_sign[4] = {1, 1, 1, 1};
+  bool jacobi_only = false;  // some field fits neither block: fall back to the point-Jacobi preconditioner
+};
+
 // Scalar field operand of a stencil kernel: owned planes + (3-D slabs) one ghost plane per side.
 struct FieldRef {
   const double* p;

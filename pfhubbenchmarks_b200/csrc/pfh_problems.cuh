@@ -261,3 +261,8 @@ struct ProbBench2 {
     }
   }
 };
+
+// A generated model (codegen.py): `struct ProbUser` with the interface of the functors above.
+#ifdef PFH_USER_PROBLEM_HEADER
+#include PFH_USER_PROBLEM_HEADER
+#endif

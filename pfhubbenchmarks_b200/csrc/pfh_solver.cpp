@@ -19,6 +19,9 @@
 #include <cmath>
 
 #include "pfh_internal.h"
+#ifdef PFH_USER_PROBLEM_HEADER
+#include "pfh_problems.cuh"  // ProbUser: the generated model this copy of the library is built for
+#endif
 
 // ------------------------------------------------------------------------------------------
 // operator wrappers (ghost exchange + kernel)
@@ -251,13 +254,7 @@ HostTables host_tables(const pfh_ctx* c) {
 }
 
 // which fields form the Cahn-Hilliard pair, and what the remaining fields' diagonal blocks are
-struct PcLayout {
-  bool has_ch = false;
-  double Mob = 0, kappa = 0;
-  int n_spd = 0;
-  int spd_field[4];
-  double spd_am[4], spd_ak[4], spd_sign[4];
-};
+using PcLayout = PfhPcLayout;
 PcLayout pc_layout(const pfh_ctx* c) {
   PcLayout L;
   const LinCoefs lc = pfh_lin_coefs(c, c->dt);
@@ -283,6 +280,11 @@ PcLayout pc_layout(const pfh_ctx* c) {
       }
       L.n_spd = 2;
       break;
+#ifdef PFH_USER_PROBLEM_HEADER
+    case PFH_PROBLEM_USER:
+      ProbUser::pc_layout(lc, L);
+      break;
+#endif
   }
   return L;
 }
@@ -315,11 +317,11 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
     v_copy(c, z, r, c->nf * n);
     return;
   }
-  if (o.preconditioner == 1) {
+  const PcLayout L = pc_layout(c);
+  if (o.preconditioner == 1 || L.jacobi_only) {
     k_jacobi(c, c->jac_point, r, z);
     return;
   }
-  const PcLayout L = pc_layout(c);
   const int nM = o.pc_sweeps_mass > 0 ? o.pc_sweeps_mass : 3;
   const int nA = o.pc_sweeps_shifted > 0 ? o.pc_sweeps_shifted : 5;
   if (L.has_ch) {

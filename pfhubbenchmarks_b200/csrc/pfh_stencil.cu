@@ -386,18 +386,34 @@ Fields<P::NF> state_fields(const pfh_ctx* c, const double* u, const double* glo,
   return F;
 }
 
+// A library generated for one user model (PFH_USER_PROBLEM_HEADER, codegen.py) instantiates the kernels for that
+// model in addition to Cahn-Hilliard (whose TMA kernels are compiled in any case); PFH_ONLY_USER drops the other
+// shipped systems from it to keep the just-in-time build short.
+#ifdef PFH_USER_PROBLEM_HEADER
+#define PFH_USER_CASE(BODY) case PFH_PROBLEM_USER: { using P = ProbUser; BODY; } break;
+#else
+#define PFH_USER_CASE(BODY)
+#endif
+#ifdef PFH_ONLY_USER
+#define PFH_SHIPPED_CASES(BODY)
+#else
+#define PFH_SHIPPED_CASES(BODY)                                           \
+    case PFH_PROBLEM_BENCH2: { using P = ProbBench2; BODY; } break;       \
+    case PFH_PROBLEM_BENCH3: { using P = ProbBench3; BODY; } break;       \
+    case PFH_PROBLEM_BENCH6: { using P = ProbBench6; BODY; } break;
+#endif
 #define PFH_DISPATCH2(c, BODY)                                            \
   switch ((c)->prob.id) {                                                 \
     case PFH_PROBLEM_CH: { using P = ProbCH; BODY; } break;               \
-    case PFH_PROBLEM_BENCH2: { using P = ProbBench2; BODY; } break;       \
-    case PFH_PROBLEM_BENCH3: { using P = ProbBench3; BODY; } break;       \
-    case PFH_PROBLEM_BENCH6: { using P = ProbBench6; BODY; } break;       \
+    PFH_SHIPPED_CASES(BODY)                                               \
+    PFH_USER_CASE(BODY)                                                   \
     default: throw PfhError("unknown problem id");                        \
   }
 #define PFH_DISPATCH3(c, BODY)                                                     \
   switch ((c)->prob.id) {                                                          \
     case PFH_PROBLEM_CH: { using P = ProbCH; BODY; } break;                        \
-    default: throw PfhError("3-D meshes support PFH_PROBLEM_CH only (b13d)");      \
+    PFH_USER_CASE(BODY)                                                            \
+    default: throw PfhError("3-D meshes support PFH_PROBLEM_CH (b13d) and generated models only"); \
   }
 
 template <class P>
@@ -434,7 +450,10 @@ void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
 
 void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
-  const int nin = c->prob.id == PFH_PROBLEM_BENCH2 ? 5 : (c->prob.id == PFH_PROBLEM_BENCH3 ? 2 : 1);
+  int nin = c->prob.id == PFH_PROBLEM_BENCH2 ? 5 : (c->prob.id == PFH_PROBLEM_BENCH3 ? 2 : 1);
+#ifdef PFH_USER_PROBLEM_HEADER
+  if (c->prob.id == PFH_PROBLEM_USER) nin = ProbUser::NIN;
+#endif
   ProfScope ps(c, T_JAC_APPLY, 8.0 * (2 * c->nf + nin) * c->n_owned);
   if (c->dim == 3 && k3_jac_tma_launch(c, L, ulin, x, y)) return;
   if (c->dim == 3) {

@@ -301,30 +301,62 @@ class NonlinearVariationalProblem:
     """df.NonlinearVariationalProblem(F, w, bcs, J)  (bench1.py:76).  F is lowered and matched to a compiled operator
     family (forms.compile_form); the physical coefficients are read out of the form itself."""
 
-    def __init__(self, F, w, bcs=None, J=None, device=0, rank=0, nranks=1, nccl_id=None, krylov_basis=30):
-        if parameters["form_compiler"].get("quadrature_degree", 3) != 3:
-            raise NotImplementedError("the compiled operators integrate with the degree-3 rules the reference sets (bench1.py:14)")
-        if J is not None and not (isinstance(J, tuple) and J[0] == "derivative" and J[1] is F):
-            raise NotImplementedError("J must be df.derivative(F, w, dw)")
-        prev = None
-        for t in F.terms:
-            if t[0] == "src":
-                for s in sy.sympify(t[2]).free_symbols:
-                    if isinstance(s, forms.FieldSymbol) and s.owner is not w:
-                        prev = s.owner
-        if prev is None:
-            raise NotImplementedError("no previous-step Function in the form")
-        name, params, dt = forms.compile_form(F, w.W.nfields, w.symbols, prev.symbols, bcs or ())
+    def __init__(self, F, w, bcs=None, J=None, device=0, rank=0, nranks=1, nccl_id=None, krylov_basis=30, functionals=None):
+        """`functionals=(energy_form, second_form)`: only for forms that are none of the shipped systems -- the two
+        integrals the generated model's fused reduction kernel evaluates (df.assemble of exactly these is then one
+        launch); the shipped systems have theirs built in."""
+        problem, name, params, dt, prev, self.model = self._analyse(F, w, bcs, J, functionals)
         mesh = w.W.mesh
         if name == "bench1" and mesh.kind == "kuhn3d":
-            name = "b13d"
+            name = problem = "b13d"
         self.benchmark, self.mesh, self.dt, self.params = name, mesh, dt, params
-        self.ctx = engine.Context(name, mesh.ncell, mesh.length, params=params, device=device, rank=rank, nranks=nranks,
+        self.ctx = engine.Context(problem, mesh.ncell, mesh.length, params=params, device=device, rank=rank, nranks=nranks,
                                   nccl_id=nccl_id, krylov_basis=krylov_basis)
         self.w, self.w0 = w, prev
         w._bind(self)
         prev._bind(self)
         self._functionals = {}
+
+
+def _analyse(F, w, bcs, J, functionals):
+    """Everything the problem constructor does before it touches the GPU: checks, recognition of the shipped systems or
+    code generation for anything else.  Returns (problem for engine.Context, name, params, dt Constant, w0, model)."""
+    if parameters["form_compiler"].get("quadrature_degree", 3) != 3:
+        raise NotImplementedError("the compiled operators integrate with the degree-3 rules the reference sets (bench1.py:14)")
+    if J is not None and not (isinstance(J, tuple) and J[0] == "derivative" and J[1] is F):
+        raise NotImplementedError("J must be df.derivative(F, w, dw)")
+    prev = None
+    for t in F.terms:
+        if t[0] == "src":
+            for s in sy.sympify(t[2]).free_symbols:
+                if isinstance(s, forms.FieldSymbol) and s.owner is not w:
+                    prev = s.owner
+    if prev is None:
+        raise NotImplementedError("no previous-step Function in the form")
+    try:
+        name, params, dt = forms.compile_form(F, w.W.nfields, w.symbols, prev.symbols, bcs or ())
+        return name, name, params, dt, prev, None
+    except NotImplementedError:
+        # not one of the shipped systems: generate a functor for it and build its own copy of the library
+        # (what FFC does for every form at this point in the reference, bench1.py:76)
+        from . import codegen
+        if bcs:
+            raise NotImplementedError("Dirichlet conditions on a generated model")
+        L = codegen.lower(F, w.W.nfields, w.symbols, prev.symbols)
+        e_form, m_form = functionals if functionals is not None else (None, None)
+        model = codegen.UserModel(L, e_form, m_form)
+        return model, "user_" + model.tag, [], model.dt_const, prev, model
+
+
+NonlinearVariationalProblem._analyse = staticmethod(_analyse)
+
+
+def compile_only(F, w, bcs=None, J=None, functionals=None):
+    """Build (or find in the cache) the library a form needs, without creating a GPU context: None for the shipped
+    systems, the path of the generated copy otherwise.  Lets a GPU-less build host pre-compile a model."""
+    from . import build
+    model = _analyse(F, w, bcs, J, functionals)[5]
+    return None if model is None else build.build_user(model.source, model.tag)
 
 
 class NonlinearVariationalSolver(_Solver):
@@ -347,7 +379,11 @@ def assemble(form):
     key = repr(form.terms)
     plan = pr._functionals.get(key)
     if plan is None:
-        plan = forms.plan_functional(form, pr.benchmark, pr.ctx.params, owner.symbols)
+        tmpl = None
+        if pr.model is not None:       # generated model: its own energy density / second integrand
+            sub = dict(zip(pr.model.U, owner.symbols))
+            tmpl = (sy.sympify(pr.model.e_expr).subs(sub), dict(pr.model.grad), sy.sympify(pr.model.m_expr).subs(sub), 1.0)
+        plan = forms.plan_functional(form, pr.benchmark, pr.ctx.params, owner.symbols, tmpl)
         pr._functionals[key] = plan
     which, scale, corrections = plan
     val = scale * pr.ctx.energy(owner.tensor)[which] if which is not None else 0.0

@@ -44,8 +44,14 @@ def _ptr(t):
 class Context:
     def __init__(self, problem, ncell, length, params=None, device=0, rank=0, nranks=1, nccl_id=None,
                  krylov_basis=30, stream=None):
-        self.lib = _lib.load()
-        pid, nf, dparams, dic, names = PROBLEMS[problem]
+        if isinstance(problem, str):
+            self.lib = _lib.load()
+            pid, nf, dparams, dic, names = PROBLEMS[problem]
+        else:      # codegen.UserModel: its own copy of the library, built (or found in the cache) now
+            from . import build
+            self.lib = _lib.load_user(build.build_user(problem.source, problem.tag))
+            pid, nf, dparams, dic, names = _lib.PROBLEM_USER, problem.nf, [], [0.0], problem.field_names
+            problem = "user_" + problem.tag
         self.problem, self.nf, self.field_names, self.default_ic = problem, nf, names, list(dic)
         dim = len(ncell)
         assert dim in (2, 3) and len(length) == dim
@@ -75,11 +81,14 @@ class Context:
         self.device = int(device)
         self.ncell, self.length, self.dim, self.params = tuple(ncell), tuple(length), dim, params
         h = C.c_void_p()
-        _lib.check(self.lib.pfh_create(C.byref(cfg), C.byref(h)))
+        self._ck(self.lib.pfh_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self.n_owned = int(self.lib.pfh_n_owned(h))
         self.n_global = int(self.lib.pfh_n_global(h))
         self.rank, self.nranks = rank, nranks
+
+    def _ck(self, rc):
+        _lib.check(rc, self.lib)
 
     # ---- lifetime ----
     def close(self):
@@ -122,48 +131,48 @@ class Context:
 
     @dt.setter
     def dt(self, v):
-        _lib.check(self.lib.pfh_set_dt(self._h, float(v)))
+        self._ck(self.lib.pfh_set_dt(self._h, float(v)))
 
     # ---- device entry points ----
     def initial_condition(self, ic_params=None, out=None):
         q = np.ascontiguousarray(self.default_ic if ic_params is None else ic_params, dtype=np.float64)
         w = self.new_vector() if out is None else out
-        _lib.check(self.lib.pfh_initial_condition_dev(self._h, q.ctypes.data_as(C.POINTER(C.c_double)), len(q), _ptr(w)))
+        self._ck(self.lib.pfh_initial_condition_dev(self._h, q.ctypes.data_as(C.POINTER(C.c_double)), len(q), _ptr(w)))
         return w
 
     def residual(self, w, w0, out=None):
         F = self.new_vector() if out is None else out
-        _lib.check(self.lib.pfh_residual_dev(self._h, _ptr(w), _ptr(w0), _ptr(F)))
+        self._ck(self.lib.pfh_residual_dev(self._h, _ptr(w), _ptr(w0), _ptr(F)))
         return F
 
     def jac_setup(self, w):
         self._jac_point = w       # keep the tensor alive: the ctx only stores the pointer
-        _lib.check(self.lib.pfh_jac_setup_dev(self._h, _ptr(w)))
+        self._ck(self.lib.pfh_jac_setup_dev(self._h, _ptr(w)))
 
     def jac_apply(self, x, out=None):
         y = self.new_vector() if out is None else out
-        _lib.check(self.lib.pfh_jac_apply_dev(self._h, _ptr(x), _ptr(y)))
+        self._ck(self.lib.pfh_jac_apply_dev(self._h, _ptr(x), _ptr(y)))
         return y
 
     def precond_setup(self, **opts):
         o = _lib.default_opts(**opts)
-        _lib.check(self.lib.pfh_precond_setup(self._h, C.byref(o)))
+        self._ck(self.lib.pfh_precond_setup(self._h, C.byref(o)))
 
     def precond_apply(self, r, out=None):
         z = self.new_vector() if out is None else out
-        _lib.check(self.lib.pfh_precond_apply_dev(self._h, _ptr(r), _ptr(z)))
+        self._ck(self.lib.pfh_precond_apply_dev(self._h, _ptr(r), _ptr(z)))
         return z
 
     def newton_solve(self, w, w0, opts=None, **kw):
         """In place on w (initial guess -> solution). Returns the report dict."""
         o = opts if opts is not None else _lib.default_opts(**kw)
         rep = _lib.SolveReport()
-        _lib.check(self.lib.pfh_newton_solve_dev(self._h, _ptr(w), _ptr(w0), C.byref(o), C.byref(rep)))
+        self._ck(self.lib.pfh_newton_solve_dev(self._h, _ptr(w), _ptr(w0), C.byref(o), C.byref(rep)))
         return rep.as_dict()
 
     def energy(self, w):
         out = (C.c_double * 4)()
-        _lib.check(self.lib.pfh_energy_dev(self._h, _ptr(w), out))
+        self._ck(self.lib.pfh_energy_dev(self._h, _ptr(w), out))
         return float(out[0]), float(out[1])
 
     def eval_points(self, w, field, points):
@@ -174,14 +183,14 @@ class Context:
         d_pts = torch.from_numpy(pts).to(dev)
         out = torch.empty(len(pts), dtype=torch.float64, device=dev)
         if len(pts):
-            _lib.check(self.lib.pfh_eval_points_dev(self._h, _ptr(w), int(field), _ptr(d_pts.reshape(-1)), len(pts), _ptr(out)))
+            self._ck(self.lib.pfh_eval_points_dev(self._h, _ptr(w), int(field), _ptr(d_pts.reshape(-1)), len(pts), _ptr(out)))
             self.synchronize()               # the library ran on its own stream
         return out.cpu().numpy()
 
     def bilinear(self, w, field_a, field_b, am, ak):
         """u_a^T (am M + ak K) u_b: one piece of a df.assemble functional (bench2.py:190-192)."""
         out = C.c_double()
-        _lib.check(self.lib.pfh_bilinear_dev(self._h, _ptr(w), int(field_a), int(field_b), float(am), float(ak), C.byref(out)))
+        self._ck(self.lib.pfh_bilinear_dev(self._h, _ptr(w), int(field_a), int(field_b), float(am), float(ak), C.byref(out)))
         return float(out.value)
 
     # ---- host-buffer entry points (numpy fp64, C-contiguous) ----
@@ -194,29 +203,29 @@ class Context:
         o = opts if opts is not None else _lib.default_opts(**kw)
         rep = _lib.SolveReport()
         diag = (C.c_double * 4)()
-        _lib.check(self.lib.pfh_step_host(self._h, self._np(w), self._np(w0), float(dt), C.byref(o), C.byref(rep), diag))
+        self._ck(self.lib.pfh_step_host(self._h, self._np(w), self._np(w0), float(dt), C.byref(o), C.byref(rep), diag))
         d = rep.as_dict()
         d["energy"], d["mass"] = float(diag[0]), float(diag[1])
         return d
 
     def residual_host(self, w, w0):
         F = np.empty_like(w)
-        _lib.check(self.lib.pfh_residual_host(self._h, self._np(w), self._np(w0), self._np(F)))
+        self._ck(self.lib.pfh_residual_host(self._h, self._np(w), self._np(w0), self._np(F)))
         return F
 
     def jac_apply_host(self, w, x):
         y = np.empty_like(w)
-        _lib.check(self.lib.pfh_jac_apply_host(self._h, self._np(w), self._np(x), self._np(y)))
+        self._ck(self.lib.pfh_jac_apply_host(self._h, self._np(w), self._np(x), self._np(y)))
         return y
 
     def energy_host(self, w):
         out = (C.c_double * 4)()
-        _lib.check(self.lib.pfh_energy_host(self._h, self._np(w), out))
+        self._ck(self.lib.pfh_energy_host(self._h, self._np(w), out))
         return float(out[0]), float(out[1])
 
     # ---- instrumentation ----
     def set_option(self, key, value):
-        _lib.check(self.lib.pfh_set_option(self._h, key.encode(), float(value)))
+        self._ck(self.lib.pfh_set_option(self._h, key.encode(), float(value)))
 
     def launch_count(self):
         return int(self.lib.pfh_launch_count(self._h))
@@ -225,12 +234,12 @@ class Context:
         ms = (C.c_double * _lib.N_TIMERS)()
         n = (C.c_longlong * _lib.N_TIMERS)()
         nbytes = (C.c_double * _lib.N_TIMERS)()
-        _lib.check(self.lib.pfh_timers(self._h, ms, n, nbytes, 1 if reset else 0))
+        self._ck(self.lib.pfh_timers(self._h, ms, n, nbytes, 1 if reset else 0))
         return {self.lib.pfh_timer_name(i).decode(): {"ms": float(ms[i]), "launches": int(n[i]), "bytes": float(nbytes[i])}
                 for i in range(_lib.N_TIMERS)}
 
     def synchronize(self):
-        _lib.check(self.lib.pfh_synchronize(self._h))
+        self._ck(self.lib.pfh_synchronize(self._h))
 
 
 def nccl_unique_id():

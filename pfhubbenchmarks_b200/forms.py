@@ -490,9 +490,10 @@ def _match_bench2(L, bcs):
 # ------------------------------------------------------------------------------------------------------------------
 # functionals: the fused energy kernel returns (total free energy, second diagnostic); anything else is a correction
 # ------------------------------------------------------------------------------------------------------------------
-def plan_functional(form, name, params, fields):
+def plan_functional(form, name, params, fields, templates=None):
     """How to evaluate df.assemble(form): (which, scale, corrections) meaning
-    scale * energy()[which] + sum_k coef_k * u_k^T K u_k  (which None: only the gradient pieces)."""
+    scale * energy()[which] + sum_k coef_k * u_k^T K u_k  (which None: only the gradient pieces).
+    `templates` = (energy density, {field: gradient coefficient}, second integrand, scale) of a generated model."""
     pt = sy.Integer(0)
     grads = {}
     for t in form.terms:
@@ -511,7 +512,7 @@ def plan_functional(form, name, params, fields):
 
     pt = values(pt)
     grads = {k: _num(values(v)) for k, v in grads.items()}
-    e_t, g_t, m_t, m_scale = _functional_templates(name, params, fields)
+    e_t, g_t, m_t, m_scale = templates if templates is not None else _functional_templates(name, params, fields)
     if _is_zero(pt):
         which, scale, base = None, 1.0, {}
     elif _close(pt - m_t, 1e-9):

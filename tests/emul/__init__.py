@@ -13,12 +13,18 @@ _DEPS = _SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", f)
                 for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh")]
 
 
-def build():
-    if os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in _DEPS):
-        return _LIB
+def build(user_header=None):
+    """user_header: path of a generated model (codegen.UserModel.source written to a file): a separate library that
+    also dispatches PFH_PROBLEM_USER to it."""
+    lib, extra, deps = _LIB, [], _DEPS
+    if user_header is not None:
+        tag = os.path.basename(user_header).rsplit(".", 1)[0]
+        lib, extra, deps = os.path.join(_HERE, "libpfh_emul_%s.so" % tag), ['-DPFH_USER_PROBLEM_HEADER="%s"' % user_header], _DEPS + [user_header]
+    if os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in deps):
+        return lib
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-I" + cuda_inc, "-o", _LIB] + _SRC)
-    return _LIB
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-I" + cuda_inc, "-o", lib] + extra + _SRC)
+    return lib
 
 
 _P = ctypes.POINTER(ctypes.c_double)
@@ -29,13 +35,13 @@ def _p(a):
 
 
 def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=None, icp=None, nf=2,
-        z0=0, nzl=-1, glo=None, ghi=None):
+        z0=0, nzl=-1, glo=None, ghi=None, user_header=None):
     """mode: 0 residual, 1 jac_apply, 2 energy -> [E, M], 3 scalar op -> [Av, diag], 4 initial condition,
     5 nonlinear Jacobian block via the low-flop cube routine (3-D quartic problems)."""
-    lib = ctypes.CDLL(build())
+    lib = ctypes.CDLL(build(user_header))
     nc = (ctypes.c_int * 3)(*(list(ncell) + [1] * (3 - len(ncell))))
     ln = (ctypes.c_double * 3)(*(list(length) + [1.0] * (3 - len(length))))
-    pr = np.ascontiguousarray(params, dtype=np.float64)
+    pr = np.ascontiguousarray(params if len(params) else [0.0], dtype=np.float64)
     if mesh_kind == 3:
         nzv = ncell[2] + 1
         n = (ncell[0] + 1) * (ncell[1] + 1) * (nzv if nzl < 0 else nzl)

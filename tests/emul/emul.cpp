@@ -196,6 +196,9 @@ extern "C" int emul_run(int mesh_kind, int problem, const int* ncell, const doub
       case PFH_PROBLEM_BENCH2: return run<ProbBench2>(S, pp, dt, mode, U, X, U0, glo, ghi, out, icp);
       case PFH_PROBLEM_BENCH3: return run<ProbBench3>(S, pp, dt, mode, U, X, U0, glo, ghi, out, icp);
       case PFH_PROBLEM_BENCH6: return run<ProbBench6>(S, pp, dt, mode, U, X, U0, glo, ghi, out, icp);
+#ifdef PFH_USER_PROBLEM_HEADER
+      case PFH_PROBLEM_USER: return run<ProbUser>(S, pp, dt, mode, U, X, U0, glo, ghi, out, icp);   // a generated model (codegen.py)
+#endif
     }
     return -2;
   } catch (const std::exception& e) {

@@ -1,0 +1,118 @@
+"""sympy -> functor code generation (pfhubbenchmarks_b200/codegen.py), CPU side: a model that is none of the shipped
+systems (Cahn-Hilliard with a Flory-Huggins free energy coupled to an Allen-Cahn field) is written with the pfbase
+builders, lowered, emitted as `struct ProbUser`, compiled for the CPU by tests/emul together with the product's
+per-vertex operator code, and compared with the oracle's assembled operators for the same expressions."""
+import os
+
+import numpy as np
+import pytest
+import sympy as sy
+
+import emul
+import pfhubbenchmarks_b200.dolfin as df
+from helpers import rel_max
+from oracle import mesh as omesh, problems, stepper
+from pfhubbenchmarks_b200 import codegen
+from pfhubbenchmarks_b200.drivers import custom_model as cm
+from pfhubbenchmarks_b200.drivers.common import mixed_p1
+from pfhubbenchmarks_b200.pfbase import allen_cahn_weak_form, cahn_hilliard_weak_form, dx, grad, inner
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PARAMS = dict(M=cm.MOBILITY, kappa=cm.KAPPA, L=cm.L_ETA, ke=cm.KAPPA_ETA, chi=cm.CHI)
+free_energy = cm.free_energy
+
+
+def build_model(mesh):
+    """The weak form of drivers/custom_model.py, statement for statement, stopping before the problem constructor."""
+    W, w, w0, w_, dw = mixed_p1(mesh, 3)
+    dt = df.Constant(0.05)
+    M, kappa, L, ke = (df.Constant(PARAMS[k]) for k in ("M", "kappa", "L", "ke"))
+    c, mu, eta = df.split(w)
+    f = free_energy(c, eta)
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, M, kappa, df.diff(f, c)) \
+        + allen_cahn_weak_form(eta, w_[2], w0[2], dt, L, ke, df.diff(f, eta), df.Constant(0))
+    E = f * dx + kappa / 2.0 * inner(grad(c), grad(c)) * dx + ke / 2.0 * inner(grad(eta), grad(eta)) * dx
+    return dict(W=W, w=w, w0=w0, dw=dw, dt=dt, F=F, E=E, S=c * dx, f=f, c=c, eta=eta, kappa=kappa, ke=ke)
+
+
+class OracleModel(problems.Problem):
+    """The same model in the oracle's terms (assembled operators, lambdified sympy)."""
+    nf = 3
+    fields = ("c", "mu", "eta")
+
+    def __init__(self):
+        c, mu, eta = sy.symbols("c mu eta")
+        self.syms = (c, mu, eta)
+        f = free_energy(c, eta, sy.log)
+        self.g_exprs = [sy.Integer(0), -sy.diff(f, c), PARAMS["L"] * sy.diff(f, eta)]
+        self.e_expr, self.m_expr = f, c
+        self.grad_e = [(0, PARAMS["kappa"] / 2.0), (2, PARAMS["ke"] / 2.0)]
+        self._compile()
+
+    def lin(self, dt):
+        Mc = np.zeros((3, 3)); Kc = np.zeros((3, 3)); Mp = np.zeros(3)
+        Mc[0, 0] = 1.0 / dt; Mp[0] = 1.0 / dt; Kc[0, 1] = PARAMS["M"]
+        Mc[1, 1] = 1.0; Kc[1, 0] = -PARAMS["kappa"]
+        Mc[2, 2] = 1.0 / dt; Mp[2] = 1.0 / dt; Kc[2, 2] = PARAMS["L"] * PARAMS["ke"]
+        return Mc, Kc, Mp
+
+
+@pytest.fixture(scope="module")
+def model():
+    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(14.0, 10.0), 7, 5, "crossed")
+    parts = build_model(mesh)
+    L = codegen.lower(parts["F"], 3, parts["w"].symbols, parts["w0"].symbols)
+    m = codegen.UserModel(L, parts["E"], parts["S"], ("c", "mu", "eta"))
+    hdr = os.path.join(HERE, "emul", "user_%s.cuh" % m.tag)
+    if not os.path.exists(hdr) or open(hdr).read() != m.source:
+        open(hdr, "w").write(m.source)
+    return m, hdr
+
+
+def test_lowering_splits_linear_and_nonlinear_parts(model):
+    m, _ = model
+    assert m.inputs == [0, 2] and m.outputs == [1, 2]
+    dt = m.dt_sym
+    assert sy.simplify(m.Mc[0][0] - 1 / dt) == 0 and sy.simplify(m.Mp[0] - 1 / dt) == 0 and float(m.Kc[0][1]) == 2.0
+    # the -2 chi c term of f' is linear with a constant coefficient: it lands in the mass stencil, not in g
+    assert float(m.Mc[1][0]) == pytest.approx(2 * PARAMS["chi"]) and float(m.Mc[1][1]) == 1.0 and float(m.Kc[1][0]) == -1.5
+    assert sy.simplify(m.Mc[2][2] - (PARAMS["L"] * 1.0 + 1 / dt)) == 0 and float(m.Kc[2][2]) == pytest.approx(PARAMS["L"] * PARAMS["ke"])
+    assert m.layout == dict(has_ch=True, Mob=2.0, kappa=1.5, spd=[2], jacobi_only=False)
+    assert m.grad == {0: 0.75, 2: 0.35}
+    assert "struct ProbUser" in m.source and "log(" in m.source and "pow(" not in m.source
+
+
+@pytest.mark.parametrize("mk,ncell,length", [(2, (7, 5), (14.0, 10.0)), (3, (4, 3, 3), (8.0, 6.0, 6.0))])
+def test_generated_functor_matches_oracle(model, mk, ncell, length):
+    m, hdr = model
+    rng = np.random.default_rng(2)
+    om = omesh.crossed2d(*ncell, *length) if mk == 2 else omesh.kuhn3d(*ncell, *length)
+    D = stepper.Discretization(om, OracleModel())
+    U = np.stack([0.5 + 0.2 * rng.random(om.nv), rng.standard_normal(om.nv), 0.5 + 0.3 * rng.standard_normal(om.nv)])
+    U0 = np.stack([0.5 + 0.2 * rng.random(om.nv), rng.standard_normal(om.nv), 0.5 + 0.3 * rng.standard_normal(om.nv)])
+    X = rng.standard_normal((3, om.nv))
+    dt = 0.05
+    kw = dict(nf=3, user_header=hdr)
+    R = emul.run(mk, 100, ncell, length, [], dt, 0, U=U, U0=U0, **kw)
+    assert rel_max(R, D.residual(U, U0, dt)) < 1e-12
+    JX = emul.run(mk, 100, ncell, length, [], dt, 1, U=U, X=X, **kw)
+    assert rel_max(JX, (D.jacobian(U, dt) @ X.ravel()).reshape(3, -1)) < 1e-12
+    E, S = emul.run(mk, 100, ncell, length, [], dt, 2, U=U, **kw)
+    assert abs(E / D.energy(U) - 1) < 1e-12 and abs(S / D.mass(U) - 1) < 1e-13
+
+
+def test_unsupported_forms_are_refused():
+    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(4.0, 4.0), 2, 2, "crossed")
+    pe = df.FunctionSpace(mesh, "P", 1).ufl_element()
+    W = df.FunctionSpace(mesh, df.MixedElement([pe] * 2))
+    w, w0, w_ = df.Function(W), df.Function(W), df.TestFunction(W)
+    dt, one = df.Constant(0.1), df.Constant(1.0)
+    c, mu = df.split(w)
+    # a mobility that depends on the field is not a constant-coefficient stiffness term
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, c * (1 - c), one, df.diff(c ** 6, c))
+    with pytest.raises(NotImplementedError, match="diffusion"):
+        codegen.UserModel(codegen.lower(F, 2, w.symbols, w0.symbols))
+    # a load that depends on the previous step (semi-implicit splitting) does not fit the discrete form either
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, one, one, df.diff(c ** 6, c) - w0[0] ** 3)
+    with pytest.raises(NotImplementedError):
+        codegen.UserModel(codegen.lower(F, 2, w.symbols, w0.symbols))
