@@ -213,18 +213,4 @@ struct ProbUser {
            lin="\n".join(lin), pc="\n".join(pc))
 
 
-def lower(F, nfields, fields, prev):
-    """forms.Lowered of a residual form, with dt identified as in forms.compile_form."""
-    dt = None
-    for t in F.terms:
-        if t[0] != "src":
-            continue
-        e = sy.sympify(t[2])
-        for p in prev:
-            d = sy.diff(e, p)
-            for s in d.free_symbols:
-                if isinstance(s, forms.ConstSymbol):
-                    dt = s
-    if dt is None:
-        raise NotImplementedError("no time-derivative term (u - u0)/dt found")
-    return forms.Lowered(F, nfields, fields, prev, dt)
+lower = forms.lower

@@ -300,18 +300,26 @@ def _close(e, tol=1e-12):
         return False
 
 
-def compile_form(F, nfields, fields, prev, bcs=()):
-    """Map a residual form onto (benchmark name, params) of engine.PROBLEMS; NotImplementedError if it is none of them."""
-    dts = {s for t in F.terms if t[0] == "src" for s in sy.sympify(t[2]).free_symbols if isinstance(s, ConstSymbol)}
-    # dt is the Constant that multiplies a (u - u0) difference: identify it as the one whose removal kills the prev terms
+def lower(F, nfields, fields, prev):
+    """Lowered form of a residual; dt is the Constant in the coefficient of the previous-step fields, (u - u0)/dt."""
     dt = None
-    for s in dts:
-        if any(sy.diff(sy.sympify(t[2]), p) != 0 and sy.sympify(sy.diff(sy.sympify(t[2]), p)).has(s)
-               for t in F.terms if t[0] == "src" for p in prev):
-            dt = s
+    for t in F.terms:
+        if t[0] != "src":
+            continue
+        for p in prev:
+            for s in sy.diff(sy.sympify(t[2]), p).free_symbols:
+                if isinstance(s, ConstSymbol):
+                    dt = s
     if dt is None:
         raise NotImplementedError("no time-derivative term (u - u0)/dt found")
-    L = Lowered(F, nfields, fields, prev, dt)
+    return Lowered(F, nfields, fields, prev, dt)
+
+
+def compile_form(F, nfields, fields, prev, bcs=()):
+    """Map a residual form onto (benchmark name, params) of engine.PROBLEMS; NotImplementedError if it is none of them
+    (the caller then generates a functor for it, codegen.py)."""
+    L = lower(F, nfields, fields, prev)
+    dt = L.dt
     for matcher in (_match_ch, _match_bench6, _match_bench3, _match_bench2):
         try:
             out = matcher(L, bcs)
@@ -320,8 +328,7 @@ def compile_form(F, nfields, fields, prev, bcs=()):
         if out is not None:
             return out[0], [_snap(v) for v in out[1]], dt.const
     raise NotImplementedError(
-        "this weak form is not one of the compiled operator families (bench1/b13d, bench2, bench3, bench6); "
-        "generating a functor for new free energies is not implemented")
+        "this weak form is not one of the compiled operator families (bench1/b13d, bench2, bench3, bench6)")
 
 
 def _time_row(L, a):
