@@ -158,3 +158,38 @@ def test_function_storage_is_deferred():
     assert isinstance(df.Constant((0.0, 0.0)), forms.VectorZero)
     with pytest.raises(NotImplementedError):
         df.HDF5File(None, "x.h5", "w")
+
+
+def test_problem_constructor_binds_functions(monkeypatch):
+    """The whole df.NonlinearVariationalProblem constructor with the GPU context stubbed out: benchmark selection (2-D
+    -> bench1, BoxMesh -> b13d), coefficients handed to the context, w / w0 bound, an interpolate() issued before the
+    problem existed replayed on the new storage."""
+    from pfhubbenchmarks_b200.pfbase import InitialConditionsBench1
+    calls = []
+
+    class StubContext:
+        def __init__(self, problem, ncell, length, **kw):
+            calls.append(("ctx", problem, tuple(ncell), kw["params"]))
+            self.nf, self.params = 2, kw["params"]
+
+        def new_vector(self):
+            return object()
+
+        def initial_condition(self, args, out=None):
+            calls.append(("ic", list(args)))
+
+    monkeypatch.setattr(engine, "Context", StubContext)
+    for mesh, want in [(df.RectangleMesh(df.Point(0.0, 0.0), df.Point(8.0, 8.0), 4, 4, "crossed"), "bench1"),
+                       (df.BoxMesh(df.Point(0.0, 0.0, 0.0), df.Point(8.0, 8.0, 8.0), 4, 4, 4), "b13d")]:
+        del calls[:]
+        pe = df.FunctionSpace(mesh, "P", 1).ufl_element()
+        W = df.FunctionSpace(mesh, df.MixedElement([pe, pe]))
+        w, w0, w_, dw = df.Function(W), df.Function(W), df.TestFunction(W), df.TrialFunction(W)
+        dt = df.Constant(0.1)
+        c, mu = df.split(w)
+        w0.interpolate(InitialConditionsBench1(0.5, 0.05, degree=2))
+        F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, df.Constant(5.0), df.Constant(2.0),
+                                    df.diff(5.0 * (c - 0.3) ** 2 * (0.7 - c) ** 2, c))
+        p = df.NonlinearVariationalProblem(F, w, [], df.derivative(F, w, dw))
+        assert p.benchmark == want and p.model is None and p.w is w and p.w0 is w0 and p.dt is dt
+        assert calls == [("ctx", want, mesh.ncell, [0.3, 0.7, 5.0, 2.0, 5.0]), ("ic", [0.5, 0.05])]
