@@ -397,6 +397,45 @@ struct KspResult {
 //
 KspResult gmres_compressed(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o, pfh_solve_report* rep);
 
+// Hessenberg matrix of one GMRES cycle, kept upper triangular by Givens rotations; g carries the rotated right-hand
+// side, |g[j+1]| is the residual norm after column j.
+struct Arnoldi {
+  int m;
+  std::vector<double> H, cs, sn, g, y;
+  explicit Arnoldi(int m_) : m(m_), H((size_t)(m_ + 1) * m_, 0.0), cs(m_), sn(m_), g(m_ + 1), y(m_) {}
+  double& at(int i, int j) { return H[(size_t)i * m + j]; }
+  void start(double beta) {
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta;
+  }
+  // append column j (h[0..j] projections, hn the sub-diagonal entry); returns the new residual norm estimate
+  double push(int j, const double* h, double hn) {
+    for (int i = 0; i <= j; ++i) at(i, j) = h[i];
+    at(j + 1, j) = hn;
+    for (int i = 0; i < j; ++i) {
+      const double t = cs[i] * at(i, j) + sn[i] * at(i + 1, j);
+      at(i + 1, j) = -sn[i] * at(i, j) + cs[i] * at(i + 1, j);
+      at(i, j) = t;
+    }
+    const double den = std::hypot(at(j, j), at(j + 1, j));
+    cs[j] = at(j, j) / den;
+    sn[j] = at(j + 1, j) / den;
+    at(j, j) = den;
+    at(j + 1, j) = 0.0;
+    g[j + 1] = -sn[j] * g[j];
+    g[j] = cs[j] * g[j];
+    return std::fabs(g[j + 1]);
+  }
+  // y = H^-1 g for the first jd columns
+  void solve(int jd) {
+    for (int i = jd - 1; i >= 0; --i) {
+      double t = g[i];
+      for (int k = i + 1; k < jd; ++k) t -= at(i, k) * y[k];
+      y[i] = t / at(i, i);
+    }
+  }
+};
+
 KspResult gmres(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o, pfh_solve_report* rep) {
   const long long N = c->nf * c->n_owned;
   const long long vs = (N + 31) / 32 * 32;
@@ -404,8 +443,8 @@ KspResult gmres(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o
   double* V = c->V;
   double* w = c->W1;
   if (c->basis_precision == 2 || (c->basis_precision == 0 && o.krylov_rtol >= 1e-6)) return gmres_compressed(c, b, x, o, rep);
-  std::vector<double> H((m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), h(m + 2);
-  auto Hij = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
+  Arnoldi A(m);
+  std::vector<double> h(m + 2);
 
   v_zero(c, x, N);
   const double bnorm = std::sqrt(v_norm2(c, b, N));
@@ -418,8 +457,7 @@ KspResult gmres(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o
     // V0 = r / beta  (first cycle: r = b)
     if (first_cycle) v_scale(c, 1.0 / beta, b, V, N);
     first_cycle = false;
-    std::fill(g.begin(), g.end(), 0.0);
-    g[0] = beta;
+    A.start(beta);
     int jd = 0;
     bool done = false;
     for (int j = 0; j < m; ++j) {
@@ -444,40 +482,23 @@ KspResult gmres(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o
         hn = std::sqrt(hn2);
         v_multiaxpy(c, V, vs, j + 1, h.data(), w, 1.0 / hn, Vn, N);
       }
-      for (int i = 0; i <= j; ++i) Hij(i, j) = h[i];
-      Hij(j + 1, j) = hn;
-      for (int i = 0; i < j; ++i) {
-        const double t = cs[i] * Hij(i, j) + sn[i] * Hij(i + 1, j);
-        Hij(i + 1, j) = -sn[i] * Hij(i, j) + cs[i] * Hij(i + 1, j);
-        Hij(i, j) = t;
-      }
-      const double den = std::hypot(Hij(j, j), Hij(j + 1, j));
-      cs[j] = Hij(j, j) / den;
-      sn[j] = Hij(j + 1, j) / den;
-      Hij(j, j) = den;
-      Hij(j + 1, j) = 0.0;
-      g[j + 1] = -sn[j] * g[j];
-      g[j] = cs[j] * g[j];
+      const double res = A.push(j, h.data(), hn);
       ++its;
       jd = j + 1;
-      if (o.verbose > 1) fprintf(stderr, "      gmres it %3d  |r|/|b| = %.3e\n", its, std::fabs(g[j + 1]) / bnorm);
-      if (!(std::fabs(g[j + 1]) == std::fabs(g[j + 1]))) return {its, NAN, false};
-      if (std::fabs(g[j + 1]) <= tol || its >= o.krylov_maximum_iterations) {
+      if (o.verbose > 1) fprintf(stderr, "      gmres it %3d  |r|/|b| = %.3e\n", its, res / bnorm);
+      if (!(res == res)) return {its, NAN, false};
+      if (res <= tol || its >= o.krylov_maximum_iterations) {
         done = true;
         break;
       }
     }
     // y = H^-1 g ; x += P^-1 (V y)
-    for (int i = jd - 1; i >= 0; --i) {
-      double s = g[i];
-      for (int k = i + 1; k < jd; ++k) s -= Hij(i, k) * y[k];
-      y[i] = s / Hij(i, i);
-    }
-    v_combine(c, V, vs, jd, y.data(), w, N);
+    A.solve(jd);
+    v_combine(c, V, vs, jd, A.y.data(), w, N);
     s_precond_apply(c, w, c->DX2);
     rep->pc_applies++;
     v_axpy(c, 1.0, c->DX2, x, N);
-    const double est = std::fabs(g[jd]);
+    const double est = std::fabs(A.g[jd]);
     if (done) return {its, est / bnorm, est <= tol};
     // restart: true residual r = b - J x -> V0
     s_jac_apply(c, x, w);
@@ -506,8 +527,8 @@ KspResult gmres_compressed(pfh_ctx* c, const double* b, double* x, const pfh_sol
   float* U = reinterpret_cast<float*>(c->V);                            // fp32 basis shares the allocation ...
   double* ucur = c->V + ((long long)(m + 1) * vs / 2 + 31) / 32 * 32;   // ... and the fp64 working copy sits behind it
   double* w = c->W1;
-  std::vector<double> H((m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), d(m + 2), sv(m + 1), cf(m + 1);
-  auto Hij = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
+  Arnoldi A(m);
+  std::vector<double> d(m + 2), sv(m + 1), cf(m + 1), h(m + 1);
 
   v_zero(c, x, N);
   const double bnorm = std::sqrt(v_norm2(c, b, N));
@@ -520,8 +541,7 @@ KspResult gmres_compressed(pfh_ctx* c, const double* b, double* x, const pfh_sol
     double s2 = 0.0;
     v_multiaxpy32(c, U, vs, 0, nullptr, r, 1.0 / beta, ucur, U, N, &s2);   // u_0 = round(r / beta)
     sv[0] = std::sqrt(s2);
-    std::fill(g.begin(), g.end(), 0.0);
-    g[0] = beta * sv[0];                                                   // r = beta u_0 = beta s_0 v_0
+    A.start(beta * sv[0]);                                                 // r = beta u_0 = beta s_0 v_0
     int jd = 0;
     bool done = false;
     for (int j = 0; j < m; ++j) {
@@ -540,41 +560,25 @@ KspResult gmres_compressed(pfh_ctx* c, const double* b, double* x, const pfh_sol
       v_multiaxpy32(c, U, vs, j + 1, cf.data(), w, a, ucur, U + (long long)(j + 1) * vs, N, &s2);
       sv[j + 1] = std::sqrt(s2);
       const double hn = sv[j + 1] / (a * sv[j]);
-      for (int i = 0; i <= j; ++i) Hij(i, j) = d[i] / (sv[i] * sv[j]);
-      Hij(j + 1, j) = hn;
-      for (int i = 0; i < j; ++i) {
-        const double t = cs[i] * Hij(i, j) + sn[i] * Hij(i + 1, j);
-        Hij(i + 1, j) = -sn[i] * Hij(i, j) + cs[i] * Hij(i + 1, j);
-        Hij(i, j) = t;
-      }
-      const double den = std::hypot(Hij(j, j), Hij(j + 1, j));
-      cs[j] = Hij(j, j) / den;
-      sn[j] = Hij(j + 1, j) / den;
-      Hij(j, j) = den;
-      Hij(j + 1, j) = 0.0;
-      g[j + 1] = -sn[j] * g[j];
-      g[j] = cs[j] * g[j];
+      for (int i = 0; i <= j; ++i) h[i] = d[i] / (sv[i] * sv[j]);
+      const double res = A.push(j, h.data(), hn);
       ++its;
       jd = j + 1;
-      if (o.verbose > 1) fprintf(stderr, "      gmres it %3d  |r|/|b| = %.3e\n", its, std::fabs(g[j + 1]) / bnorm);
-      if (!(std::fabs(g[j + 1]) == std::fabs(g[j + 1]))) return {its, NAN, false};
-      if (std::fabs(g[j + 1]) <= tol || its >= o.krylov_maximum_iterations || !(sv[j + 1] > 0.0)) {
+      if (o.verbose > 1) fprintf(stderr, "      gmres it %3d  |r|/|b| = %.3e\n", its, res / bnorm);
+      if (!(res == res)) return {its, NAN, false};
+      if (res <= tol || its >= o.krylov_maximum_iterations || !(sv[j + 1] > 0.0)) {
         done = true;
         break;
       }
     }
     // y = H^-1 g ; x += P^-1 (sum_j (y_j / s_j) u_j)
-    for (int i = jd - 1; i >= 0; --i) {
-      double s = g[i];
-      for (int k = i + 1; k < jd; ++k) s -= Hij(i, k) * y[k];
-      y[i] = s / Hij(i, i);
-    }
-    for (int i = 0; i < jd; ++i) cf[i] = y[i] / sv[i];
+    A.solve(jd);
+    for (int i = 0; i < jd; ++i) cf[i] = A.y[i] / sv[i];
     v_combine32(c, U, vs, jd, cf.data(), w, N);
     s_precond_apply(c, w, c->DX2);
     rep->pc_applies++;
     v_axpy(c, 1.0, c->DX2, x, N);
-    const double estr = std::fabs(g[jd]);
+    const double estr = std::fabs(A.g[jd]);
     if (done) return {its, estr / bnorm, estr <= tol};
     // restart: true residual r = b - J x
     s_jac_apply(c, x, w);
