@@ -69,8 +69,25 @@ def BoxMesh(p0, p1, nx, ny, nz):
     return Mesh("kuhn3d", (nx, ny, nz), p1.x[:3])
 
 
+class _CommWorld:
+    """MPI.comm_world of the drivers (bench1.py:117, pfbase.py:73): rank / size of the torch.distributed job."""
+
+    @property
+    def rank(self):
+        return MPI.rank()
+
+    @property
+    def size(self):
+        try:
+            import torch.distributed as dist
+            return dist.get_world_size() if dist.is_initialized() else 1
+        except Exception:
+            return 1
+
+
 class MPI:
     """df.MPI.rank(mesh.mpi_comm()) guards (bench1.py:150): rank of this process in the torch.distributed job."""
+    comm_world = _CommWorld()
 
     @staticmethod
     def rank(_comm=None):

@@ -193,3 +193,23 @@ def test_problem_constructor_binds_functions(monkeypatch):
         p = df.NonlinearVariationalProblem(F, w, [], df.derivative(F, w, dw))
         assert p.benchmark == want and p.model is None and p.w is w and p.w0 is w0 and p.dt is dt
         assert calls == [("ctx", want, mesh.ncell, [0.3, 0.7, 5.0, 2.0, 5.0]), ("ic", [0.5, 0.05])]
+
+
+def test_namespace_covers_the_reference_drivers():
+    """Every name the reference drivers take from `import dolfin as df` / `from pfbase import *` exists here
+    (bench1.py, bench2.py, bench3.py, bench6.py, b13d.py and the weak-form section of pfbase.py)."""
+    import pfhubbenchmarks_b200.pfbase as pb
+    for name in ["parameters", "RectangleMesh", "BoxMesh", "Point", "Constant", "FunctionSpace", "MixedElement", "Function",
+                 "TrialFunction", "TestFunction", "split", "variable", "diff", "derivative", "set_log_level", "LogLevel",
+                 "NonlinearVariationalProblem", "NonlinearVariationalSolver", "assemble", "File", "MPI", "DOLFIN_EPS", "grad",
+                 "inner", "atan", "near", "Expression", "DirichletBC", "UserExpression", "SubDomain", "warning", "HDF5File"]:
+        assert hasattr(df, name), name
+    for name in ["InitialConditionsBench1", "InitialConditionsBench2", "InitialConditionsBench3", "InitialConditionsBench6",
+                 "cahn_hilliard_weak_form", "allen_cahn_RHS_IBP", "allen_cahn_weak_form", "poisson_weak_form",
+                 "diffusion_weak_form_RHS", "diffusion_weak_form", "euler_bwd_weak_form", "peval", "sample", "dx", "inner", "grad",
+                 "variable", "MPI", "HDF5File", "near", "UserExpression"]:
+        assert hasattr(pb, name), name
+    assert df.MPI.comm_world.rank == 0 and df.MPI.comm_world.size == 1 and df.MPI.rank(None) == 0
+    assert df.LogLevel.WARNING < df.LogLevel.ERROR
+    df.parameters["form_compiler"]["cpp_optimize_flags"] = "-O3 -ffast-math"      # accepted and ignored (bench1.py:12-13)
+    del df.parameters["form_compiler"]["cpp_optimize_flags"]
