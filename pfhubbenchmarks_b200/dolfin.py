@@ -59,7 +59,27 @@ class SubDomain:
         pass
 
 
-class Constant:
+class _SymArith:
+    """Arithmetic of objects that stand for a sympy symbol (`.sym`) inside expressions."""
+
+    def _op(self, other, fn):
+        if isinstance(other, (forms.Grad, forms.GradPair, forms.Test, forms.Tested, forms.Mixed, forms.Form, forms.Measure)):
+            return NotImplemented
+        return fn(self.sym, forms._expr(other))
+
+    def __add__(self, o): return self._op(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._op(o, lambda a, b: b + a)
+    def __sub__(self, o): return self._op(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._op(o, lambda a, b: b - a)
+    def __mul__(self, o): return self._op(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._op(o, lambda a, b: b * a)
+    def __truediv__(self, o): return self._op(o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return self._op(o, lambda a, b: b / a)
+    def __pow__(self, o): return self._op(o, lambda a, b: a ** b)
+    def __neg__(self): return -self.sym
+
+
+class Constant(_SymArith):
     """df.Constant: a symbol in forms, a float for the time loop (`float(dt)`, `dt.assign(x)`, bench1.py:29,171,180-183)."""
 
     def __new__(cls, value):
@@ -81,22 +101,6 @@ class Constant:
 
     def __repr__(self):
         return "Constant(%r)" % self.value
-
-    def _op(self, other, fn):
-        if isinstance(other, (forms.Grad, forms.GradPair, forms.Test, forms.Tested, forms.Mixed, forms.Form, forms.Measure)):
-            return NotImplemented
-        return fn(self.sym, forms._expr(other))
-
-    def __add__(self, o): return self._op(o, lambda a, b: a + b)
-    def __radd__(self, o): return self._op(o, lambda a, b: b + a)
-    def __sub__(self, o): return self._op(o, lambda a, b: a - b)
-    def __rsub__(self, o): return self._op(o, lambda a, b: b - a)
-    def __mul__(self, o): return self._op(o, lambda a, b: a * b)
-    def __rmul__(self, o): return self._op(o, lambda a, b: b * a)
-    def __truediv__(self, o): return self._op(o, lambda a, b: a / b)
-    def __rtruediv__(self, o): return self._op(o, lambda a, b: b / a)
-    def __pow__(self, o): return self._op(o, lambda a, b: a ** b)
-    def __neg__(self): return -self.sym
 
 
 class _Element:
@@ -244,12 +248,18 @@ class Function:
         return self.tensor.cpu().numpy().reshape(self.W.nfields, -1)
 
 
-class SubFunction:
-    """One component of a mixed Function: `f(x)` evaluates its P1 interpolant at a point (what pfbase.peval calls,
-    pfbase.py:50-62); `f.at(points)` does many points in one kernel launch."""
+class SubFunction(_SymArith):
+    """One component of a mixed Function (`c, _ = w.split()`, `w.sub(0)`).  In expressions it is the same symbol as
+    `df.split(w)[i]` -- the reference assembles `f_chem*dx + kappa/2*inner(grad(c), grad(c))*dx` and `c*dx` with the
+    split() component (bench1.py:188-194); `f(x)` evaluates its P1 interpolant at a point (what pfbase.peval calls,
+    pfbase.py:50-62), `f.at(points)` many points in one kernel launch; `file << (c, t)` writes it."""
 
     def __init__(self, owner, index):
         self.owner, self.index = owner, index
+
+    @property
+    def sym(self):
+        return self.owner.symbols[self.index]
 
     def at(self, points):
         return self.owner._problem.ctx.eval_points(self.owner.tensor, self.index, points)
@@ -393,7 +403,22 @@ def assemble(form):
 
 
 class HDF5File:
-    """bench1.py:116-118 opens an HDF5 checkpoint; h5py / HDF5 are not in this image: use df.File(<name>.pvd)."""
+    """`outfile = HDF5File(MPI.comm_world, filename + ".h5", "w")`; `outfile.write(mesh, "mesh")`;
+    `outfile.write(c, "c", float(t))`  (bench1.py:116-118,191).  HDF5 is not available in this image: the same time
+    series is written as <filename>.pvd + one VTU per step (what b13d.py / bench2.py write), with a warning."""
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError("HDF5 output is not available; use File('<name>.pvd') (VTU) instead")
+    def __init__(self, comm, path, mode="w"):
+        if mode != "w":
+            raise NotImplementedError("reading HDF5 checkpoints")
+        self._pvd = File((path[:-3] if path.endswith(".h5") else path) + ".pvd", "compressed")
+        warnings.warn("HDF5 is not available: writing %s (VTU series) instead of %s" % (self._pvd.path, path))
+
+    def write(self, obj, name, t=None):
+        if isinstance(obj, Mesh):                      # outfile.write(mesh, "mesh"): every VTU carries the mesh
+            self._pvd.mesh = obj
+            return
+        self._pvd.name = name
+        self._pvd << (obj, 0.0 if t is None else t)
+
+    def close(self):
+        pass

@@ -213,12 +213,14 @@ class Form:
 
 
 def _expr(x):
-    if hasattr(x, "sym"):
+    if hasattr(x, "sym"):          # dolfin.Constant, dolfin.SubFunction (a component from `c, _ = w.split()`)
         return x.sym
     return sy.sympify(x)
 
 
 def grad(u):
+    if hasattr(u, "sym") and isinstance(u.sym, FieldSymbol):   # grad(c) with c from `c, _ = w.split()` (bench1.py:188-193)
+        u = u.sym
     if isinstance(u, Test):
         return Grad(u)
     if isinstance(u, Tested):                       # grad(L * u_) with constant L  (pfbase.py:442)

@@ -182,3 +182,33 @@ def test_peval_and_sample():
     got = ctx.eval_points(w3, 0, pts)
     assert np.max(np.abs(got - fem.eval_points(m3, w3.cpu().numpy()[:m3.nv], pts))) < 1e-13
     ctx.close()
+
+
+def test_module_level_script_end_to_end(tmp_path):
+    """`python -m pfhubbenchmarks_b200.run_script tests/scripts/spinodal_module_level.py`: a reference-style program
+    (import dolfin as df / from pfbase import *, inline time loop, HDF5File, split() components inside assemble) runs
+    unchanged; its CSV equals the name-selected API stepping the same mesh with the same dt sequence."""
+    import os
+    import subprocess
+    import sys
+    from oracle import golden_io
+    from pfhubbenchmarks_b200 import engine
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pfhubbenchmarks_b200.run_script", os.path.join(root, "tests", "scripts", "spinodal_module_level.py"),
+                        str(tmp_path)], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(str(tmp_path / "stats.csv"), delimiter=",", skiprows=1)
+    assert rows.shape == (3, 3) and np.allclose(rows[:, 0], [0.1, 0.3, 0.7])
+    ctx = engine.Context("bench1", (24, 24), (48.0, 48.0))
+    w = ctx.initial_condition()
+    for k, h in enumerate((0.1, 0.2, 0.4)):
+        w0 = w.clone()
+        ctx.dt = h
+        assert ctx.newton_solve(w, w0)["converged"]
+        E, S = ctx.energy(w)
+        assert abs(rows[k, 1] - E) <= 1e-9 * abs(E) and abs(rows[k, 2] - S) <= 1e-9 * abs(S)
+    entries = golden_io.read_pvd(str(tmp_path / "conc.pvd"))              # the HDF5File stand-in
+    assert [t for t, _ in entries] == [0.1, pytest.approx(0.3), pytest.approx(0.7)]
+    last = golden_io.read_vtu_scalar(str(tmp_path / entries[-1][1]))
+    assert np.array_equal(last, w.cpu().numpy()[:ctx.n_owned])
+    ctx.close()
