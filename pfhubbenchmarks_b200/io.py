@@ -106,6 +106,7 @@ class File:
         if self._geom is None:
             self._geom = mesh_of(self.mesh)
         stem = os.path.basename(self.path)[:-4]
+        os.makedirs(os.path.dirname(self.path) or ".", exist_ok=True)      # DOLFIN creates results/<name>/ on first write
         fn = "%s%06d.vtu" % (stem, len(self.entries))
         write_vtu(os.path.join(os.path.dirname(self.path) or ".", fn), self._geom[0], self._geom[1], values, self.name, self.binary)
         self.entries.append((float(t), fn))
