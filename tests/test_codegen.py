@@ -116,3 +116,83 @@ def test_unsupported_forms_are_refused():
     F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, one, one, df.diff(c ** 6, c) - w0[0] ** 3)
     with pytest.raises(NotImplementedError):
         codegen.UserModel(codegen.lower(F, 2, w.symbols, w0.symbols))
+
+
+class _Generic(problems.Problem):
+    """An oracle problem from explicit pieces (syms, g, e, m, grad_e, lin matrices)."""
+
+    def __init__(self, syms, g_exprs, e_expr, m_expr, grad_e, lin):
+        self.nf, self.syms, self.g_exprs, self.e_expr, self.m_expr, self.grad_e, self._lin = len(syms), syms, g_exprs, e_expr, m_expr, grad_e, lin
+        self.fields = tuple(str(s) for s in syms)
+        self._compile()
+
+    def lin(self, dt):
+        return self._lin(dt)
+
+
+def _emit(parts_F, w, w0, E, S, names):
+    m = codegen.UserModel(codegen.lower(parts_F, len(names), w.symbols, w0.symbols), E, S, names)
+    hdr = os.path.join(HERE, "emul", "user_%s.cuh" % m.tag)
+    if not os.path.exists(hdr) or open(hdr).read() != m.source:
+        open(hdr, "w").write(m.source)
+    return m, hdr
+
+
+def _compare(m, hdr, D, nf, mk, ncell, length, U, U0, X, dt):
+    kw = dict(nf=nf, user_header=hdr)
+    assert rel_max(emul.run(mk, 100, ncell, length, [], dt, 0, U=U, U0=U0, **kw), D.residual(U, U0, dt)) < 1e-12
+    assert rel_max(emul.run(mk, 100, ncell, length, [], dt, 1, U=U, X=X, **kw), (D.jacobian(U, dt) @ X.ravel()).reshape(nf, -1)) < 1e-12
+    E, S = emul.run(mk, 100, ncell, length, [], dt, 2, U=U, **kw)
+    assert abs(E / D.energy(U) - 1) < 1e-12 and abs(S / D.mass(U) - 1) < 1e-12
+
+
+def test_two_coupled_parabolic_fields():
+    """A thermal phase-field pair with a different coupling polynomial than bench3 and an exponential source:
+    off-diagonal stiffness (the latent-heat term), both fields nonlinear inputs, SPD/SPD preconditioner layout."""
+    from pfhubbenchmarks_b200.pfbase import allen_cahn_RHS_IBP, diffusion_weak_form
+    ncell, length = (6, 5), (12.0, 10.0)
+    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(*length), *ncell, "crossed")
+    W, w, w0, w_, dw = mixed_p1(mesh, 2)
+    dt, D_, tau, W2 = df.Constant(0.02), df.Constant(4.0), df.Constant(0.8), df.Constant(1.3)
+    U, p = df.split(w)
+    dfdp = (p - 0.7 * U * (1 - p ** 2) * df.exp(-U ** 2)) * (1 - p ** 2) * (1 + 0.1 * p)
+    zero = df.Constant(0.0)
+    F = diffusion_weak_form(U, w_[0], w0[0], dt, df.Constant(1.0), D_, df.Constant((0.0, 0.0)), zero) \
+        - 0.5 * allen_cahn_RHS_IBP(p, w_[0], 1 / tau, W2, -dfdp, zero) * dx \
+        + allen_cahn_weak_form(p, w_[1], w0[1], dt, 1 / tau, W2, -dfdp, zero)
+    E = (0.25 * p ** 4 - 0.5 * p ** 2 + 0.5 * W2 * inner(grad(p), grad(p))) * dx
+    m, hdr = _emit(F, w, w0, E, 0.5 * (p + 1.0) * dx, ("U", "phi"))
+    assert m.inputs == [0, 1] and m.outputs == [0, 1] and m.layout["spd"] == [0, 1] and not m.layout["has_ch"]
+    sU, sp = sy.symbols("U phi")
+    g = (sp - 0.7 * sU * (1 - sp ** 2) * sy.exp(-sU ** 2)) * (1 - sp ** 2) * (1 + 0.1 * sp)
+
+    def lin(h):
+        return (np.array([[1 / h, 0.0], [0.0, 1 / h]]), np.array([[4.0, 0.5 * 1.3 / 0.8], [0.0, 1.3 / 0.8]]), np.array([1 / h, 1 / h]))
+
+    om = omesh.crossed2d(*ncell, *length)
+    D = stepper.Discretization(om, _Generic((sU, sp), [-(0.5 / 0.8) * g, -(1 / 0.8) * g], 0.25 * sp ** 4 - 0.5 * sp ** 2,
+                                            0.5 * (sp + 1.0), [(1, 0.65)], lin))
+    rng = np.random.default_rng(4)
+    U_, U0_, X_ = (rng.standard_normal((2, om.nv)) * 0.6 for _ in range(3))
+    _compare(m, hdr, D, 2, 2, ncell, length, U_, U0_, X_, 0.02)
+
+
+def test_single_allen_cahn_field():
+    """One field only (nf = 1): the smallest model the generator and the operator code accept."""
+    ncell, length = (5, 4), (5.0, 4.0)
+    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(*length), *ncell, "crossed")
+    W, w, w0, w_, dw = mixed_p1(mesh, 1)
+    dt, L, k = df.Constant(0.1), df.Constant(2.0), df.Constant(0.5)
+    e = df.split(w)[0]
+    f = e ** 2 * (1 - e) ** 2 + 0.3 * df.sin(e)
+    F = allen_cahn_weak_form(e, w_[0], w0[0], dt, L, k, df.diff(f, e), df.Constant(0))
+    m, hdr = _emit(F, w, w0, f * dx + k / 2.0 * inner(grad(e), grad(e)) * dx, e * dx, ("eta",))
+    assert m.nf == 1 and m.inputs == [0] and m.outputs == [0] and m.layout["spd"] == [0]
+    s = sy.Symbol("eta")
+    fs = s ** 2 * (1 - s) ** 2 + 0.3 * sy.sin(s)
+    om = omesh.crossed2d(*ncell, *length)
+    D = stepper.Discretization(om, _Generic((s,), [2.0 * sy.diff(fs, s)], fs, s, [(0, 0.25)],
+                                            lambda h: (np.array([[1 / h]]), np.array([[1.0]]), np.array([1 / h]))))
+    rng = np.random.default_rng(6)
+    U_, U0_, X_ = (rng.standard_normal((1, om.nv)) * 0.5 for _ in range(3))
+    _compare(m, hdr, D, 1, 2, ncell, length, U_, U0_, X_, 0.1)
