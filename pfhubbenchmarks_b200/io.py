@@ -128,3 +128,67 @@ class File:
             values = values.detach().cpu().numpy()
         self.write(values, float(t))
         return self
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# readers: what process_bench1.py / b1_read.py do with the HDF5 time series (`c/vector_{i}`), on the PVD/VTU series
+# ---------------------------------------------------------------------------------------------------------------------
+_NP_TYPES = {"Float64": "<f8", "Float32": "<f4", "UInt32": "<u4", "Int32": "<i4", "UInt8": "u1", "Int64": "<i8", "UInt64": "<u8"}
+
+
+def _inline_zlib(text, dtype):
+    """VTK inline compressed DataArray: base64 of the uint32 header (nblocks, block size, last block size, compressed
+    sizes...) directly followed by base64 of the concatenated zlib blocks."""
+    text = "".join(text.split())
+    nblocks = struct.unpack("<I", base64.b64decode(text[:8])[:4])[0]
+    hlen = 4 * (3 + nblocks)
+    hchars = 4 * ((hlen + 2) // 3)
+    sizes = struct.unpack("<%dI" % (3 + nblocks), base64.b64decode(text[:hchars])[:hlen])[3:]
+    blob, out, pos = base64.b64decode(text[hchars:]), [], 0
+    for n in sizes:
+        out.append(zlib.decompress(blob[pos:pos + n]))
+        pos += n
+    return np.frombuffer(b"".join(out), dtype=dtype)
+
+
+def read_vtu(path):
+    """(points (n, 3), cells (m, k), {name: values (n,)}) of a VTU file as DOLFIN (or write_vtu) writes it:
+    `format="ascii"` or `format="binary"` with vtkZLibDataCompressor."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(path).getroot()
+    piece = root.find("./UnstructuredGrid/Piece")
+    npts, ncells = int(piece.get("NumberOfPoints")), int(piece.get("NumberOfCells"))
+
+    def array(node):
+        dtype = np.dtype(_NP_TYPES[node.get("type")])
+        if node.get("format") == "binary":
+            if root.get("compressor") != "vtkZLibDataCompressor":
+                raise ValueError("only zlib-compressed inline binary arrays are supported")
+            return _inline_zlib(node.text, dtype)
+        return np.array(node.text.split(), dtype=np.float64).astype(dtype)
+
+    points = array(piece.find("./Points/DataArray")).reshape(npts, 3).astype(np.float64)
+    conn = next(a for a in piece.findall("./Cells/DataArray") if a.get("Name") == "connectivity")
+    cells = array(conn).reshape(ncells, -1).astype(np.int64)
+    data = {a.get("Name"): array(a).astype(np.float64) for a in piece.findall("./PointData/DataArray")}
+    return points, cells, data
+
+
+def read_pvd(path):
+    """[(time, vtu path), ...] of a PVD collection (paths resolved relative to the PVD file)."""
+    import xml.etree.ElementTree as ET
+    base = os.path.dirname(os.path.abspath(path))
+    return [(float(d.get("timestep")), os.path.join(base, d.get("file"))) for d in ET.parse(path).getroot().iter("DataSet")]
+
+
+def read_series(path):
+    """times (nt,), values (nt, n_vertices) of the single scalar field of a PVD series: the arrays the reference's
+    post-processing builds from `c/vector_{i}` (process_bench1.py:8-34)."""
+    entries = read_pvd(path)
+    vals = []
+    for _, fn in entries:
+        data = read_vtu(fn)[2]
+        if len(data) != 1:
+            raise ValueError("expected one scalar field per VTU, found %s" % sorted(data))
+        vals.append(next(iter(data.values())))
+    return np.array([t for t, _ in entries]), np.array(vals)

@@ -1,4 +1,6 @@
 """Field output (VTU/PVD, "next" row N2): round trip through the golden readers and mesh identity with DOLFIN's files."""
+import os
+
 import numpy as np
 import pytest
 
@@ -40,3 +42,38 @@ def test_large_binary_array_uses_several_zlib_blocks(tmp_path):
     io.write_vtu(str(tmp_path / "a.vtu"), pts, cells, v, name="c", binary=True)
     d = golden_io.read_vtu(str(tmp_path / "a.vtu"))
     assert np.array_equal(d["data"]["c"], v) and np.array_equal(d["cells"], cells) and np.array_equal(d["points"], pts)
+
+
+@pytest.mark.parametrize("mode", ["ascii", "compressed"])
+def test_product_readers_round_trip(tmp_path, mode):
+    """io.read_vtu / read_pvd / read_series (the PVD/VTU counterpart of process_bench1.py's HDF5 reading) against the
+    writer and against the oracle's independent reader; large enough for several zlib blocks in compressed mode."""
+    from oracle import golden_io
+    mesh = api.RectangleMesh(api.Point(0.0, 0.0), api.Point(40.0, 30.0), 40, 30, "crossed")
+    n = 41 * 31 + 40 * 30
+    rng = np.random.default_rng(0)
+    f = io.File(str(tmp_path / "out" / "conc.pvd"), mode, mesh=mesh, name="c")
+    fields = [rng.standard_normal(n) for _ in range(3)]
+    for k, v in enumerate(fields):
+        f << (v, 0.1 * (k + 1))
+    times, vals = io.read_series(str(tmp_path / "out" / "conc.pvd"))
+    assert np.allclose(times, [0.1, 0.2, 0.3]) and vals.shape == (3, n)
+    assert all(np.array_equal(vals[k], fields[k]) for k in range(3))
+    pts, cells, data = io.read_vtu(io.read_pvd(str(tmp_path / "out" / "conc.pvd"))[1][1])
+    ref = golden_io.read_vtu(io.read_pvd(str(tmp_path / "out" / "conc.pvd"))[1][1])
+    assert np.array_equal(pts, ref["points"]) and np.array_equal(cells, ref["cells"]) and list(data) == ["c"]
+    gp, gc = io.crossed_mesh(40, 30, 40.0, 30.0)
+    assert np.array_equal(pts[:, :2], gp[:, :2]) and np.array_equal(cells, gc)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/results/bench1/conc.pvd"), reason="reference checkout not present on this box")
+def test_product_reader_on_the_committed_reference_series(golden):
+    """The reference's own output files (zlib/base64 VTU for bench1, ASCII for bench2) through the product reader:
+    identical to the golden arrays that were extracted with the oracle's reader."""
+    t, v = io.read_series("/root/reference/results/bench1/conc.pvd")
+    assert np.allclose(t, [0.1, 0.3, 0.7, 1.5, 3.1, 4.7]) and np.array_equal(v, golden["bench1_fields"]["c"])
+    t2, v2 = io.read_series("/root/reference/results/bench2/conc.pvd")
+    g2 = golden["bench2_fields"]                      # a subset of the 29 snapshots: index, times, fields[k, (c, eta1..4), :]
+    assert v2.shape == (29, 20201)
+    for k, idx in enumerate(g2["index"]):
+        assert t2[int(idx)] == g2["times"][k] and np.array_equal(v2[int(idx)], g2["fields"][k, 0])
