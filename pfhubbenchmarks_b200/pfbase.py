@@ -17,7 +17,59 @@ import numpy as np
 from .api import (InitialConditionsBench1, InitialConditionsBench2, InitialConditionsBench3,  # noqa: F401
                   InitialConditionsBench6)
 from .dolfin import *  # noqa: F401,F403
-from .dolfin import MPI, HDF5File, dx, grad, inner  # noqa: F401
+from .dolfin import MPI, HDF5File, UserExpression, dx, grad, inner  # noqa: F401
+
+
+def _spinodal(x, c0, epsilon):
+    return c0 + epsilon * (np.cos(0.105 * x[0]) * np.cos(0.11 * x[1]) + (np.cos(0.13 * x[0]) * np.cos(0.087 * x[1])) ** 2
+                           + np.cos(0.025 * x[0] - 0.15 * x[1]) * np.cos(0.07 * x[0] - 0.02 * x[1]))
+
+
+class _ReducedBench2(UserExpression):
+    """Initial data of the reduced Ostwald-ripening drivers (bench2_eta1.py / bench2_eta2.py; pfbase.py:195-260): c as in
+    benchmark 1, mu = 0, and the first N_ETA order parameters of the PFHub formula.  Evaluated on the host; a weak form
+    with fewer than four order parameters is not one of the shipped systems, so it runs as a generated model."""
+    N_ETA = 1
+
+    def __init__(self, c0, epsilon, epsilon_eta, psi, **kwargs):
+        super().__init__(**kwargs)
+        self.c0, self.epsilon, self.epsilon_eta, self.psi = c0, epsilon, epsilon_eta, psi
+
+    def eval(self, values, x):
+        values[0] = _spinodal(x, self.c0, self.epsilon)
+        values[1] = 0.0
+        for i in range(self.N_ETA):
+            k = i + 1.0
+            wave = (np.cos(0.01 * k * x[0] - 4.0) * np.cos((0.007 + 0.01 * k) * x[1])
+                    + np.cos((0.11 + 0.01 * k) * x[0]) * np.cos((0.11 + 0.01 * k) * x[1]))
+            beat = np.cos((0.046 + 0.001 * k) * x[0] - (0.0405 + 0.001 * k) * x[1]) * np.cos((0.031 + 0.001 * k) * x[0] - (0.004 + 0.001 * k) * x[1])
+            values[2 + i] = self.epsilon_eta * (wave + self.psi * beat ** 2) ** 2
+
+    def value_shape(self):
+        return (2 + self.N_ETA,)
+
+
+class ICB2_jank1(_ReducedBench2):
+    N_ETA = 1
+
+
+class ICB2_jank2(_ReducedBench2):
+    N_ETA = 2
+
+
+class LangevinNoise(UserExpression):
+    """Uniform noise of amplitude `amp` on three components (pfbase.py:341-356; unused by the drivers).  `seed` makes it
+    reproducible, which the reference's version is not."""
+
+    def __init__(self, amp, seed=None, **kwargs):
+        super().__init__(**kwargs)
+        self.amp, self._rng = amp, np.random.default_rng(seed)
+
+    def eval(self, values, x):
+        values[:3] = self.amp * self._rng.uniform(-0.5, 0.5, 3)
+
+    def value_shape(self):
+        return (3,)
 
 
 def peval(f, x):

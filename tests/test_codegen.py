@@ -196,3 +196,51 @@ def test_single_allen_cahn_field():
     rng = np.random.default_rng(6)
     U_, U0_, X_ = (rng.standard_normal((1, om.nv)) * 0.5 for _ in range(3))
     _compare(m, hdr, D, 1, 2, ncell, length, U_, U0_, X_, 0.1)
+
+
+@pytest.mark.parametrize("num_eta", [1, 2])
+def test_reduced_ostwald_models(num_eta):
+    """dolfin/bench2_eta1.py / bench2_eta2.py (benchmark 2's free energy with one / two order parameters) are not
+    shipped systems: drivers/bench2_eta.py runs them as generated models.  The emitted functor against the oracle."""
+    import itertools
+    from pfhubbenchmarks_b200 import dolfin as shim
+    from pfhubbenchmarks_b200.drivers import bench2_eta
+    ncell, length = (6, 5), (12.0, 10.0)
+    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(*length), *ncell, "crossed")
+    got = {}
+    orig = shim.compile_only
+
+    def capture(F, w, bcs=None, J=None, functionals=None):
+        got["model"] = shim._analyse(F, w, bcs, J, functionals)[5]
+        return None
+
+    shim.compile_only = capture
+    try:
+        bench2_eta.setup(mesh, num_eta, compile_only=True)
+    finally:
+        shim.compile_only = orig
+    m = got["model"]
+    assert m is not None and m.nf == 2 + num_eta and m.layout["has_ch"] and m.layout["spd"] == list(range(2, 2 + num_eta))
+    hdr = os.path.join(HERE, "emul", "user_%s.cuh" % m.tag)
+    if not os.path.exists(hdr) or open(hdr).read() != m.source:
+        open(hdr, "w").write(m.source)
+    syms = sy.symbols("c mu eta1 eta2")[:2 + num_eta]
+    c, es = syms[0], syms[2:]
+    H = sum(e ** 3 * (6 * e ** 2 - 15 * e + 10) for e in es)
+    Wd = sum(e ** 2 * (1 - e) ** 2 for e in es) + 5.0 * sum(a ** 2 * b ** 2 for a, b in itertools.combinations(es, 2))
+    f = 2.0 * (c - 0.3) ** 2 * (1 - H) + 2.0 * (c - 0.7) ** 2 * H + Wd
+    nf = 2 + num_eta
+
+    def lin(h):
+        Mc = np.zeros((nf, nf)); Kc = np.zeros((nf, nf)); Mp = np.zeros(nf)
+        Mc[0, 0] = 1 / h; Mp[0] = 1 / h; Kc[0, 1] = 5.0; Mc[1, 1] = 1.0; Kc[1, 0] = -3.0
+        for i in range(2, nf):
+            Mc[i, i] = 1 / h; Mp[i] = 1 / h; Kc[i, i] = 15.0
+        return Mc, Kc, Mp
+
+    om = omesh.crossed2d(*ncell, *length)
+    D = stepper.Discretization(om, _Generic(syms, [sy.Integer(0), -sy.diff(f, c)] + [5.0 * sy.diff(f, e) for e in es], f, c,
+                                            [(0, 1.5)] + [(2 + i, 1.5) for i in range(num_eta)], lin))
+    rng = np.random.default_rng(8)
+    U_, U0_, X_ = (0.5 + 0.3 * rng.standard_normal((nf, om.nv)) for _ in range(3))
+    _compare(m, hdr, D, nf, 2, ncell, length, U_, U0_, X_, 0.01)
