@@ -65,3 +65,18 @@ def test_generated_model_steps_match_oracle():
     assert ctx.newton_solve(v.clone(), v)["converged"]
     ctx.close()
     problem.ctx.close()
+
+
+def test_reduced_ostwald_driver(tmp_path):
+    """`python -m pfhubbenchmarks_b200.drivers.bench2_eta --num-eta 1`: the reference's bench2_eta1 model end to end as a
+    generated model with the host-evaluated ICB2_jank1 initial data: converges, solute conserved, energy decays."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pfhubbenchmarks_b200.drivers.bench2_eta", "--num-eta", "1", "--max-steps", "4", "--quiet",
+                        "--outdir", str(tmp_path)], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(str(tmp_path / "bench2_eta1_out.csv"), delimiter=",", skiprows=1)
+    assert rows.shape == (4, 3) and np.all(np.diff(rows[:, 0]) > 0)
+    assert np.all(np.diff(rows[:, 1]) < 0) and np.allclose(rows[:, 2], rows[0, 2], rtol=1e-9)
