@@ -320,6 +320,8 @@ class NonlinearVariationalProblem:
         if name == "bench1" and mesh.kind == "kuhn3d":
             name = problem = "b13d"
         self.benchmark, self.mesh, self.dt, self.params = name, mesh, dt, params
+        self._frozen = [(s.const, s.const.value) for t in F.terms for e in t[1:] if isinstance(e, sy.Basic)
+                        for s in e.free_symbols if isinstance(s, forms.ConstSymbol) and s.const is not dt]
         self.ctx = engine.Context(problem, mesh.ncell, mesh.length, params=params, device=device, rank=rank, nranks=nranks,
                                   nccl_id=nccl_id, krylov_basis=krylov_basis)
         self.w, self.w0 = w, prev
@@ -370,7 +372,15 @@ def compile_only(F, w, bcs=None, J=None, functionals=None):
 
 
 class NonlinearVariationalSolver(_Solver):
-    pass
+    def solve(self):
+        """As api.NonlinearVariationalSolver.solve; additionally refuses to run with a stale model: the coefficients
+        were read out of the form (or baked into generated code) when the problem was created, so a Constant other than
+        dt that has been re-assigned since would silently be ignored, where DOLFIN would honour it."""
+        for const, value in self.problem._frozen:
+            if const.value != value:
+                raise RuntimeError("%r was %r when the problem was created; only dt may change between solves -- "
+                                   "create a new NonlinearVariationalProblem" % (const, value))
+        return super().solve()
 
 
 def assemble(form):

@@ -246,3 +246,31 @@ def test_module_level_script_runs_through_the_aliases(monkeypatch, tmp_path):
             else:
                 sys.modules[k] = v
     assert created == [("bench1", (24, 24), [0.3, 0.7, 5.0, 2.0, 5.0])]
+
+
+def test_reassigned_coefficient_is_refused(monkeypatch):
+    """Coefficients are read from the form when the problem is created: re-assigning one later (DOLFIN would pick it
+    up) must not be silently ignored."""
+    class StubContext:
+        def __init__(self, problem, ncell, length, **kw):
+            self.nf, self.params, self.dt = 2, kw["params"], None
+
+        def new_vector(self):
+            return object()
+
+        def newton_solve(self, w, w0, opts=None):
+            return dict(niters=2, converged=1, reason=2)
+
+    monkeypatch.setattr(engine, "Context", StubContext)
+    W, w, w0, w_ = _ch()
+    dt, M, kappa = df.Constant(0.1), df.Constant(5.0), df.Constant(2.0)
+    c, mu = df.split(w)
+    F = cahn_hilliard_weak_form(c, mu, w_[0], w_[1], w0[0], dt, M, kappa, df.diff(5.0 * (c - 0.3) ** 2 * (0.7 - c) ** 2, c))
+    problem = df.NonlinearVariationalProblem(F, w, [], df.derivative(F, w, df.TrialFunction(W)))
+    solver = df.NonlinearVariationalSolver(problem)
+    assert solver.solve() == (2, True)
+    dt.assign(0.2)                       # the time step may change
+    assert solver.solve() == (2, True) and problem.ctx.dt == 0.2
+    kappa.assign(3.0)                    # anything else may not
+    with pytest.raises(RuntimeError, match="only dt may change"):
+        solver.solve()
