@@ -442,7 +442,9 @@ KspResult gmres(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o
   const int m = std::max(1, std::min(o.krylov_restart > 0 ? o.krylov_restart : 30, c->cfg.krylov_basis));
   double* V = c->V;
   double* w = c->W1;
-  if (c->basis_precision == 2 || (c->basis_precision == 0 && o.krylov_rtol >= 1e-6)) return gmres_compressed(c, b, x, o, rep);
+  // the fp32 basis and its fp64 working copy share the basis allocation: that needs room for two vectors behind half of it
+  const bool fits = m >= 2 && vs >= 64;
+  if (fits && (c->basis_precision == 2 || (c->basis_precision == 0 && o.krylov_rtol >= 1e-6))) return gmres_compressed(c, b, x, o, rep);
   Arnoldi A(m);
   std::vector<double> h(m + 2);
 
