@@ -4,6 +4,7 @@ recognised as the compiled operator family they are, and give back the coefficie
 import importlib
 import sys
 
+import numpy as np
 import pytest
 import sympy as sy
 
@@ -274,3 +275,17 @@ def test_reassigned_coefficient_is_refused(monkeypatch):
     kappa.assign(3.0)                    # anything else may not
     with pytest.raises(RuntimeError, match="only dt may change"):
         solver.solve()
+
+
+def test_vertex_coordinates_follow_the_dolfin_order():
+    """engine.Context.vertex_coordinates (used to evaluate user-written UserExpressions on the host) lists vertices in the
+    library's order: the oracle's crossed / Kuhn meshes, and the owned planes only for a z-slab."""
+    import types
+    from oracle import mesh as omesh
+    ctx = types.SimpleNamespace(dim=2, ncell=(7, 5), length=(14.0, 10.0))
+    assert np.allclose(engine.Context.vertex_coordinates(ctx), omesh.crossed2d(7, 5, 14.0, 10.0).coords, atol=1e-14)
+    full = omesh.kuhn3d(4, 3, 5, 8.0, 6.0, 10.0).coords
+    ctx = types.SimpleNamespace(dim=3, ncell=(4, 3, 5), length=(8.0, 6.0, 10.0), z_range=(0, 6))
+    assert np.allclose(engine.Context.vertex_coordinates(ctx), full, atol=1e-14)
+    ctx.z_range = (2, 4)
+    assert np.allclose(engine.Context.vertex_coordinates(ctx), full[2 * 20:4 * 20], atol=1e-14)
