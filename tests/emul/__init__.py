@@ -75,3 +75,38 @@ def sample(mesh_kind, ncell, length, u, pts, z0=0, nzl=-1, glo=None, ghi=None):
     rc = lib.emul_sample(mesh_kind, nc, ln, z0, nzl, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(pts), len(pts), _p(out))
     assert rc == 0, rc
     return out
+
+
+_SOLVER_LIB = os.path.join(_HERE, "libpfh_emul_solver.so")
+_SOLVER_SRC = [os.path.join(_HERE, "emul_solver.cpp"), os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_tables.cpp")]
+
+
+def build_solver():
+    """CPU build of the product's host solver (csrc/pfh_solver.cpp) over loop versions of the kernel launchers."""
+    deps = _DEPS + _SOLVER_SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_solver.cpp")]
+    if os.path.exists(_SOLVER_LIB) and all(os.path.getmtime(_SOLVER_LIB) >= os.path.getmtime(s) for s in deps):
+        return _SOLVER_LIB
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-I" + cuda_inc, "-o", _SOLVER_LIB] + _SOLVER_SRC)
+    return _SOLVER_LIB
+
+
+def newton_step(mesh_kind, problem, ncell, length, params, dt, w, w0, basis_precision=0, **opts):
+    """One backward-Euler step with the product's Newton-Krylov solver on the CPU.  Returns (w_new (nf, n), report dict);
+    `opts` are pfh_solver_opts fields (pfhubbenchmarks_b200._lib.default_opts)."""
+    from pfhubbenchmarks_b200 import _lib
+    lib = ctypes.CDLL(build_solver())
+    nc = (ctypes.c_int * 3)(*(list(ncell) + [1] * (3 - len(ncell))))
+    ln = (ctypes.c_double * 3)(*(list(length) + [1.0] * (3 - len(length))))
+    pr = np.ascontiguousarray(params, dtype=np.float64)
+    o = _lib.default_opts(**opts)
+    w = np.ascontiguousarray(w, dtype=np.float64).copy()
+    w0 = np.ascontiguousarray(w0, dtype=np.float64)
+    rep = np.zeros(8)
+    lib.emul_newton_step.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _P, ctypes.c_int, ctypes.c_double,
+                                     ctypes.c_void_p, ctypes.c_int, _P, _P, _P]
+    rc = lib.emul_newton_step(mesh_kind, problem, nc, ln, _p(pr), len(pr), float(dt), ctypes.byref(o), int(basis_precision),
+                              _p(w.reshape(-1)), _p(w0.reshape(-1)), _p(rep))
+    assert rc == 0, rc
+    keys = ("niters", "converged", "reason", "fnorm0", "fnorm", "krylov_its", "residual_evals", "pc_applies")
+    return w, dict(zip(keys, rep))

@@ -1,0 +1,61 @@
+"""The product's host solver (csrc/pfh_solver.cpp: Newton, 'basic' / 'cp' line searches, GMRES with the fp64 and the
+fp32-stored basis, Schur/Chebyshev preconditioner with its block layouts, Dirichlet handling) compiled for the CPU by
+tests/emul over loop versions of the kernel launchers, against the oracle's Newton/LU step.  No GPU: this is the leg that
+lets solver-side changes be checked where there is none (the launch layer is what the GPU tests cover)."""
+import numpy as np
+import pytest
+
+import emul
+from helpers import discretization
+from oracle import krylov
+
+CASES = [
+    # name, mesh kind, problem id, cells, lengths, params, dt, line search
+    ("bench1", 2, 1, (12, 10), (24.0, 20.0), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, 0),
+    ("bench2", 2, 2, (10, 8), (20.0, 16.0), [0.3, 0.7, 2.0, 3.0, 3.0, 5.0, 1.0, 5.0, 5.0], 0.01, 1),
+    ("bench3", 2, 3, (10, 8), (27.0, 22.0), [1.0, 1.0, 10.0, 10.0 / 0.6267, 27.0 * 22.0], 0.01, 0),
+    ("bench6", 2, 6, (10, 8), (10.0, 8.0), [0.3, 0.7, 5.0, 2.0, 5.0, 0.09, 90.0], 0.01, 1),
+    ("b13d", 3, 1, (6, 5, 4), (12.0, 10.0, 8.0), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, 0),
+]
+
+
+@pytest.mark.parametrize("name,mk,pid,ncell,length,params,dt,ls", CASES)
+def test_newton_krylov_step_matches_oracle(name, mk, pid, ncell, length, params, dt, ls):
+    D = discretization(name, ncell, length)
+    u0 = D.prob.ic(D.mesh)
+    w, rep = emul.newton_step(mk, pid, ncell, length, params, dt, u0, u0, basis_precision=1, absolute_tolerance=1e-10, krylov_rtol=1e-10,
+                              maximum_iterations=30, krylov_maximum_iterations=5000, line_search=ls)
+    assert rep["converged"] == 1 and rep["fnorm"] < 1e-10 * max(1.0, rep["fnorm0"]) + 1e-10, rep
+    u, n, ok = D.solve_step(u0, u0, dt, atol=1e-11, linear="lu" if mk == 2 else krylov.make_linear(rtol=1e-12))
+    assert ok
+    for f in range(D.nf):
+        scale = max(np.linalg.norm(u[f]), 1e-3 * np.sqrt(u[f].size))
+        assert np.linalg.norm(w[f] - u[f]) / scale < 2e-8, (name, f, np.linalg.norm(w[f] - u[f]) / scale)
+
+
+@pytest.mark.parametrize("name,mk,pid,ncell,length,params,dt,ls", CASES[:1] + CASES[4:])
+def test_compressed_basis_is_equivalent(name, mk, pid, ncell, length, params, dt, ls):
+    """Default tolerances (atol 1e-6, GMRES rtol 1e-5): the fp32-stored basis needs the same number of Krylov iterations
+    as the fp64 one (+-1) and lands on the same Newton iterate to the nonlinear tolerance."""
+    D = discretization(name, ncell, length)
+    u0 = D.prob.ic(D.mesh)
+    w64, r64 = emul.newton_step(mk, pid, ncell, length, params, dt, u0, u0, basis_precision=1)
+    w32, r32 = emul.newton_step(mk, pid, ncell, length, params, dt, u0, u0, basis_precision=2)
+    wau, rau = emul.newton_step(mk, pid, ncell, length, params, dt, u0, u0, basis_precision=0)
+    assert r64["converged"] == r32["converged"] == 1 and r64["niters"] == r32["niters"]
+    assert abs(r64["krylov_its"] - r32["krylov_its"]) <= 1, (r64, r32)
+    assert np.linalg.norm(w64[0] - w32[0]) / np.linalg.norm(w64[0]) < 1e-7
+    assert np.array_equal(wau, w32) and rau["krylov_its"] == r32["krylov_its"]          # auto = fp32 at rtol 1e-5
+
+
+def test_nonconvergence_is_reported_not_raised():
+    """maximum_iterations hit => converged = 0, reason < 0 (the drivers' dt-halving retry depends on it, bench1.py:164-177)."""
+    D = discretization("bench1", (8, 6), (16.0, 12.0))
+    u0 = D.prob.ic(D.mesh)
+    w, rep = emul.newton_step(2, 1, (8, 6), (16.0, 12.0), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, u0, u0, absolute_tolerance=1e-14,
+                              relative_tolerance=0.0, maximum_iterations=1)
+    assert rep["converged"] == 0 and rep["reason"] == -5 and rep["niters"] == 1
+    # a preconditioner choice the Schur layout does not cover falls back to point Jacobi and still converges
+    w, rep = emul.newton_step(2, 1, (8, 6), (16.0, 12.0), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, u0, u0, preconditioner=1,
+                              krylov_maximum_iterations=4000)
+    assert rep["converged"] == 1
