@@ -23,7 +23,8 @@ def build(user_header=None):
     if os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in deps):
         return lib
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-I" + cuda_inc, "-o", lib] + extra + _SRC)
+    # -Bsymbolic: the product library may be loaded RTLD_GLOBAL in the same process and exports functions of the same names
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", lib] + extra + _SRC)
     return lib
 
 
@@ -87,7 +88,7 @@ def build_solver():
     if os.path.exists(_SOLVER_LIB) and all(os.path.getmtime(_SOLVER_LIB) >= os.path.getmtime(s) for s in deps):
         return _SOLVER_LIB
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-I" + cuda_inc, "-o", _SOLVER_LIB] + _SOLVER_SRC)
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", _SOLVER_LIB] + _SOLVER_SRC)
     return _SOLVER_LIB
 
 
