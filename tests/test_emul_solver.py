@@ -59,3 +59,35 @@ def test_nonconvergence_is_reported_not_raised():
     w, rep = emul.newton_step(2, 1, (8, 6), (16.0, 12.0), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, u0, u0, preconditioner=1,
                               krylov_maximum_iterations=4000)
     assert rep["converged"] == 1
+
+
+@pytest.mark.parametrize("basis", [1, 2])
+@pytest.mark.parametrize("opts", [dict(krylov_restart=5), dict(krylov_restart=3), dict(pc_variant=0), dict(pc_variant=0, krylov_restart=4),
+                                  dict(preconditioner=2, krylov_restart=30, krylov_maximum_iterations=20000)])
+def test_restarts_and_preconditioner_variants(basis, opts):
+    """Short restart cycles (the restart path recomputes the true residual and re-seeds the basis), the full
+    block-triangular variant of the Schur preconditioner and no preconditioner at all reach the same Newton solution,
+    with the fp64 and with the fp32-stored basis."""
+    ncell, length, params = (8, 6), (16.0, 12.0), [0.3, 0.7, 5.0, 2.0, 5.0]
+    D = discretization("bench1", ncell, length)
+    u0 = D.prob.ic(D.mesh)
+    ref, r0 = emul.newton_step(2, 1, ncell, length, params, 0.1, u0, u0, basis_precision=1, absolute_tolerance=1e-9, krylov_rtol=1e-6)
+    kw = dict(absolute_tolerance=1e-9, krylov_rtol=1e-6, maximum_iterations=30)
+    kw.update(opts)
+    w, rep = emul.newton_step(2, 1, ncell, length, params, 0.1, u0, u0, basis_precision=basis, **kw)
+    assert rep["converged"] == 1, rep
+    assert np.linalg.norm(w[0] - ref[0]) / np.linalg.norm(ref[0]) < 1e-7, (opts, rep)
+
+
+def test_stagnating_linear_solve_stops_newton():
+    """GMRES(2) stagnates on the block-triangularly preconditioned system of the second Newton iteration: the Krylov
+    iteration cap is hit, Newton stops with reason -3 (SNES_DIVERGED_LINEAR_SOLVE) and reports converged = 0 -- identically
+    for both basis storages."""
+    ncell, length, params = (8, 6), (16.0, 12.0), [0.3, 0.7, 5.0, 2.0, 5.0]
+    D = discretization("bench1", ncell, length)
+    u0 = D.prob.ic(D.mesh)
+    reps = [emul.newton_step(2, 1, ncell, length, params, 0.1, u0, u0, basis_precision=b, absolute_tolerance=1e-9, krylov_rtol=1e-6,
+                             krylov_restart=2, krylov_maximum_iterations=300)[1] for b in (1, 2)]
+    for rep in reps:
+        assert rep["converged"] == 0 and rep["reason"] == -3 and rep["niters"] == 1
+    assert reps[0]["krylov_its"] == reps[1]["krylov_its"]
