@@ -73,7 +73,7 @@ typedef struct {
   double relative_tolerance;     /* ||F|| < rtol ||F_0||      (DOLFIN default 1e-9) */
   double solution_tolerance;     /* ||dw|| < stol ||w||       (DOLFIN default 1e-16) */
   int maximum_iterations;        /* drivers: 10 */
-  int line_search;               /* 0 = 'basic' (full step), 1 = 'cp' (critical point, one secant iteration) */
+  int line_search;               /* 0 = 'basic' (full step), 1 = 'cp' (critical point, one secant iteration), 2 = 'bt' (backtracking) */
   double krylov_rtol;            /* relative residual of each linear solve (PETSc default 1e-5) */
   double krylov_atol;
   int krylov_maximum_iterations; /* drivers: 1000 / 5000 / N^3/10 */

@@ -167,7 +167,7 @@ class _Params(dict):
         super().__setitem__(k, v)
 
 
-_LINE_SEARCH = {"basic": 0, "cp": 1}
+_LINE_SEARCH = {"basic": 0, "cp": 1, "bt": 2}
 
 
 class NonlinearVariationalSolver:

@@ -652,7 +652,8 @@ void s_newton(pfh_ctx* c, double* w, const double* w0, const pfh_solver_opts* op
       // 'cp' (critical point, PETSc SNESLINESEARCHCP with its default single secant iteration; bench2.py:140,
       // bench6.py:117): find lambda with F(x + lambda dx) . dx = 0 from the values at lambda = 0 and 1
       double d0[2], d1[2];
-      v_multidot(c, c->DX, 0, 1, c->R, N, d0);   // F(x) . dx
+      v_multidot(c, c->DX, 0, 1, c->B, N, d0);   // B = -F(x) survives the linear solve (R may serve as its scratch)
+      d0[0] = -d0[0];                            // F(x) . dx
       s_residual(c, U, w0, c->W1, true);
       rep->residual_evals++;
       v_multidot(c, c->DX, 0, 1, c->W1, N, d1);  // F(x + dx) . dx
@@ -662,6 +663,50 @@ void s_newton(pfh_ctx* c, double* w, const double* w0, const pfh_solver_opts* op
       if (!(lambda == lambda) || lambda <= 1e-3 || lambda > 4.0) lambda = 1.0;  // guard: keep the full step
       if (o.verbose) fprintf(stderr, "    cp line search: lambda = %.4f\n", lambda);
       if (lambda != 1.0) v_axpy(c, lambda - 1.0, c->DX, U, N);
+    }
+    if (o.line_search == 2) {
+      // 'bt' (PETSc SNESLINESEARCHBT, its default; the drivers mention it as working, bench3.py:127): backtracking on
+      // phi(lambda) = 1/2 |F(x + lambda dx)|^2 with the Armijo condition phi(lambda) <= phi(0) + alpha lambda phi'(0),
+      // alpha = 1e-4; first a quadratic, then cubic fits through the last two trial points, each new lambda clamped to
+      // [0.1, 0.5] of the previous one, at most 40 trials.  phi'(0) = F . (J dx) is taken from one extra J.v.
+      const double alpha = 1e-4, f2 = fnorm * fnorm;
+      double d[2];
+      s_jac_apply(c, c->DX, c->W2);
+      rep->jac_applies++;
+      v_multidot(c, c->W2, 0, 1, c->B, N, d);     // B = -F(x) survives the linear solve (R may serve as its scratch)
+      double slope = -d[0];
+      if (slope > 0.0) slope = -slope;
+      if (slope == 0.0) slope = -1.0;
+      auto gnorm2_at = [&](double lam_new, double lam_cur) {   // moves U from x + lam_cur dx to x + lam_new dx
+        if (lam_new != lam_cur) v_axpy(c, lam_new - lam_cur, c->DX, U, N);
+        s_residual(c, U, w0, c->W1, true);
+        rep->residual_evals++;
+        return v_norm2(c, c->W1, N);
+      };
+      double lam = 1.0, g2 = gnorm2_at(1.0, 1.0);
+      if (!(0.5 * g2 <= 0.5 * f2 + alpha * lam * slope)) {
+        double lam_prev = lam, g2_prev = g2;
+        double lt = -slope / (g2 - f2 - 2.0 * slope);             // minimiser of the quadratic through phi(0), phi'(0), phi(1)
+        lt = std::fmin(std::fmax(lt, 0.1 * lam), 0.5 * lam);
+        if (!(lt == lt)) lt = 0.5 * lam;
+        g2 = gnorm2_at(lt, lam);
+        lam = lt;
+        for (int k = 0; k < 40 && !(0.5 * g2 <= 0.5 * f2 + alpha * lam * slope); ++k) {
+          const double t1 = 0.5 * (g2 - f2) - lam * slope, t2 = 0.5 * (g2_prev - f2) - lam_prev * slope;
+          const double a = (t1 / (lam * lam) - t2 / (lam_prev * lam_prev)) / (lam - lam_prev);
+          const double b = (-lam_prev * t1 / (lam * lam) + lam * t2 / (lam_prev * lam_prev)) / (lam - lam_prev);
+          double disc = b * b - 3.0 * a * slope;
+          if (disc < 0.0) disc = 0.0;
+          lt = a == 0.0 ? -slope / (2.0 * b) : (-b + std::sqrt(disc)) / (3.0 * a);
+          lt = std::fmin(std::fmax(lt, 0.1 * lam), 0.5 * lam);
+          if (!(lt == lt)) lt = 0.5 * lam;
+          lam_prev = lam;
+          g2_prev = g2;
+          g2 = gnorm2_at(lt, lam);
+          lam = lt;
+        }
+      }
+      if (o.verbose) fprintf(stderr, "    bt line search: lambda = %.4g\n", lam);
     }
     if (o.solution_tolerance > 1e-14) {
       const double dn = std::sqrt(v_norm2(c, c->DX, N)), un = std::sqrt(v_norm2(c, U, N));

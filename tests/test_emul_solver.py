@@ -91,3 +91,25 @@ def test_stagnating_linear_solve_stops_newton():
     for rep in reps:
         assert rep["converged"] == 0 and rep["reason"] == -3 and rep["niters"] == 1
     assert reps[0]["krylov_its"] == reps[1]["krylov_its"]
+
+
+def test_backtracking_line_search():
+    """'bt' (PETSc's default backtracking): identical iterates to 'basic' when the full Newton step already decreases
+    the residual, and a converged step where the full step ('basic') and the secant step ('cp') both diverge
+    (benchmark 2 from its initial condition at dt = 0.64)."""
+    ncell, length, params = (10, 8), (20.0, 16.0), [0.3, 0.7, 5.0, 2.0, 5.0]
+    D = discretization("bench1", ncell, length)
+    u0 = D.prob.ic(D.mesh)
+    wb, rb = emul.newton_step(2, 1, ncell, length, params, 0.1, u0, u0, basis_precision=1, line_search=0)
+    wt, rt = emul.newton_step(2, 1, ncell, length, params, 0.1, u0, u0, basis_precision=1, line_search=2)
+    assert np.array_equal(wb, wt) and rb["niters"] == rt["niters"] and rb["krylov_its"] == rt["krylov_its"]
+    p2 = [0.3, 0.7, 2.0, 3.0, 3.0, 5.0, 1.0, 5.0, 5.0]
+    D2 = discretization("bench2", (12, 10), (24.0, 20.0))
+    v0 = D2.prob.ic(D2.mesh)
+    out = {ls: emul.newton_step(2, 2, (12, 10), (24.0, 20.0), p2, 0.64, v0, v0, basis_precision=1, line_search=ls, maximum_iterations=25)
+           for ls in (0, 1, 2)}
+    assert out[0][1]["converged"] == 0 and out[1][1]["converged"] == 0
+    w, rep = out[2]
+    assert rep["converged"] == 1 and rep["fnorm"] < 1e-6
+    u, n, ok = D2.solve_step(w, v0, 0.64, atol=1e-11)            # the oracle's Newton/LU started from that solution stays there
+    assert ok and max(np.linalg.norm(w[f] - u[f]) / max(np.linalg.norm(u[f]), 1.0) for f in range(6)) < 1e-6
