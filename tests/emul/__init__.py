@@ -82,31 +82,36 @@ _SOLVER_LIB = os.path.join(_HERE, "libpfh_emul_solver.so")
 _SOLVER_SRC = [os.path.join(_HERE, "emul_solver.cpp"), os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_tables.cpp")]
 
 
-def build_solver():
-    """CPU build of the product's host solver (csrc/pfh_solver.cpp) over loop versions of the kernel launchers."""
+def build_solver(user_header=None):
+    """CPU build of the product's host solver (csrc/pfh_solver.cpp) over loop versions of the kernel launchers;
+    user_header: additionally for one generated model (codegen.py), in a library of its own."""
+    lib, extra = _SOLVER_LIB, []
     deps = _DEPS + _SOLVER_SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_solver.cpp")]
-    if os.path.exists(_SOLVER_LIB) and all(os.path.getmtime(_SOLVER_LIB) >= os.path.getmtime(s) for s in deps):
-        return _SOLVER_LIB
+    if user_header is not None:
+        tag = os.path.basename(user_header).rsplit(".", 1)[0]
+        lib, extra, deps = os.path.join(_HERE, "libpfh_emul_solver_%s.so" % tag), ['-DPFH_USER_PROBLEM_HEADER="%s"' % user_header], deps + [user_header]
+    if os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in deps):
+        return lib
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", _SOLVER_LIB] + _SOLVER_SRC)
-    return _SOLVER_LIB
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", lib] + extra + _SOLVER_SRC)
+    return lib
 
 
-def newton_step(mesh_kind, problem, ncell, length, params, dt, w, w0, basis_precision=0, **opts):
+def newton_step(mesh_kind, problem, ncell, length, params, dt, w, w0, basis_precision=0, user_header=None, **opts):
     """One backward-Euler step with the product's Newton-Krylov solver on the CPU.  Returns (w_new (nf, n), report dict);
     `opts` are pfh_solver_opts fields (pfhubbenchmarks_b200._lib.default_opts)."""
     from pfhubbenchmarks_b200 import _lib
-    lib = ctypes.CDLL(build_solver())
+    lib = ctypes.CDLL(build_solver(user_header))
     nc = (ctypes.c_int * 3)(*(list(ncell) + [1] * (3 - len(ncell))))
     ln = (ctypes.c_double * 3)(*(list(length) + [1.0] * (3 - len(length))))
-    pr = np.ascontiguousarray(params, dtype=np.float64)
+    pr = np.ascontiguousarray(params if len(params) else [0.0], dtype=np.float64)
     o = _lib.default_opts(**opts)
     w = np.ascontiguousarray(w, dtype=np.float64).copy()
     w0 = np.ascontiguousarray(w0, dtype=np.float64)
     rep = np.zeros(8)
     lib.emul_newton_step.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _P, ctypes.c_int, ctypes.c_double,
                                      ctypes.c_void_p, ctypes.c_int, _P, _P, _P]
-    rc = lib.emul_newton_step(mesh_kind, problem, nc, ln, _p(pr), len(pr), float(dt), ctypes.byref(o), int(basis_precision),
+    rc = lib.emul_newton_step(mesh_kind, problem, nc, ln, _p(pr), len(params), float(dt), ctypes.byref(o), int(basis_precision),
                               _p(w.reshape(-1)), _p(w0.reshape(-1)), _p(rep))
     assert rc == 0, rc
     keys = ("niters", "converged", "reason", "fnorm0", "fnorm", "krylov_its", "residual_evals", "pc_applies")

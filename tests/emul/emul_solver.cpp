@@ -24,12 +24,18 @@ namespace {
 std::map<const pfh_ctx*, Setup*> g_setup;
 const Setup& setup_of(const pfh_ctx* c) { return *g_setup.at(c); }
 
+#ifdef PFH_USER_PROBLEM_HEADER
+#define EMUL_USER_CASE(BODY) case PFH_PROBLEM_USER: { using P = ProbUser; BODY; } break;   // a generated model (codegen.py)
+#else
+#define EMUL_USER_CASE(BODY)
+#endif
 #define EMUL_DISPATCH(c, BODY)                                           \
   switch ((c)->prob.id) {                                                \
     case PFH_PROBLEM_CH: { using P = ProbCH; BODY; } break;              \
     case PFH_PROBLEM_BENCH2: { using P = ProbBench2; BODY; } break;      \
     case PFH_PROBLEM_BENCH3: { using P = ProbBench3; BODY; } break;      \
     case PFH_PROBLEM_BENCH6: { using P = ProbBench6; BODY; } break;      \
+    EMUL_USER_CASE(BODY)                                                 \
     default: throw PfhError("emul: unknown problem id");                 \
   }
 
@@ -283,6 +289,9 @@ extern "C" int emul_newton_step(int mesh_kind, int problem, const int* ncell, co
     c.prob.id = problem;
     for (int i = 0; i < nparams; ++i) c.prob.p[i] = params[i];
     c.nf = problem == PFH_PROBLEM_BENCH2 ? 6 : (problem == PFH_PROBLEM_BENCH6 ? 3 : 2);
+#ifdef PFH_USER_PROBLEM_HEADER
+    if (problem == PFH_PROBLEM_USER) c.nf = ProbUser::NF;
+#endif
     c.prob.nf = c.nf;
     c.n_owned = c.n_global = S.dim == 3 ? S.m3.n_owned : S.m2.n_owned;
     c.dt = dt;
@@ -297,7 +306,7 @@ extern "C" int emul_newton_step(int mesh_kind, int problem, const int* ncell, co
     c.R = alloc(vs); c.B = alloc(vs); c.DX = alloc(vs); c.DX2 = alloc(vs); c.W1 = alloc(vs); c.W2 = alloc(vs);
     c.V = alloc((size_t)vs * (c.cfg.krylov_basis + 1));
     for (int i = 0; i < 5; ++i) c.S[i] = alloc(c.n_owned + 32);
-    if (c.dim == 2 && (problem == PFH_PROBLEM_BENCH2 || problem == PFH_PROBLEM_BENCH3))
+    if (c.dim == 2 && (problem == PFH_PROBLEM_BENCH2 || problem == PFH_PROBLEM_BENCH3 || problem == PFH_PROBLEM_USER))
       for (int i = 0; i < 4; ++i) c.SIG[i] = alloc(c.n_owned + 32);
     pfh_solve_report rep;
     s_newton(&c, w, w0, opts, &rep);

@@ -244,3 +244,25 @@ def test_reduced_ostwald_models(num_eta):
     rng = np.random.default_rng(8)
     U_, U0_, X_ = (0.5 + 0.3 * rng.standard_normal((nf, om.nv)) for _ in range(3))
     _compare(m, hdr, D, nf, 2, ncell, length, U_, U0_, X_, 0.01)
+
+
+def test_generated_model_newton_step_on_the_cpu(model):
+    """The whole Newton-Krylov step of the generated Flory-Huggins model through the product's host solver (CPU leg,
+    tests/emul/emul_solver.cpp, with the model's own preconditioner layout from the emitted pc_layout) against the
+    oracle's Newton/LU step -- the CPU counterpart of tests/test_gpu_codegen.py."""
+    m, hdr = model
+    ncell, length = (10, 8), (20.0, 16.0)
+    om = omesh.crossed2d(*ncell, *length)
+    D = stepper.Discretization(om, OracleModel())
+    ic = cm.InitialConditions(degree=2)
+    u0 = np.zeros((om.nv, 3))
+    for i in range(om.nv):
+        ic.eval(u0[i], om.coords[i])
+    u0 = np.ascontiguousarray(u0.T)
+    w, rep = emul.newton_step(2, 100, ncell, length, [], 0.05, u0, u0, basis_precision=1, user_header=hdr, absolute_tolerance=1e-10,
+                              krylov_rtol=1e-10, maximum_iterations=30, krylov_maximum_iterations=5000)
+    assert rep["converged"] == 1, rep
+    u, n, ok = D.solve_step(u0, u0, 0.05, atol=1e-11)
+    assert ok and max(np.linalg.norm(w[f] - u[f]) / np.linalg.norm(u[f]) for f in (0, 2)) < 1e-8
+    w2, rep2 = emul.newton_step(2, 100, ncell, length, [], 0.05, u0, u0, user_header=hdr)        # default tolerances, fp32 basis
+    assert rep2["converged"] == 1 and np.linalg.norm(w2[0] - u[0]) / np.linalg.norm(u[0]) < 1e-6
