@@ -185,6 +185,8 @@ def run_b200(args):
     if world > 1 and os.environ.get("PFH_OVERLAP", "1") == "0":
         ctx.set_option("overlap", 0)
     ctx.set_option("basis_precision", {"auto": 0, "fp64": 1, "fp32": 2}[args.basis])
+    if args.jac_fp32:
+        ctx.set_option("jac_quadrature_fp32", 1)
     opts = _lib.default_opts(krylov_restart=args.restart, pc_variant=args.pc_variant, pc_sweeps_mass=args.sweeps_mass,
                              pc_sweeps_shifted=args.sweeps_shifted, krylov_maximum_iterations=max(1000, int(n ** 3 / 10)) if args.workload == "b13d" else 1000,
                              line_search=1 if args.workload in ("bench2", "bench6") else 0)
@@ -356,6 +358,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--basis", default="auto", choices=["auto", "fp64", "fp32"],
                     help="Krylov basis storage (auto: fp32 at the default linear tolerance, DESIGN.md section 5)")
+    ap.add_argument("--jac-fp32", action="store_true",
+                    help="experimental: quadrature block of the Krylov J.v in single precision (DESIGN.md section 9, not the default)")
     args = ap.parse_args()
     if args.warmup < 3:
         print("warning: timing rules ask for >= 3 warm-up steps", file=sys.stderr)

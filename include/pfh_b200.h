@@ -162,7 +162,8 @@ long long pfh_launch_count(const pfh_ctx* ctx);
  * "use_first2" 0/1 first two Chebyshev iterates in one pass (default 1); "use_fused" 0/1 temporally blocked sweeps
  * (default 0, slower); "scalar_variant" tile-shape variants of the 3-D scalar kernel (tuning); "basis_precision" storage
  * of the GMRES basis: 0 = fp32 when krylov_rtol >= 1e-6 else fp64 (default), 1 = fp64, 2 = fp32 (arithmetic is fp64
- * in all cases).  Unknown keys are an error. */
+ * in all cases); "jac_quadrature_fp32" 0/1 (default 0): the quadrature block of the Krylov J.v of the 3-D fast path in
+ * single precision (Newton's residual stays fp64).  Unknown keys are an error. */
 int pfh_set_option(pfh_ctx* ctx, const char* key, double value);
 #define PFH_N_TIMERS 16
 int pfh_timers(pfh_ctx* ctx, double ms[PFH_N_TIMERS], long long launches[PFH_N_TIMERS],

@@ -431,6 +431,8 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
   } else if (k == "basis_precision") {
     PFH_CHECK(value == 0.0 || value == 1.0 || value == 2.0, "basis_precision: 0 auto, 1 fp64, 2 fp32");
     c->basis_precision = (int)value;
+  } else if (k == "jac_quadrature_fp32") {
+    c->jac_quadrature_fp32 = value != 0.0;
   } else if (k == "use_first2") {
     c->use_first2 = value != 0.0;
   } else if (k == "use_tma") {

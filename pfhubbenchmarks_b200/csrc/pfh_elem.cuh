@@ -111,6 +111,40 @@ PFH_HD void cube_jac_quartic(const QuarticJac& k, const double (&c)[8], const do
   }
 }
 
+// The same block with single-precision arithmetic (operands and accumulation in float, result widened): the Krylov
+// J.v tolerates it -- iteration counts of the Newton-Krylov solve are unchanged (tests/probe/README.md) -- and it takes
+// the ~230 operations per cube off the fp64 pipe.  Opt-in (pfh_set_option "jac_quadrature_fp32"); Newton's residual
+// always uses the fp64 routines.
+PFH_HD void cube_jac_quartic_f32(const QuarticJac& k, const double (&c)[8], const double (&x)[8], double (&out)[8]) {
+  const float Q2 = (float)k.Q2, Q1 = (float)k.Q1, Q0 = (float)k.Q0, R2 = (float)k.R2, R1 = (float)k.R1, R0 = (float)k.R0;
+  float cf[8], xf[8], of[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    cf[i] = (float)c[i];
+    xf[i] = (float)x[i];
+    of[i] = 0.0f;
+  }
+  const float c07 = cf[0] + cf[7], x07 = xf[0] + xf[7];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    const int p = kuhn_mid(t, 0), q = kuhn_mid(t, 1);
+    const float s = c07 + cf[p] + cf[q], sx = x07 + xf[p] + xf[q];
+    const int v[4] = {0, 7, p, q};
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float tc = 2.0f * cf[v[j]] + s, tx = 2.0f * xf[v[j]] + sx;
+      h[j] = ((Q2 * tc + Q1) * tc + Q0) * tx;
+    }
+    const float S = (h[0] + h[1]) + (h[2] + h[3]);
+    const float base = 0.5f * S + ((R2 * s + R1) * s + R0) * sx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) of[v[j]] += base + h[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] += (double)of[i];
+}
+
 // Residual counterpart: load of a cubic g(c) = a3 c^3 + a2 c^2 + a1 c + a0 (= -f'(c) of the double well) over one cube,
 // with the same folding: corner k gets Q(s + 2 c_k) + 1/2 sum_j Q(s + 2 c_j) + R(s).
 struct QuarticRes {

@@ -190,6 +190,9 @@ struct pfh_ctx {
   // bound and 1.45x slower per solve than the per-sweep TMA kernel at 512^3 (profiles/README.md), so opt-in only
   bool use_fused = false;
   std::vector<double> h_mT3, h_kT3;  // host copies of the 3-D type tables (inverse diagonals for k_cheb_first2)
+  // Krylov J.v of the 3-D TMA path: quadrature block in single precision (elem::cube_jac_quartic_f32).  Opt-in: validated
+  // numerically on the CPU solver leg, not yet measured on hardware.
+  bool jac_quadrature_fp32 = false;
   bool use_first2 = true;  // 3-D: first two Chebyshev iterates in one pass over r (k_cheb_first2)
   int basis_precision = 0;  // Krylov basis storage: 0 = fp32 when krylov_rtol >= 1e-6 else fp64, 1 = fp64, 2 = fp32
   bool use_tma = true;  // 3-D fast path: TMA-staged kernels (pfh_stencil3_tma.cu); false = gather kernels only

@@ -227,7 +227,8 @@ struct MapSet {
 //         o = P::out(0), i = P::in(0) (the (kappa K + M_f'') block of the Cahn-Hilliard Jacobian for the Schur preconditioner).
 // KIND 2: residual R(u; u0): the operand fields are u, the extra ring fields hold u0 of the fields in(.) (for the
 //         problems served here the fields with a time derivative are the nonlinear inputs: c for Cahn-Hilliard).
-template <class P, int KIND, int TX, int TY, int NT, int NS>
+// F32Q (KIND 0 of a QUARTIC problem only): the quadrature block in single precision (elem::cube_jac_quartic_f32)
+template <class P, int KIND, int TX, int TY, int NT, int NS, bool F32Q = false>
 __global__ void __launch_bounds__(NT, 2)
     k3_jac_tma(const __grid_constant__ MapSet<(KIND == 1 ? 1 : P::NF) + P::NIN> maps, P prob, Mesh3 m, LinCoefs L, int has_lo,
                int has_hi, int zchunk, double* __restrict__ out) {
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(NT, 2)
         }
         if constexpr (P::QUARTIC) {
           if (RES) elem::cube_res_quartic(qr, u[0], o8[0]);
+          else if (F32Q) elem::cube_jac_quartic_f32(qj, u[0], x[0], o8[0]);
           else elem::cube_jac_quartic(qj, u[0], x[0], o8[0]);
         } else {
           if (RES) elem::cube_load<P, false>(prob, u, x, m.detJ, o8);
@@ -549,13 +551,16 @@ bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const 
   constexpr int ncube = (J_TX + 1) * (J_TY + 1);
   constexpr size_t smem = (size_t)(P::NF + P::NIN) * J_NS * stage + (size_t)P::NOUT * 8 * (ncube | 1) * 8 + J_NS * sizeof(uint64_t);
   auto kern = k3_jac_tma<P, 0, J_TX, J_TY, J_NT, J_NS>;
+  auto kern32 = k3_jac_tma<P, 0, J_TX, J_TY, J_NT, J_NS, true>;
   static bool attr_set = false;
   if (!attr_set) {
     PFH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFH_CUDA(cudaFuncSetAttribute(kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const dim3 grid((m.nxv + J_TX - 1) / J_TX, (m.nyv + J_TY - 1) / J_TY, (m.nzl + J_ZCH - 1) / J_ZCH);
-  kern<<<grid, J_NT, smem, c->stream>>>(maps, P(c->prob), m, L, lo, hi, J_ZCH, y);
+  if (c->jac_quadrature_fp32) kern32<<<grid, J_NT, smem, c->stream>>>(maps, P(c->prob), m, L, lo, hi, J_ZCH, y);
+  else kern<<<grid, J_NT, smem, c->stream>>>(maps, P(c->prob), m, L, lo, hi, J_ZCH, y);
   PFH_CUDA(cudaGetLastError());
   return true;
 }

@@ -38,7 +38,8 @@ def _p(a):
 def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=None, icp=None, nf=2,
         z0=0, nzl=-1, glo=None, ghi=None, user_header=None):
     """mode: 0 residual, 1 jac_apply, 2 energy -> [E, M], 3 scalar op -> [Av, diag], 4 initial condition,
-    5 nonlinear Jacobian block via the low-flop cube routine (3-D quartic problems)."""
+    5 nonlinear Jacobian block via the low-flop cube routine (3-D quartic problems), 6 its residual counterpart,
+    7 the single-precision variant of 5."""
     lib = ctypes.CDLL(build(user_header))
     nc = (ctypes.c_int * 3)(*(list(ncell) + [1] * (3 - len(ncell))))
     ln = (ctypes.c_double * 3)(*(list(length) + [1.0] * (3 - len(length))))
@@ -49,7 +50,7 @@ def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=
     else:
         n = (ncell[0] + 1) * (ncell[1] + 1) + ncell[0] * ncell[1]
     arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (U, X, U0, glo, ghi)]
-    out = np.zeros({0: nf * n, 1: nf * n, 2: 2, 3: 2 * n, 4: nf * n, 5: n, 6: n}[mode])
+    out = np.zeros({0: nf * n, 1: nf * n, 2: 2, 3: 2 * n, 4: nf * n, 5: n, 6: n, 7: n}[mode])
     icp = np.ascontiguousarray(icp if icp is not None else [0.0], dtype=np.float64)
     rc = lib.emul_run(mesh_kind, problem, nc, ln, _p(pr), len(pr), ctypes.c_double(dt), mode, z0, nzl,
                       _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(out), _p(icp))
@@ -58,7 +59,7 @@ def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=
         return out.reshape(nf, n)
     if mode == 3:
         return out.reshape(2, n)
-    if mode in (5, 6):
+    if mode in (5, 6, 7):
         return out
     return out
 

@@ -103,7 +103,7 @@ int run(const Setup& S, const ProblemParams& pp, double dt, int mode, const doub
               for (int l = 0; l < 8; ++l) out[idx[l]] += o8[l];
             }
       }
-      if (mode == 5) {  // nonlinear Jacobian block only, cube-centric scatter with the low-flop routine
+      if (mode == 5 || mode == 7) {  // nonlinear Jacobian block only, cube-centric scatter with the low-flop routine (7: its fp32 variant)
         double a2, a1, a0;
         prob.jac_poly(a2, a1, a0);
         const elem::QuarticJac qj(a2, a1, a0, m.detJ);
@@ -119,7 +119,8 @@ int run(const Setup& S, const ProblemParams& pp, double dt, int mode, const doub
                 idx[l] = (long long)(cz + (l >> 2)) * m.nxy + (long long)(cy + ((l >> 1) & 1)) * m.nxv + cxi + (l & 1);
                 c8[l] = cu[idx[l]]; x8[l] = cx[idx[l]];
               }
-              elem::cube_jac_quartic(qj, c8, x8, o8);
+              if (mode == 7) elem::cube_jac_quartic_f32(qj, c8, x8, o8);
+              else elem::cube_jac_quartic(qj, c8, x8, o8);
               for (int l = 0; l < 8; ++l) out[idx[l]] += o8[l];
             }
       }

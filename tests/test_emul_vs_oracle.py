@@ -96,6 +96,9 @@ def test_low_flop_cube_jacobian_routine():
     dg = D.prob.dg(D.V.at_quad(U))
     ref = D.V.weighted_mass(dg[1, 0]) @ X[0]
     assert rel_max(got, ref) < 1e-13
+    # the opt-in single-precision variant (Krylov J.v only): fp32 accuracy, no worse
+    got32 = emul.run(3, 1, list(ncell), list(length), [0.3, 0.7, 5.0, 2.0, 5.0], 0.1, 7, U=U, X=X, nf=2)
+    assert 1e-9 < rel_max(got32, ref) < 5e-6
 
 
 def test_low_flop_cube_residual_routine():
