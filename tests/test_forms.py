@@ -221,24 +221,43 @@ def test_namespace_covers_the_reference_drivers():
 
 def test_module_level_script_runs_through_the_aliases(monkeypatch, tmp_path):
     """run_script: a reference-style module-level program (`import dolfin as df`, `from pfbase import *`, HDF5File,
-    `c, _ = w.split()` re-used inside assemble) executes unchanged up to the first GPU call (context stubbed here; the
-    GPU test runs it for real)."""
+    `c, _ = w.split()` re-used inside assemble, inline adaptive loop) executes unchanged.  The GPU context is replaced by
+    a stand-in holding CPU tensors, so that everything around the C ABI calls runs here (the GPU suite runs it for real)."""
     import os
-    from pfhubbenchmarks_b200 import run_script
-    created = []
-
-    class Stop(Exception):
-        pass
+    import torch
+    from pfhubbenchmarks_b200 import io, run_script
+    log = []
 
     class StubContext:
+        nranks = 1
+
         def __init__(self, problem, ncell, length, **kw):
-            created.append((problem, tuple(ncell), kw["params"]))
-            raise Stop
+            log.append(("ctx", problem, tuple(ncell), kw["params"]))
+            self.nf, self.params, self.dt = 2, kw["params"], None
+            self.n_owned = (ncell[0] + 1) * (ncell[1] + 1) + ncell[0] * ncell[1]
+
+        def new_vector(self):
+            return torch.zeros(self.nf * self.n_owned, dtype=torch.float64)
+
+        def fields(self, w):
+            return [w[i * self.n_owned:(i + 1) * self.n_owned] for i in range(self.nf)]
+
+        def initial_condition(self, args, out=None):
+            out[:self.n_owned] = args[0]
+            log.append(("ic", list(args)))
+
+        def newton_solve(self, w, w0, opts=None):
+            w[:self.n_owned] += self.dt                      # something that depends on dt, to see the loop's dt sequence
+            log.append(("solve", self.dt, opts.line_search, opts.absolute_tolerance))
+            return dict(niters=2, converged=1, reason=2)
+
+        def energy(self, w):
+            return float(w[0]) * 10.0, float(w[0])
 
     monkeypatch.setattr(engine, "Context", StubContext)
     saved = {k: sys.modules.get(k) for k in ("dolfin", "pfbase", "matplotlib", "matplotlib.pyplot")}
     try:
-        with pytest.raises(Stop):
+        with pytest.warns(UserWarning, match="HDF5 is not available"):
             run_script.run(os.path.join(os.path.dirname(__file__), "scripts", "spinodal_module_level.py"), [str(tmp_path)])
     finally:
         for k, v in saved.items():
@@ -246,7 +265,13 @@ def test_module_level_script_runs_through_the_aliases(monkeypatch, tmp_path):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
-    assert created == [("bench1", (24, 24), [0.3, 0.7, 5.0, 2.0, 5.0])]
+    assert log[0] == ("ctx", "bench1", (24, 24), [0.3, 0.7, 5.0, 2.0, 5.0])
+    solves = [e for e in log if e[0] == "solve"]
+    assert [e[1] for e in solves] == pytest.approx([0.1, 0.2, 0.4]) and all(e[2] == 0 and e[3] == 1e-6 for e in solves)
+    rows = np.loadtxt(str(tmp_path / "stats.csv"), delimiter=",", skiprows=1)
+    assert np.allclose(rows[:, 0], [0.1, 0.3, 0.7]) and np.allclose(rows[:, 2], [0.6, 0.8, 1.2]) and np.allclose(rows[:, 1], 10 * rows[:, 2])
+    times, vals = io.read_series(str(tmp_path / "conc.pvd"))                   # what the HDF5File stand-in wrote
+    assert np.allclose(times, [0.1, 0.3, 0.7]) and vals.shape == (3, 25 * 25 + 24 * 24) and np.allclose(vals[:, 0], [0.6, 0.8, 1.2])
 
 
 def test_reassigned_coefficient_is_refused(monkeypatch):
