@@ -314,3 +314,68 @@ def test_vertex_coordinates_follow_the_dolfin_order():
     assert np.allclose(engine.Context.vertex_coordinates(ctx), full, atol=1e-14)
     ctx.z_range = (2, 4)
     assert np.allclose(engine.Context.vertex_coordinates(ctx), full[2 * 20:4 * 20], atol=1e-14)
+
+
+class _TensorStubContext:
+    """Stand-in for engine.Context holding CPU tensors: lets the Python side of a driver (model setup, recognition, time
+    loop, df.assemble plans, CSV / VTU output) run without a GPU.  Numbers are fake; the calls are recorded."""
+    nranks = 1
+    calls = []
+
+    def __init__(self, problem, ncell, length, **kw):
+        import torch
+        self._torch = torch
+        self.problem = problem
+        self.nf = engine.PROBLEMS[problem][1]
+        self.field_names = engine.PROBLEMS[problem][4]
+        self.params, self.dt = list(kw["params"]), None
+        if problem == "bench3" and self.params[4] is None:        # as engine.Context: the area the solid fraction divides by
+            self.params[4] = float(length[0] * length[1])
+        n = 1
+        for c in ncell:
+            n *= c + 1
+        self.n_owned = n + (ncell[0] * ncell[1] if len(ncell) == 2 else 0)
+        type(self).calls.append(("ctx", problem, tuple(ncell)))
+
+    def new_vector(self):
+        return self._torch.zeros(self.nf * self.n_owned, dtype=self._torch.float64)
+
+    def fields(self, w):
+        return [w[i * self.n_owned:(i + 1) * self.n_owned] for i in range(self.nf)]
+
+    def initial_condition(self, args, out=None):
+        out[:] = 1.0
+
+    def newton_solve(self, w, w0, opts=None):
+        w -= 0.01 * self.dt
+        type(self).calls.append(("solve", self.dt, opts.line_search))
+        return dict(niters=3, converged=1, reason=2)
+
+    def energy(self, w):
+        return 100.0 * float(w[0]), 7.0
+
+    def bilinear(self, w, a, b, am, ak):
+        type(self).calls.append(("bilinear", a, b, am, ak))
+        return 0.5
+
+
+@pytest.mark.parametrize("name,csv,ls,nbil", [("bench1", "bench1/stats.csv", 0, 0), ("bench2", "bench2_out.csv", 1, 8), ("bench3", "bench3_out.csv", 0, 0),
+                                              ("bench6", "bench6_out.csv", 1, 0), ("b13d", "bench1_out.csv", 0, 0)])
+def test_driver_mains_run_on_a_stub_context(monkeypatch, tmp_path, name, csv, ls, nbil):
+    """Every shipped driver's main() end to end on the stand-in context: the model is recognised, the solver gets the
+    driver's line search, the driver's own df.assemble functionals are planned (bench2's energy in five pieces: the four
+    order-parameter pieces go through pfh_bilinear_dev once as corrections and once on their own), the CSV is written."""
+    _TensorStubContext.calls = []
+    monkeypatch.setattr(engine, "Context", _TensorStubContext)
+    argv = [name, "--max-steps", "2", "--quiet", "--outdir", str(tmp_path)] + (["--n", "6"] if name == "b13d" else [])
+    monkeypatch.setattr(sys, "argv", argv)
+    rows, spent = importlib.import_module("pfhubbenchmarks_b200.drivers." + name).main()
+    calls = _TensorStubContext.calls
+    assert calls[0][:2] == ("ctx", name)
+    solves = [c for c in calls if c[0] == "solve"]
+    assert len(solves) == 2 and all(c[2] == ls for c in solves)
+    assert len([c for c in calls if c[0] == "bilinear"]) == nbil * 2
+    back = np.loadtxt(str(tmp_path / csv), delimiter=",", skiprows=1)
+    assert back.shape == (2, 3) and np.allclose(back, np.array(rows), atol=1e-9)
+    if name == "bench3":
+        assert np.allclose(back[:, 2], 7.0)                  # solid fraction: assemble(...) / (Lx Ly) undoes the area factor
