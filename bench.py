@@ -28,10 +28,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 must print exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its version line on stdout for VERSION/WARN/INFO
-if os.environ.get("PFH_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = os.environ["PFH_NCCL_DEBUG"]
+# NCCL_DEBUG is left as the launcher set it (the harness reads the rank count from NCCL's own log); whatever NCCL prints
+# on stdout comes first, the JSON line is the LAST line rank 0 prints.
 
 METRIC = "CH DOF*Newton-steps/s (b13d 3-D Cahn-Hilliard, implicit step)"
 UNIT = "DOF*Newton-steps/s"
@@ -94,7 +92,7 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on a bounded sample of the same workload
 # ------------------------------------------------------------------------------------------------
-def oracle_steps(sample_grid, n_steps, skip=0):
+def oracle_steps(sample_grid, n_steps, skip=0, n_m=3, n_a=4):
     """Run backward-Euler steps of the oracle (assemble + Newton + preconditioned GMRES, reference solver
     tolerances) on a Kuhn grid with `sample_grid` vertices per edge. Returns (dof, newton_its list, seconds list)."""
     import numpy as np
@@ -108,7 +106,7 @@ def oracle_steps(sample_grid, n_steps, skip=0):
     for k, dt in enumerate(dt_schedule(skip + n_steps)):
         t0 = time.perf_counter()
         u, nit, ok = D.solve_step(u, u, dt, atol=1e-6, rtol=1e-9, max_it=10,
-                                  linear=krylov.make_linear(rtol=1e-5, n_m=3, n_a=6))
+                                  linear=krylov.make_linear(rtol=1e-5, n_m=n_m, n_a=n_a, variant="upper", symbol_lmax=True))
         E, C = D.energy(u), D.mass(u)
         t1 = time.perf_counter()
         assert ok and np.isfinite(E) and np.isfinite(C)
@@ -117,53 +115,73 @@ def oracle_steps(sample_grid, n_steps, skip=0):
     return 2 * m.nv, its, secs
 
 
-def cpu_baseline(sample_grid=40, n_steps=2):
-    dof, its, secs = oracle_steps(sample_grid, n_steps)
-    return {"value": dof * sum(its) / sum(secs), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "oracle port (numpy/scipy: assembled P1 operators, Newton, Schur-Chebyshev GMRES), %d^3-vertex "
-                      "Kuhn grid, first %d steps of the dt list, single thread" % (sample_grid, n_steps)}
+def _oracle_worker(job):
+    """One replica of the CPU arm (runs in its own process, pinned to nothing: the OS spreads the replicas over the cores)."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    grid, n_steps, skip, n_m, n_a = job
+    dof, its, secs = oracle_steps(grid, n_steps, skip, n_m, n_a)
+    return dof, its, secs
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def oracle_all_cores(sample_grid, n_steps, skip=0, n_m=3, n_a=4, cores=None):
+    """The CPU arm on all host cores: the oracle's solver is a single-threaded scipy code (as one FEniCS/PETSc rank is),
+    so one replica per core runs the same sample concurrently -- the analogue of `mpirun -np <cores>` for a code with no
+    MPI here.  Returns (aggregate DOF*Newton-steps/s, cores, mean seconds per step of a replica, newton its of a replica)."""
+    import multiprocessing as mp
+    cores = cores or host_cores()
+    if cores == 1:
+        res = [_oracle_worker((sample_grid, n_steps, skip, n_m, n_a))]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_oracle_worker, [(sample_grid, n_steps, skip, n_m, n_a)] * cores)
+    value = sum(dof * sum(its) / sum(secs) for dof, its, secs in res)
+    step_s = sum(sum(secs) for _, _, secs in res) / (len(res) * n_steps)
+    return value, cores, step_s, sum(res[0][1])
+
+
+def cpu_baseline(sample_grid=48, n_steps=2, n_m=3, n_a=4):
+    value, cores, step_s, _ = oracle_all_cores(sample_grid, n_steps, 0, n_m, n_a)
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port (numpy/scipy: assembled P1 operators, Newton, Schur-Chebyshev(%d,%d) GMRES, the product's algorithm), "
+                      "%d^3-vertex Kuhn grid, first %d steps of the dt list, one single-threaded replica per host core (%d), "
+                      "aggregate throughput" % (n_m, n_a, sample_grid, n_steps, cores)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    dof, its, secs = oracle_steps(args.ref_grid, args.steps, skip=args.warmup)
-    total = sum(secs)
-    val = dof * sum(its) / total
+    value, cores, step_s, _ = oracle_all_cores(args.ref_grid, args.steps, args.warmup, args.sweeps_mass, args.sweeps_shifted)
     sample = ("oracle port (numpy/scipy restatement; FEniCS/PETSc not installable here), %d^3-vertex Kuhn grid sample of the "
-              "b13d workload, steps %d..%d of the dt list, single thread" % (args.ref_grid, args.warmup, args.warmup + args.steps - 1))
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+              "b13d workload, steps %d..%d of the dt list, one single-threaded replica per host core (%d), aggregate throughput"
+              % (args.ref_grid, args.warmup, args.warmup + args.steps - 1, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "b13d_kuhn3d_%d" % args.grid, "sample_grid": args.ref_grid, "fields": "c,mu"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
+def bench_case(args, workload, grid, steps, warmup, dist_env, e2e=True, fp64_pass=False):
+    """W warm-up + K timed steps of one workload on its own ctx; returns the measured quantities of this rank's view
+    (times already reduced to the maximum over ranks)."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from pfhubbenchmarks_b200 import _lib, engine
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, "launch with torchrun --nproc-per-node N for --gpus N"
-    torch.cuda.set_device(local)
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        buf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(engine.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
+    rank, world, local, nccl_id = dist_env
 
     def barrier():
         torch.cuda.synchronize()
@@ -171,34 +189,36 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = args.grid - 1
-    L = 2.0 * n
-    if args.workload != "b13d":       # 2-D crossed mesh with `grid` cells per edge (reference: 100 / 350), replicas only
+    if workload != "b13d":       # 2-D crossed mesh with `grid` cells per edge (reference: 100 / 350), replicas only
         assert world == 1, "2-D cases do not shard (DESIGN.md section 6)"
-        n = args.grid
-        h = {"bench1": 2.0, "bench2": 2.0, "bench3": 960.0 / 350.0, "bench6": 1.0}[args.workload]   # reference cell sizes
-        ctx = engine.Context(args.workload, (n, n), (h * n, h * n), device=local, krylov_basis=args.restart)
+        n = grid
+        h = {"bench1": 2.0, "bench2": 2.0, "bench3": 960.0 / 350.0, "bench6": 1.0}[workload]   # reference cell sizes
+        ctx = engine.Context(workload, (n, n), (h * n, h * n), device=local, krylov_basis=args.restart)
     else:
+        n = grid - 1
+        L = 2.0 * n
         ctx = engine.Context("b13d", (n, n, n), (L, L, L), device=local, rank=rank, nranks=world, nccl_id=nccl_id,
                              krylov_basis=args.restart)
     dof = ctx.nf * ctx.n_global
-    if world > 1 and os.environ.get("PFH_OVERLAP", "1") == "0":
-        ctx.set_option("overlap", 0)
+    if world > 1 and os.environ.get("PFH_WIDE", "1") == "0":
+        ctx.set_option("use_wide", 0)
+    for kv in args.option:
+        k, v = kv.split("=")
+        ctx.set_option(k, float(v))
     ctx.set_option("basis_precision", {"auto": 0, "fp64": 1, "fp32": 2}[args.basis])
     if args.jac_fp32:
         ctx.set_option("jac_quadrature_fp32", 1)
     opts = _lib.default_opts(krylov_restart=args.restart, pc_variant=args.pc_variant, pc_sweeps_mass=args.sweeps_mass,
-                             pc_sweeps_shifted=args.sweeps_shifted, krylov_maximum_iterations=max(1000, int(n ** 3 / 10)) if args.workload == "b13d" else 1000,
-                             line_search=1 if args.workload in ("bench2", "bench6") else 0)
+                             pc_sweeps_shifted=args.sweeps_shifted, krylov_maximum_iterations=max(1000, int(n ** 3 / 10)) if workload == "b13d" else 1000,
+                             line_search=1 if workload in ("bench2", "bench6") else 0)
     stream = torch.cuda.ExternalStream(ctx.lib.pfh_stream(ctx._h), device=torch.device("cuda", local))
-    dts = dt_schedule(args.warmup + args.steps)
-    if args.workload in ("bench2", "bench3", "bench6"):      # these drivers start at dt = 1e-2 (bench2.py:222)
+    dts = dt_schedule(warmup + steps)
+    if workload in ("bench2", "bench3", "bench6"):      # these drivers start at dt = 1e-2 (bench2.py:222)
         # capped at 0.08: the reference's own run rejects dt = 0.16 at t = 0.15 for bench2 (results/bench2_out.csv rows 4-5)
-        dts = [min(0.01 * 2 ** k, 0.08) for k in range(args.warmup + args.steps)]
+        dts = [min(0.01 * 2 ** k, 0.08) for k in range(warmup + steps)]
 
     w = ctx.initial_condition()
     w0 = torch.empty_like(w)
-    reports = []
 
     def one_step(dt):
         w0.copy_(w)                      # w0.assign(w)       (b13d.py:146)
@@ -208,7 +228,7 @@ def run_b200(args):
         rep["energy"], rep["solute"] = E, C
         return rep
 
-    for k in range(args.warmup):
+    for k in range(warmup):
         rep = one_step(dts[k])
         assert rep["converged"], rep
     # state at the start of the timed region, kept on the host for the e2e pass
@@ -233,8 +253,8 @@ def run_b200(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for k in range(args.steps):
-            reps.append(one_step(dts[args.warmup + k]))
+        for k in range(steps):
+            reps.append(one_step(dts[warmup + k]))
         e1.record(stream)
         barrier()
         t_ms = e0.elapsed_time(e1)
@@ -242,34 +262,6 @@ def run_b200(args):
         tm = ctx.timers(reset=True)
         ctx.set_option("profiling", 0)
         return t_ms, n_launch, tm, reps
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    ms, launches, timers, reports = timed_pass(profile_in_timed)
-    clocks = sampler.finish()
-    if not profile_in_timed:
-        ms_prof, _, timers, _ = timed_pass(True)
-    else:
-        ms_prof = ms
-    assert all(r["converged"] for r in reports), reports
-    newton = sum(r["niters"] for r in reports)
-    krylov = sum(r["krylov_its"] for r in reports)
-
-    # ---- e2e: the same K steps through the host-buffer plugin call ----
-    h_w = start_host.numpy()
-    h_w0 = torch.empty(w.shape, dtype=w.dtype, pin_memory=True).numpy()
-    e2e_ms, e2e_newton = 0.0, 0
-    for k in range(args.steps):
-        np.copyto(h_w0, h_w)             # w0.assign(w) on the host, outside the timed call
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        rep = ctx.step_host(h_w, h_w0, dts[args.warmup + k], opts=opts)
-        b.record(stream)
-        barrier()
-        e2e_ms += a.elapsed_time(b)
-        e2e_newton += rep["niters"]
-        assert rep["converged"], rep
 
     def allmax(x):
         if world == 1:
@@ -285,57 +277,160 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ms = allmax(ms)
-    e2e_ms = allmax(e2e_ms)
-    launches_all = int(allsum(launches))
-    value = dof * newton / (ms * 1e-3)
-    e2e_value = dof * e2e_newton / (e2e_ms * 1e-3)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches, timers, reports = timed_pass(profile_in_timed)
+    clocks = sampler.finish()
+    if not profile_in_timed:
+        ms_prof, _, timers, _ = timed_pass(True)
+    else:
+        ms_prof = ms
+    assert all(r["converged"] for r in reports), reports
+    out = {"dof": dof, "nf": ctx.nf, "fields": ",".join(ctx.field_names), "bytes_vec": bytes_vec, "dts": dts[warmup:],
+           "newton": sum(r["niters"] for r in reports), "krylov": sum(r["krylov_its"] for r in reports),
+           "energy": reports[-1]["energy"], "solute": reports[-1]["solute"], "ms": allmax(ms), "ms_prof": ms_prof,
+           "launches": int(allsum(launches)), "timers": timers, "clocks": clocks, "profile_in_timed": bool(profile_in_timed)}
 
-    peak, peak_src = measured_peak()
-    fam = {k: v for k, v in timers.items() if v["launches"] > 0}
-    total_fam_ms = sum(v["ms"] for v in fam.values())
+    # ---- the same K steps with every vector stored in fp64 (the Krylov basis included) ----
+    if fp64_pass and args.basis != "fp64":
+        ctx.set_option("basis_precision", 1)
+        ms64, _, _, reps64 = timed_pass(False)
+        ctx.set_option("basis_precision", {"auto": 0, "fp64": 1, "fp32": 2}[args.basis])
+        assert all(r["converged"] for r in reps64), reps64
+        out["fp64"] = {"ms": allmax(ms64), "newton": sum(r["niters"] for r in reps64), "krylov": sum(r["krylov_its"] for r in reps64),
+                       "energy": reps64[-1]["energy"]}
+
+    # ---- e2e: the same K steps through the host-buffer plugin call ----
+    if e2e:
+        w.copy_(start_host)
+        h_w = start_host.numpy()
+        h_w0 = torch.empty(w.shape, dtype=w.dtype, pin_memory=True).numpy()
+        e2e_ms, e2e_newton = 0.0, 0
+        for k in range(steps):
+            np.copyto(h_w0, h_w)             # w0.assign(w) on the host, outside the timed call
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            rep = ctx.step_host(h_w, h_w0, dts[warmup + k], opts=opts)
+            b.record(stream)
+            barrier()
+            e2e_ms += a.elapsed_time(b)
+            e2e_newton += rep["niters"]
+            assert rep["converged"], rep
+        out["e2e_ms"], out["e2e_newton"] = allmax(e2e_ms), e2e_newton
+    ctx.close()
+    del w, w0
+    torch.cuda.empty_cache()
+    return out
+
+
+def kernel_table(res):
+    fam = {k: v for k, v in res["timers"].items() if v["launches"] > 0}
+    total = sum(v["ms"] for v in fam.values())
     ours = {k: v for k, v in fam.items() if k not in ("halo", "allreduce", "copy")}
     dom = max(ours, key=lambda k: ours[k]["ms"])
-    d = ours[dom]
+    kernels = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                   "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                   "share": round(v["ms"] / res["ms_prof"], 4)} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    return dom, ours[dom], kernels, total / res["ms_prof"]
+
+
+def workload_name(workload, grid):
+    return ("b13d_kuhn3d_%d" % grid) if workload == "b13d" else "%s_crossed2d_%d" % (workload, grid)
+
+
+def roofline_of(res, name, world):
+    peak, peak_src = measured_peak()
+    dom, d, kernels, cover = kernel_table(res)
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         try:
-            traffic = json.load(open(tpath)).get(("b13d_kuhn3d_%d" if args.workload == "b13d" else args.workload + "_crossed2d_%d") % args.grid, {}).get(dom) if world == 1 else None
+            traffic = json.load(open(tpath)).get(name, {}).get(dom)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": d["bytes"] / d["launches"],
-                "ms_per_launch": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms_prof,
-                "timed_region_profiled": bool(profile_in_timed)}
-    kernels = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
-                   "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
-                   "share": round(v["ms"] / ms_prof, 4)} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    # whole-step figure: algorithmic bytes of every family of the timed region over its wall time
+    tot_bytes = sum(v["bytes"] for k, v in res["timers"].items() if k not in ("halo", "allreduce"))
+    roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": d["bytes"] / d["launches"],
+            "ms_per_launch": d["ms"] / d["launches"], "share_of_step": d["ms"] / res["ms_prof"],
+            "timed_region_profiled": res["profile_in_timed"],
+            "whole_step": {"algorithmic_bytes": tot_bytes, "gbs": tot_bytes / (res["ms_prof"] * 1e-3) / 1e9,
+                           "frac": tot_bytes / (res["ms_prof"] * 1e-3) / 1e9 / peak}}
+    return roof, kernels, cover
 
-    line = None
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pfhubbenchmarks_b200 import _lib, engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node N for --gpus N"
+    # the CPU leg first: its worker processes are spawned before this process holds a CUDA context
+    cpu = cpu_baseline(args.cpu_grid, 2, args.sweeps_mass, args.sweeps_shifted) if (world == 1 and rank == 0 and not args.no_cpu) else None
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().numpy().tobytes())
+    env = (rank, world, local, nccl_id)
+
+    res = bench_case(args, args.workload, args.grid, args.steps, args.warmup, env, e2e=True, fp64_pass=not args.no_fp64_pass)
+    name = workload_name(args.workload, args.grid)
+    dof, ms = res["dof"], res["ms"]
+    value = dof * res["newton"] / (ms * 1e-3)
+    e2e_value = dof * res["e2e_newton"] / (res["e2e_ms"] * 1e-3)
+    roofline, kernels, cover = roofline_of(res, name, world)
+    stored = "fp64" if args.basis == "fp64" else "fp32"
+
+    # ---- the other sizes BASELINE.json's metric names (bench1 2-D), one record each; single GPU only ----
+    extra = []
+    if world == 1 and args.workload == "b13d" and not args.no_configs:
+        for wl, grid in [("bench1", 1024), ("bench1", 4096), ("bench1", 8192)]:
+            r2 = bench_case(args, wl, grid, min(args.steps, 3), 3, env, e2e=False)
+            roof2, kern2, _ = roofline_of(r2, workload_name(wl, grid), 1)
+            extra.append({"workload": workload_name(wl, grid), "dof": r2["dof"], "steps": min(args.steps, 3), "warmup": 3,
+                          "value": r2["dof"] * r2["newton"] / (r2["ms"] * 1e-3), "unit": UNIT, "ms_per_step": r2["ms"] / min(args.steps, 3),
+                          "newton_its": r2["newton"], "krylov_its": r2["krylov"], "energy": r2["energy"], "solute": r2["solute"],
+                          "roofline": {k: roof2[k] for k in ("kernel", "achieved", "peak", "frac", "share_of_step", "whole_step")}})
+
     if rank == 0:
-        cpu = cpu_baseline(args.cpu_grid, 2) if (world == 1 and not args.no_cpu) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": ("b13d_kuhn3d_%d" % args.grid) if args.workload == "b13d" else "%s_crossed2d_%d" % (args.workload, args.grid),
+                "ms_per_step": ms / args.steps,
+                # results of the run first: the N-GPU lines must reproduce the N = 1 values (same grid, same steps)
+                "newton_its": res["newton"], "krylov_its": res["krylov"], "energy": res["energy"], "solute": res["solute"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64 arithmetic; Krylov basis stored %s, everything else fp64" % stored, "data": "synthetic",
+                "config": {"workload": name,
                            "grid_vertices": [args.grid] * 3 if args.workload == "b13d" else [args.grid + 1] * 2, "dof": dof,
-                           "fields": ",".join(ctx.field_names), "dt_list": dts[args.warmup:], "parallelism": "z-slabs x%d" % world,
+                           "fields": res["fields"], "dt_list": res["dts"], "parallelism": "z-slabs x%d" % world,
                            "solver": "newton(atol 1e-6, max 10) + GMRES(%d, rtol 1e-5, basis stored %s) + Schur/Chebyshev(%d,%d,%s)" % (
-                               args.restart, "fp64" if args.basis == "fp64" else "fp32", args.sweeps_mass, args.sweeps_shifted,
-                               "upper" if args.pc_variant else "full"),
-                           "l2_policy": ("inputs_exceed_l2 (every vector is %.0f MB >> 126 MB L2)" % (bytes_vec / 1e6)) if bytes_vec > 2.6e8
-                           else "L2-resident working set (%.1f MB per vector): launch-bound regime, no flush" % (bytes_vec / 1e6)},
-                "newton_its": newton, "krylov_its": krylov, "energy": reports[-1]["energy"], "solute": reports[-1]["solute"],
-                "gpu_launches": launches_all, "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * bytes_vec * world,
-                        "d2h_bytes_per_step": bytes_vec * world + 32, "ms_per_step": e2e_ms / args.steps},
-                "roofline": roofline, "kernels": kernels, "kernel_time_coverage": total_fam_ms / ms_prof}
+                               args.restart, stored, args.sweeps_mass, args.sweeps_shifted, "upper" if args.pc_variant else "full"),
+                           "l2_policy": ("inputs_exceed_l2 (every vector is %.0f MB >> 126 MB L2)" % (res["bytes_vec"] / 1e6)) if res["bytes_vec"] > 2.6e8
+                           else "L2-resident working set (%.1f MB per vector): launch-bound regime, no flush" % (res["bytes_vec"] / 1e6)},
+                "gpu_launches": res["launches"], "clocks": res["clocks"],
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * res["bytes_vec"] * world,
+                        "d2h_bytes_per_step": res["bytes_vec"] * world + 32, "ms_per_step": res["e2e_ms"] / args.steps},
+                "roofline": roofline, "kernels": kernels, "kernel_time_coverage": cover}
+        if "fp64" in res:
+            f = res["fp64"]
+            line["value_fp64_storage"] = dof * f["newton"] / (f["ms"] * 1e-3)
+            line["fp64_storage"] = {"ms_per_step": f["ms"] / args.steps, "newton_its": f["newton"], "krylov_its": f["krylov"],
+                                    "energy": f["energy"]}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
-    ctx.close()
+        if extra:
+            line["configs"] = extra
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -352,10 +447,13 @@ def main():
     ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--pc-variant", type=int, default=1)
     ap.add_argument("--sweeps-mass", type=int, default=3)
-    ap.add_argument("--sweeps-shifted", type=int, default=5)
-    ap.add_argument("--cpu-grid", type=int, default=64, help="sample grid of the cpu_baseline leg")
-    ap.add_argument("--ref-grid", type=int, default=64, help="sample grid of --impl reference")
+    ap.add_argument("--sweeps-shifted", type=int, default=4)
+    ap.add_argument("--cpu-grid", type=int, default=48, help="sample grid of the cpu_baseline leg")
+    ap.add_argument("--ref-grid", type=int, default=48, help="sample grid of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the bench1 2-D records (1024^2, 4096^2, 8192^2)")
+    ap.add_argument("--no-fp64-pass", action="store_true", help="skip the second timed pass with the Krylov basis stored in fp64")
+    ap.add_argument("--option", action="append", default=[], help="library tuning option key=value (pfh_set_option), repeatable")
     ap.add_argument("--basis", default="auto", choices=["auto", "fp64", "fp32"],
                     help="Krylov basis storage (auto: fp32 at the default linear tolerance, DESIGN.md section 5)")
     ap.add_argument("--jac-fp32", action="store_true",

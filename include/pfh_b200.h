@@ -81,7 +81,7 @@ typedef struct {
   int preconditioner;            /* 0 = Schur-complement + Jacobi-Chebyshev (default), 1 = point Jacobi, 2 = none */
   int pc_variant;                /* Schur: 0 = full block-LDU, 1 = block upper-triangular */
   int pc_sweeps_mass;            /* Chebyshev sweeps per mass solve */
-  int pc_sweeps_shifted;         /* Chebyshev sweeps per (M + alpha K) solve */
+  int pc_sweeps_shifted;         /* Chebyshev sweeps per (M + alpha K) solve; 0 = automatic (5; 4 in 3-D) */
   int verbose;                   /* 1: print Newton/Krylov history to stderr */
 } pfh_solver_opts;
 
@@ -157,10 +157,13 @@ int pfh_energy_host(pfh_ctx* ctx, const double* w_host, double out[4]);
 /* Instrumentation: kernels launched by this ctx since creation / last reset; and device
  * time (ms, CUDA events on the ctx stream) accumulated per kernel family when profiling is on. */
 long long pfh_launch_count(const pfh_ctx* ctx);
-/* Options (key, value): "profiling" 0/1 per-family event timers; "reset_launch_count"; "overlap" 0/1 halo/compute
- * overlap on slab-decomposed meshes (default 1); "use_tma" 0/1 TMA-staged 3-D kernels (default 1; 0 = gather kernels);
- * "use_first2" 0/1 first two Chebyshev iterates in one pass (default 1); "use_fused" 0/1 temporally blocked sweeps
- * (default 0, slower); "scalar_variant" tile-shape variants of the 3-D scalar kernel (tuning); "basis_precision" storage
+/* Options (key, value): "profiling" 0/1 per-family event timers; "reset_launch_count"; "use_tma" 0/1 staged 3-D
+ * kernels (default 1; 0 = gather kernels); "use_tma_loader" 0/1 fill the stages by TMA when rows are 16-byte aligned
+ * (default 1; 0 = always the cp.async loader that also serves odd vertex counts); "use_wide" 0/1 wide-ghost
+ * preconditioner on slab-decomposed meshes (default 1; 0 = one ghost-plane exchange per sweep); "use_first2" 0/1 first
+ * two Chebyshev iterates in one pass (default 1); "scalar_variant", "scalar_zchunk", "jac_variant", "jac_zchunk" tile /
+ * ring / chunk variants of the staged kernels (tuning); "cheb_bounds" 1 = Chebyshev interval of the 3-D shifted solves
+ * from the operator's symbol (default), 0 = generic bounds, with factors "cheb_flo", "cheb_fhi"; "basis_precision" storage
  * of the GMRES basis: 0 = fp32 when krylov_rtol >= 1e-6 else fp64 (default), 1 = fp64, 2 = fp32 (arithmetic is fp64
  * in all cases); "jac_quadrature_fp32" 0/1 (default 0): the quadrature block of the Krylov J.v of the 3-D fast path in
  * single precision (Newton's residual stays fp64).  Unknown keys are an error. */

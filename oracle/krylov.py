@@ -43,10 +43,28 @@ def jacobi_bounds(A, M=None):
     return float(np.min(rs / d))
 
 
+def symbol_lmax(A, mesh, ng=24):
+    """Largest value of the symbol of D^-1 A on the interior rows of a structured 3-D mesh (the spectrum's upper end up to
+    boundary effects of a fraction of a per cent): the row of a vertex in the middle of the mesh, Fourier-transformed on a
+    grid of (ng+1) x (2 ng+1)^2 wave vectors.  CPU statement of symbol_bounds3 in csrc/pfh_solver.cpp."""
+    nx, ny, nz = mesh.shape
+    h = np.array(mesh.lengths) / np.array(mesh.shape)
+    i = (nz // 2) * (nx + 1) * (ny + 1) + (ny // 2) * (nx + 1) + nx // 2
+    row = A.getrow(i)
+    off = np.rint((mesh.coords[row.indices] - mesh.coords[i]) / h)          # integer offsets of the stencil
+    th = np.pi * np.arange(0, ng + 1) / ng
+    th2 = np.pi * np.arange(-ng, ng + 1) / ng
+    tx, ty, tz = np.meshgrid(th, th2, th2, indexing="ij")
+    sym = np.zeros_like(tx)
+    for v, (dx, dy, dz) in zip(row.data, off):
+        sym += v * np.cos(dx * tx + dy * ty + dz * tz)
+    return float(sym.max() / A[i, i])
+
+
 class SchurChebPC:
     """P^-1 for J = [[M/dt, Mob K], [-(M_f'' + kappa K), M]]  (SURVEY.md Appendix B.1)."""
 
-    def __init__(self, disc, u, dt, n_m=4, n_a=8, variant="full", lmax=None):
+    def __init__(self, disc, u, dt, n_m=4, n_a=8, variant="full", lmax=None, symbol_lmax=False):
         V, p = disc.V, disc.prob.p
         self.V, self.dt, self.Mob, self.kappa = V, dt, p["M"], p.get("kappa", p.get("kappa_c"))
         self.alpha = np.sqrt(dt * self.Mob * self.kappa)
@@ -57,6 +75,11 @@ class SchurChebPC:
         self.lmax = lmax if lmax is not None else 0.5 * (dim + 2)
         self.lminM = 0.5
         self.lminA = min(0.5, jacobi_bounds(self.A))
+        # interval of the shifted solves: generic upper end (d+2)/2, or the product's default in 3-D (pfh_solver.cpp):
+        # 1.015 x the maximum of the operator's symbol, which needs one sweep less for the same iteration count
+        self.lmaxA = self.lmax
+        if symbol_lmax and dim == 3 and min(disc.mesh.shape) >= 4:
+            self.lmaxA = 1.015 * globals()["symbol_lmax"](self.A, disc.mesh)
         dg = disc.prob.dg(V.at_quad(u))
         self.C = (self.kappa * V.K - V.weighted_mass(dg[1, 0])).tocsr()   # kappa K + M_f''  (g_mu = -f')
         self.n_m, self.n_a, self.variant = n_m, n_a, variant
@@ -67,7 +90,7 @@ class SchurChebPC:
         return cheb_solve(self.V.M, self.dinvM, r, self.lminM, self.lmax, self.n_m)
 
     def Ainv(self, r):
-        return cheb_solve(self.A, self.dinvA, r, self.lminA, self.lmax, self.n_a)
+        return cheb_solve(self.A, self.dinvA, r, self.lminA, self.lmaxA, self.n_a)
 
     def __call__(self, r):
         self.napply += 1

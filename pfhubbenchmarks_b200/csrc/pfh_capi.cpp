@@ -86,7 +86,7 @@ void pfh_default_solver_opts(pfh_solver_opts* o) {
   o->preconditioner = 0;
   o->pc_variant = 1;        // block upper-triangular: best time-to-solution in the 256^3 sweep (profiles/r1_pc_sweep_256.txt)
   o->pc_sweeps_mass = 3;
-  o->pc_sweeps_shifted = 5;
+  o->pc_sweeps_shifted = 0;   // automatic: 5, or 4 in 3-D where the Chebyshev interval comes from the operator's symbol (pfh_solver.cpp)
   o->verbose = 0;
 }
 
@@ -129,6 +129,10 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     PFH_CHECK(c->dim == 3 || cfg->nranks == 1, "2-D problems do not shard (replicas only)");
 
     PFH_CUDA(cudaSetDevice(cfg->device));
+    if (c->dim == 3) {  // kernel attributes are per device: set them for the device this ctx lives on
+      pfh_scalar3_init_device();
+      pfh_jac3_init_device();
+    }
     if (cfg->stream) {
       c->stream = (cudaStream_t)cfg->stream;
     } else {
@@ -172,7 +176,13 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     c->R = pfh_alloc(c, vs); c->B = pfh_alloc(c, vs); c->DX = pfh_alloc(c, vs); c->DX2 = pfh_alloc(c, vs);
     c->W1 = pfh_alloc(c, vs); c->W2 = pfh_alloc(c, vs);
     c->V = pfh_alloc(c, (size_t)vs * (c->cfg.krylov_basis + 1));
-    for (int i = 0; i < 5; ++i) c->S[i] = pfh_alloc(c, c->n_owned + 32);
+    // scalar work vectors; on a slab (nranks > 1) with `gw` spare planes on each side for the wide-ghost preconditioner
+    if (c->dim == 3 && cfg->nranks > 1) {
+      c->gw = 8;
+      c->min_slab = c->m3.nzv / cfg->nranks;  // slab_range (engine.py) balances the planes: every rank owns at least this many
+    }
+    const size_t ext = (size_t)c->gw * (size_t)c->nplane;
+    for (int i = 0; i < 5; ++i) c->S[i] = pfh_alloc(c, c->n_owned + 2 * ext + 32) + ext;
     if (c->dim == 2 && (cfg->problem == PFH_PROBLEM_BENCH2 || cfg->problem == PFH_PROBLEM_BENCH3 || cfg->problem == PFH_PROBLEM_USER))
       for (int i = 0; i < 4; ++i) c->SIG[i] = pfh_alloc(c, c->n_owned + 32);
     if (c->nplane) {
@@ -181,9 +191,7 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
       c->gU0_lo = pfh_alloc(c, g); c->gU0_hi = pfh_alloc(c, g);
       c->gX_lo = pfh_alloc(c, g); c->gX_hi = pfh_alloc(c, g);
       c->gS_lo = pfh_alloc(c, c->nplane); c->gS_hi = pfh_alloc(c, c->nplane);
-      c->g2S_lo = pfh_alloc(c, 2 * c->nplane); c->g2S_hi = pfh_alloc(c, 2 * c->nplane);
-      c->g2R_lo = pfh_alloc(c, 2 * c->nplane); c->g2R_hi = pfh_alloc(c, 2 * c->nplane);
-      c->g2P_lo = pfh_alloc(c, 2 * c->nplane); c->g2P_hi = pfh_alloc(c, 2 * c->nplane);
+      c->gR_lo = pfh_alloc(c, (size_t)c->gw * c->nplane); c->gR_hi = pfh_alloc(c, (size_t)c->gw * c->nplane);
     }
     c->d_partial = pfh_alloc(c, (size_t)PFH_RED_MAXBLOCKS * PFH_RED_MAXVALS);
     c->d_red = pfh_alloc(c, PFH_RED_MAXVALS);
@@ -218,6 +226,7 @@ int pfh_destroy(pfh_ctx* c) {
   if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  pfh_tmap_cache_free(c);
   for (double* p : c->allocs) cudaFree(p);
   if (c->h_red) cudaFreeHost(c->h_red);
   for (EventPair& e : c->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -426,8 +435,25 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->overlap = value != 0.0;
   } else if (k == "scalar_variant") {
     c->scalar_variant = (int)value;
-  } else if (k == "use_fused") {
-    c->use_fused = value != 0.0;
+  } else if (k == "scalar_zchunk") {
+    c->scalar_zchunk = (int)value;
+  } else if (k == "jac_zchunk") {
+    c->jac_zchunk = (int)value;
+  } else if (k == "jac_variant") {
+    c->jac_variant = (int)value;
+  } else if (k == "use_wide") {
+    c->use_wide = value != 0.0;
+  } else if (k == "use_tma_loader") {
+    c->use_tma_loader = value != 0.0;
+  } else if (k == "cheb_bounds") {
+    c->cheb_bounds = (int)value;
+    c->pc_ready = false;
+  } else if (k == "cheb_flo") {
+    c->cheb_flo = value;
+    c->pc_ready = false;
+  } else if (k == "cheb_fhi") {
+    c->cheb_fhi = value;
+    c->pc_ready = false;
   } else if (k == "basis_precision") {
     PFH_CHECK(value == 0.0 || value == 1.0 || value == 2.0, "basis_precision: 0 auto, 1 fp64, 2 fp32");
     c->basis_precision = (int)value;

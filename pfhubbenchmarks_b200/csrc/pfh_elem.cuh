@@ -81,6 +81,7 @@ PFH_DEV void cube_load(const P& prob, const double (&u)[P::NIN][8], const double
 //   corner k gets      h_k + S/2 + t0,  S = sum_j h_j      (39 fp64 ops per tet instead of ~90)
 struct QuarticJac {
   double Q2, Q1, Q0, R2, R1, R0;
+  QuarticJac() = default;
   PFH_HD QuarticJac(double a2, double a1, double a0, double detJ) {
     Q2 = detJ * TET_W1 * a2 / 648.0; Q1 = detJ * TET_W1 * a1 / 108.0; Q0 = detJ * TET_W1 * a0 / 18.0;
     R2 = detJ * TET_W0 * a2 / 256.0; R1 = detJ * TET_W0 * a1 / 64.0; R0 = detJ * TET_W0 * a0 / 16.0;
@@ -149,6 +150,7 @@ PFH_HD void cube_jac_quartic_f32(const QuarticJac& k, const double (&c)[8], cons
 // with the same folding: corner k gets Q(s + 2 c_k) + 1/2 sum_j Q(s + 2 c_j) + R(s).
 struct QuarticRes {
   double Q3, Q2, Q1, Q0, R3, R2, R1, R0;
+  QuarticRes() = default;
   PFH_HD QuarticRes(double a3, double a2, double a1, double a0, double detJ) {
     const double q = detJ * TET_W1 / 3.0, r = detJ * TET_W0 / 4.0;
     Q3 = q * a3 / 216.0; Q2 = q * a2 / 36.0; Q1 = q * a1 / 6.0; Q0 = q * a0;

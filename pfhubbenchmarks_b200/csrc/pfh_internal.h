@@ -141,8 +141,6 @@ struct pfh_ctx {
   cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr;
   bool overlap = true;
   const double* gS_prefetched = nullptr;  // scalar field whose ghost planes are already travelling into gS (ev_halo)
-  // z-range restriction of the next scalar-operator launches: 0 all planes, 1 boundary planes {0, nzl-1}, 2 interior [1, nzl-1)
-  int zpart = 0;
   double* d_tables = nullptr;
 
   // workspaces (device)
@@ -157,8 +155,13 @@ struct pfh_ctx {
   double *gU0_lo = nullptr, *gU0_hi = nullptr;  // previous step
   double *gX_lo = nullptr, *gX_hi = nullptr;    // operand of an operator apply
   double *gS_lo = nullptr, *gS_hi = nullptr;    // scalar operand (preconditioner sweeps)
-  // two-plane ghosts of the fused (temporally blocked) Chebyshev kernels: operand z_k, right-hand side r, z_{k-1}
-  double *g2S_lo = nullptr, *g2S_hi = nullptr, *g2R_lo = nullptr, *g2R_hi = nullptr, *g2P_lo = nullptr, *g2P_hi = nullptr;
+  // Wide-ghost preconditioner (nranks > 1): the scalar work vectors S[] are allocated with `gw`
+  // extra planes below and above the owned slab (S[i] points at owned plane 0), so a Chebyshev solve exchanges its
+  // right-hand side ONCE at the width it needs and then sweeps redundantly on a shrinking halo; gR_* hold the wide
+  // ghost planes of a right-hand side that lives in a Krylov vector.
+  int gw = 0;
+  int min_slab = 0;  // smallest slab height over the ranks (an exchange of width w needs w <= min_slab)
+  double *gR_lo = nullptr, *gR_hi = nullptr;
   const double* jac_point = nullptr;            // device pointer to linearisation point (nf*n_owned)
 
   // reductions
@@ -171,6 +174,11 @@ struct pfh_ctx {
   bool pc_ready = false;
   double pc_alpha = 0.0;
   double lmax = 2.5, lmin_m = 0.5, lmin_a = 0.1;
+  double lmax_m = 2.5, lmax_a = 2.5;       // Chebyshev intervals of the mass and the shifted (M + alpha K) solves
+  double lmin_spd[4] = {0.1, 0.1, 0.1, 0.1};
+  int cheb_bounds = 1;                     // 3-D shifted solve: 1 = interval from the operator's symbol, 0 = generic bounds
+  double cheb_flo = 0.0, cheb_fhi = 1.015;  // factors on the symbol's extreme values (flo 0: keep the Rayleigh estimate)
+  std::vector<double> h_mT, h_kT;          // host copies of the stencil type tables
 
   Comm* comm = nullptr;
 
@@ -185,17 +193,19 @@ struct pfh_ctx {
   const double* scalar_sig = nullptr;  // 2-D scalar operators: optional per-vertex diagonal shift (lumped reaction term)
   double* SIG[4] = {nullptr, nullptr, nullptr, nullptr};
   int scalar_bc = 0;    // 2-D scalar operators: 1 = Dirichlet (identity) rows on the corner vertices of x = 0 and x = Lx
-  int scalar_variant = 0;  // tile/ring variant of the TMA scalar kernel (tuning; pfh_set_option "scalar_variant")
-  // fused two-sweep (temporally blocked) Chebyshev kernels (pfh_cheb2_tma.cu): correct, but shared-memory-bandwidth
-  // bound and 1.45x slower per solve than the per-sweep TMA kernel at 512^3 (profiles/README.md), so opt-in only
-  bool use_fused = false;
-  std::vector<double> h_mT3, h_kT3;  // host copies of the 3-D type tables (inverse diagonals for k_cheb_first2)
+  int scalar_variant = 0;  // tile/ring variant of the staged scalar kernel (tuning; pfh_set_option "scalar_variant")
+  int scalar_zchunk = 0;   // planes per CTA of the staged scalar kernel (0 = default 32; tuning)
+  int jac_variant = 0;     // ring depth / occupancy variant of the cube-centric kernel (tuning)
+  int jac_zchunk = 0;      // planes per CTA of the cube-centric J.v / residual kernel (0 = default 32; tuning)
+  bool use_wide = true;    // nranks > 1: wide-ghost Schur preconditioner (false: one ghost-plane exchange per sweep)
+  void* tmap_cache = nullptr;  // tensor-map cache (pfh_scalar3_tma.cu)
   // Krylov J.v of the 3-D TMA path: quadrature block in single precision (elem::cube_jac_quartic_f32).  Opt-in: validated
   // numerically on the CPU solver leg, not yet measured on hardware.
   bool jac_quadrature_fp32 = false;
   bool use_first2 = true;  // 3-D: first two Chebyshev iterates in one pass over r (k_cheb_first2)
   int basis_precision = 0;  // Krylov basis storage: 0 = fp32 when krylov_rtol >= 1e-6 else fp64, 1 = fp64, 2 = fp32
-  bool use_tma = true;  // 3-D fast path: TMA-staged kernels (pfh_stencil3_tma.cu); false = gather kernels only
+  bool use_tma = true;  // 3-D fast path: staged kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu); false = gather kernels only
+  bool use_tma_loader = true;  // stage with TMA when the operands allow it (false: always the cp.async loader; testing)
 };
 
 #define PFH_RED_MAXBLOCKS 1184  // 8 CTAs per SM * 148 SMs
@@ -245,15 +255,40 @@ void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst);
 // sig_i = max(d g_field / d u_field (u_i), floor_coef) * rowsum(M)_i  (2-D)
 void k_reaction_diag(pfh_ctx* c, const double* u, int field, double floor_coef, double* sig);  // dst = src on the Dirichlet vertices of a scalar field
 
-// ---- TMA-staged 3-D kernels (pfh_stencil3_tma.cu); return false when the operands do not qualify ----
-bool pfh_tma_ok(const pfh_ctx* c);
-bool k3_scalar_tma_launch(pfh_ctx* c, int mode, double am, double ak, double a, double b, FieldRef in, const double* r,
-                          double* out, bool out_is_zero);
+// ---- staged 3-D kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu) ----
+bool pfh_fast3_ok(const pfh_ctx* c);   // 3-D and the staged kernels are enabled
+void pfh_scalar3_init_device();        // per-device kernel attributes (dynamic shared memory opt-in)
+void pfh_jac3_init_device();
+void pfh_tmap_cache_free(pfh_ctx* c);
+// One launch of the scalar operator A = am M + ak K on a window of planes (pfh_scalar3_tma.cu).  Output planes are
+// launch-local zl = 0 .. nzo-1 = global planes gz0 .. gz0+nzo-1; out / out1 / r / o point at launch-local plane 0.
+// The stencil operand is read on launch-local planes -1 .. nzo: plane zi has index zi + in_off in the main array `in`
+// (in_n planes); indices below 0 come from the last planes of `in_lo` (n_lo planes), indices >= in_n from `in_hi`;
+// whatever lies outside every array reads as zero (physical boundary).
+struct ScalarOp {
+  int mode = 0;                    // 0: out = a r + A in [out1 = in]; 2: out = in + a (in - o) + b D^-1 (r - A in);
+                                   // 3: out1 = b0 D^-1 in, out = out1 + a out1 + b D^-1 (in - A out1)
+  double am = 0, ak = 0, a = 0, b = 0, b0 = 0;
+  const double* in = nullptr;
+  int in_off = 0, in_n = 0;
+  const double* in_lo = nullptr;
+  int n_lo = 0;
+  const double* in_hi = nullptr;
+  int n_hi = 0;
+  const double* r = nullptr;       // pointwise operand, addressed like `in`: plane zl has index zl + r_off in `r` (r_n planes,
+  int r_off = 0, r_n = 0;          // 0 = nzo), below / above that in r_lo / r_hi
+  const double* r_lo = nullptr;
+  int n_rlo = 0;
+  const double* r_hi = nullptr;
+  int n_rhi = 0;
+  const double* o = nullptr;
+  double* out = nullptr;
+  double* out1 = nullptr;
+  int gz0 = 0, nzo = 0;
+};
+void k3_scalar_launch(pfh_ctx* c, const ScalarOp& op);
 bool k3_jac_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, const double* x, double* y);
-bool k3_cheb2_launch(pfh_ctx* c, bool first, double am, double ak, double b0, double aX, double bX, double aY, double bY,
-                     const double* zk, const double* zkm1, const double* r, double* outX, double* outY);
 bool k3_res_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* u, const double* u0, double* R);
-bool k3_cheb_first2_tma_launch(pfh_ctx* c, double am, double ak, double b0, double a1, double b1, FieldRef r, double* z1, double* z2);
 bool k3_ch_crow_tma_launch(pfh_ctx* c, const LinCoefs& L, const double* ulin, FieldRef xc, double* out);
 // out = [J(ulin) (xc, 0)]_mu for Cahn-Hilliard (scalar in, scalar out); false if no fast path applies
 bool k_ch_crow(pfh_ctx* c, const double* ulin, FieldRef xc, double* out);
@@ -291,7 +326,8 @@ void comm_allreduce_sum(pfh_ctx* c, double* d_buf, int n);
 // exchange boundary planes of nfields fields stored field-major with stride fstride
 void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, double* glo, double* ghi,
                cudaStream_t stream = nullptr);  // stream == nullptr: the ctx stream
-// exchange the first / last `nplanes` planes of one scalar field (ghost width nplanes)
+// exchange the first / last `nplanes` planes of one scalar field (ghost width nplanes): glo receives the lower
+// neighbour's last planes, ghi the upper neighbour's first planes
 void comm_halo_n(pfh_ctx* c, const double* base, int nplanes, double* glo, double* ghi);
 int comm_unique_id(void* out);
 

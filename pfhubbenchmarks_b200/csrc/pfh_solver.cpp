@@ -114,143 +114,136 @@ double lmin_estimate(const pfh_ctx* c, double am, double ak, const std::vector<d
   return lo;
 }
 
-// result is guaranteed to land in `target`; `tmp` is scratch of the same size
-// Whole solve in one (3 sweeps) or two (5 sweeps) temporally blocked passes (pfh_cheb2_tma.cu); false: not applicable
-bool cheb_solve_fused(pfh_ctx* c, double am, double ak, const std::vector<ChebCoef>& cf, const double* r, double* target,
-                      double* tmp, double* tmp2) {
-  const int ns = (int)cf.size();
-  if (c->dim != 3 || !c->use_fused || !pfh_tma_ok(c) || (ns != 3 && ns != 5) || c->m3.nzl < 2) return false;
-  if (ns == 5 && (tmp == nullptr || tmp2 == nullptr)) return false;
-  const bool multi = c->cfg.nranks > 1;
-  const double n = (double)c->n_owned;
-  if (multi) comm_halo_n(c, r, 2, c->g2R_lo, c->g2R_hi);
-  if (ns == 3) {
-    ProfScope ps(c, T_CHEB_SWEEP, 16.0 * n);
-    return k3_cheb2_launch(c, true, am, ak, cf[0].b, cf[1].a, cf[1].b, cf[2].a, cf[2].b, nullptr, nullptr, r, nullptr, target);
-  }
-  {  // r -> z2 (tmp), z3 (tmp2)
-    ProfScope ps(c, T_CHEB_SWEEP, 24.0 * n);
-    if (!k3_cheb2_launch(c, true, am, ak, cf[0].b, cf[1].a, cf[1].b, cf[2].a, cf[2].b, nullptr, nullptr, r, tmp, tmp2)) return false;
-  }
-  if (multi) {
-    comm_halo_n(c, tmp2, 2, c->g2S_lo, c->g2S_hi);
-    comm_halo_n(c, tmp, 2, c->g2P_lo, c->g2P_hi);
-  }
-  ProfScope ps(c, T_CHEB_SWEEP, 32.0 * n);  // z3, z2, r -> z5
-  return k3_cheb2_launch(c, false, am, ak, 0.0, cf[3].a, cf[3].b, cf[4].a, cf[4].b, tmp2, tmp, r, nullptr, target);
-}
-
+// result is guaranteed to land in `target`; `tmp` is scratch of the same size.  Ghost planes (nranks > 1) are
+// exchanged synchronously before every launch that reads a neighbour's plane; the wide-ghost path below avoids that.
 void cheb_solve(pfh_ctx* c, double am, double ak, double lmin, double lmax, int nsweeps, const double* r, double* target,
-                double* tmp, bool consumer_needs_ghosts = false, double* tmp2 = nullptr) {
+                double* tmp) {
   const std::vector<ChebCoef> cf = cheb_coeffs(lmin, lmax, nsweeps);
-  if (cheb_solve_fused(c, am, ak, cf, r, target, tmp, tmp2)) return;
   double* cur = ((nsweeps - 1) % 2 == 0) ? target : tmp;
   double* prev = (cur == target) ? tmp : target;
-  const bool ov = c->cfg.nranks > 1 && c->overlap && c->comm_stream && c->dim == 3 && c->m3.nzl >= 4;
   // 3-D fast path: the first two iterates come out of one pass over r (k_cheb_first2), the loop then starts at k = 2
-  const bool first2 = nsweeps >= 2 && c->use_first2 && c->dim == 3 && pfh_tma_ok(c) && c->scalar_variant == 0;
-  if (!ov) {
-    int k0 = 1;
-    if (first2 && k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, scalar_ref(c, r), cur, prev)) {
-      std::swap(cur, prev);
-      k0 = 2;
-    } else {
-      k_cheb_first(c, am, ak, cf[0].b, r, cur);
-    }
-    for (int k = k0; k < nsweeps; ++k) {
-      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev, k == 1);
-      std::swap(cur, prev);
-    }
-  } else if (first2) {
-    // as below, but the first launch pair reads r's ghost planes: they travel under the interior launch
-    if (c->gS_prefetched != r) {
-      PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
-      PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-      comm_halo(c, r, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
-      PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
-    }
-    c->gS_prefetched = nullptr;
-    const FieldRef rref{r, c->gS_lo, c->gS_hi};
-    c->zpart = 2;
-    PFH_CHECK(k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, rref, cur, prev), "internal: fused first sweeps unavailable");
-    PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-    c->zpart = 1;
-    k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, rref, cur, prev);
-    PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+  const bool first2 = nsweeps >= 2 && c->use_first2 && pfh_fast3_ok(c);
+  int k0 = 1;
+  if (first2 && k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, scalar_ref(c, r), cur, prev)) {
     std::swap(cur, prev);
-    if (nsweeps == 2 && consumer_needs_ghosts) {
-      PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-      comm_halo(c, cur, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
-      PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
-      c->gS_prefetched = cur;
-    }
-    for (int k = 2; k < nsweeps; ++k) {
-      PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-      comm_halo(c, cur, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
-      PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
-      PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-      const FieldRef ref{cur, c->gS_lo, c->gS_hi};
-      c->zpart = 1;
-      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, false);
-      PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
-      if (k == nsweeps - 1 && consumer_needs_ghosts) {
-        PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-        comm_halo(c, prev, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
-        PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
-        c->gS_prefetched = prev;
-      }
-      c->zpart = 2;
-      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, false);
-      std::swap(cur, prev);
-    }
-    c->zpart = 0;
+    k0 = 2;
   } else {
-    // Halo/compute overlap: every producer writes its two slab-boundary planes first and signals ev_bnd; the ghost
-    // exchange of those planes runs on comm_stream while the interior planes are computed on the ctx stream; the
-    // next sweep's boundary launch waits for ev_halo.  Only the interior launch never touches ghost planes.
-    c->zpart = 1;
     k_cheb_first(c, am, ak, cf[0].b, r, cur);
-    PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
-    c->zpart = 2;
-    k_cheb_first(c, am, ak, cf[0].b, r, cur);
-    for (int k = 1; k < nsweeps; ++k) {
-      PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-      comm_halo(c, cur, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
-      PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
-      PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-      const FieldRef ref{cur, c->gS_lo, c->gS_hi};
-      c->zpart = 1;
-      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, k == 1);
-      PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
-      if (k == nsweeps - 1 && consumer_needs_ghosts) {
-        // the result's slab-boundary planes are final: ship its ghost planes now, under the last interior launch
-        PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-        comm_halo(c, prev, 0, 1, c->gS_lo, c->gS_hi, c->comm_stream);
-        PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
-        c->gS_prefetched = prev;
-      }
-      c->zpart = 2;
-      k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, ref, prev, k == 1);
-      std::swap(cur, prev);
-    }
-    c->zpart = 0;
+  }
+  for (int k = k0; k < nsweeps; ++k) {
+    k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev, k == 1);
+    std::swap(cur, prev);
   }
   PFH_CHECK(cur == target, "internal: chebyshev ping-pong parity");
 }
 
-struct HostTables {
-  std::vector<double> mT, kT;
+// ------------------------------------------------------------------------------------------
+// Wide-ghost scalar operators (3-D slabs, nranks > 1)
+//
+// A Chebyshev solve with n sweeps is a polynomial of degree n-1 in the 15-point operator: its result on the owned
+// planes depends on the right-hand side up to n-1 planes beyond them.  Instead of exchanging one ghost plane before
+// every sweep (n exchanges of 2-4 MB, each costing a launch + NVLink round trip that a 100 us sweep cannot hide), the
+// right-hand side is exchanged ONCE at width n-1+d and the sweeps run redundantly on a window that shrinks by one
+// plane per sweep until it reaches the depth d the consumer needs.  The scalar work vectors S[] carry `gw` spare
+// planes on each side for this (pfh_ctx::gw); an operand that lives in a Krylov vector uses the wide ghost arrays gR_*.
+// Redundant work: at most (n-1)/nzl of a sweep per side, ~6 % of the preconditioner on a 64-plane slab.
+// ------------------------------------------------------------------------------------------
+struct Win {
+  int lo, hi;  // output planes [lo, hi) relative to the owned slab
 };
-HostTables host_tables(const pfh_ctx* c) {
-  HostTables t;
+// owned slab widened by d planes on the sides that have a neighbour
+Win win_of(const pfh_ctx* c, int d) {
+  const Mesh3& m = c->m3;
+  return Win{-std::min(d, m.z0), m.nzl + std::min(d, m.nzv - (m.z0 + m.nzl))};
+}
+struct WideOperand {
+  const double* p;       // owned plane 0
+  bool ext;              // true: one of the S[] vectors (gw spare planes on each side, contiguous)
+  const double* glo;     // !ext: separate ghost arrays holding planes -n..-1 and nzl..nzl+n-1
+  const double* ghi;
+  int n;
+};
+WideOperand ext_op(const double* p) { return WideOperand{p, true, nullptr, nullptr, 0}; }
+
+const WideOperand kNoOperand{nullptr, true, nullptr, nullptr, 0};
+
+void wide_launch(pfh_ctx* c, int timer, double bytes_per_vertex, int mode, double am, double ak, double a, double b, double b0,
+                 const WideOperand& in, const WideOperand& r, const double* o, double* out, double* out1, Win w) {
+  const Mesh3& m = c->m3;
+  const bool has_lo = c->cfg.rank > 0, has_hi = c->cfg.rank < c->cfg.nranks - 1;
+  ScalarOp op;
+  op.mode = mode; op.am = am; op.ak = ak; op.a = a; op.b = b; op.b0 = b0;
+  if (in.ext) {
+    const int elo = has_lo ? c->gw : 0, ehi = has_hi ? c->gw : 0;
+    op.in = in.p - (long long)elo * m.nxy;
+    op.in_n = elo + m.nzl + ehi;
+    op.in_off = elo + w.lo;
+  } else {
+    op.in = in.p;
+    op.in_n = m.nzl;
+    op.in_off = w.lo;
+    if (has_lo && in.glo) { op.in_lo = in.glo; op.n_lo = in.n; }
+    if (has_hi && in.ghi) { op.in_hi = in.ghi; op.n_hi = in.n; }
+  }
+  const long long off = (long long)w.lo * m.nxy;
+  if (r.p != nullptr) {
+    if (r.ext) {
+      op.r = r.p + off;  // covers the window contiguously
+    } else {
+      op.r = r.p;
+      op.r_off = w.lo;
+      op.r_n = m.nzl;
+      if (has_lo && r.glo) { op.r_lo = r.glo; op.n_rlo = r.n; }
+      if (has_hi && r.ghi) { op.r_hi = r.ghi; op.n_rhi = r.n; }
+    }
+  }
+  op.o = o ? o + off : nullptr;
+  op.out = out + off;
+  op.out1 = out1 ? out1 + off : nullptr;
+  op.gz0 = m.z0 + w.lo;
+  op.nzo = w.hi - w.lo;
+  ProfScope ps(c, timer, bytes_per_vertex * (double)op.nzo * (double)m.nxy);
+  k3_scalar_launch(c, op);
+}
+
+// exchange `w` planes of a scalar field: ext vectors receive in place, others into gR_*
+void wide_exchange(pfh_ctx* c, const double* p, bool ext, int w) {
+  if (w <= 0) return;
+  const Mesh3& m = c->m3;
+  if (ext) comm_halo_n(c, p, w, const_cast<double*>(p) - (long long)w * m.nxy, const_cast<double*>(p) + (long long)m.nzl * m.nxy);
+  else comm_halo_n(c, p, w, c->gR_lo, c->gR_hi);
+}
+
+// z_n = p_{n-1}(D^-1 A) D^-1 rhs on the window of depth d_out.  `rhs` must be valid to depth d_out + n - 1; iterates
+// alternate between the ext vectors bufA / bufB; the last sweep writes `out` (any vector that covers the window).
+void cheb_solve_wide(pfh_ctx* c, double am, double ak, double lmin, double lmax, int n, const WideOperand& rhs, int d_out,
+                     double* bufA, double* bufB, double* out) {
+  PFH_CHECK(n >= 2, "internal: wide Chebyshev solve needs at least two sweeps");
+  const std::vector<ChebCoef> cf = cheb_coeffs(lmin, lmax, n);
+  // first two iterates on the window of depth d_out + n - 2; if n == 2 the second one is the result
+  double* z1 = bufA;
+  double* z2 = n == 2 ? out : bufB;
+  wide_launch(c, T_CHEB_FIRST, 24.0, 3, am, ak, cf[1].a, cf[1].b, cf[0].b, rhs, kNoOperand, nullptr, z2, z1, win_of(c, d_out + n - 2));
+  double *cur = z2, *prev = z1;
+  for (int k = 2; k < n; ++k) {
+    double* dst = k == n - 1 ? out : prev;  // in place over z_{k-1} except for the last sweep
+    wide_launch(c, T_CHEB_SWEEP, 32.0, 2, am, ak, cf[k].a, cf[k].b, 0.0, ext_op(cur), rhs, prev, dst, nullptr,
+                win_of(c, d_out + n - 1 - k));
+    prev = cur;
+    cur = dst;
+  }
+}
+
+// host copies of the stencil type tables, built once per ctx
+void ensure_host_tables(pfh_ctx* c) {
+  if (!c->h_mT.empty()) return;
   if (c->dim == 3) {
     Mesh3 m = c->m3;
-    pfh_build_tables3(m, t.mT, t.kT);
+    pfh_build_tables3(m, c->h_mT, c->h_kT);
   } else {
     Mesh2 m = c->m2;
-    pfh_build_tables2(m, t.mT, t.kT);
+    pfh_build_tables2(m, c->h_mT, c->h_kT);
   }
-  return t;
 }
 
 // which fields form the Cahn-Hilliard pair, and what the remaining fields' diagonal blocks are
@@ -289,18 +282,96 @@ PcLayout pc_layout(const pfh_ctx* c) {
   return L;
 }
 
+// restores the scalar-operator modifiers of the ctx however the scope is left
+struct ScalarModGuard {
+  pfh_ctx* c;
+  int bc;
+  const double* sig;
+  explicit ScalarModGuard(pfh_ctx* c_) : c(c_), bc(c_->scalar_bc), sig(c_->scalar_sig) {}
+  ~ScalarModGuard() {
+    c->scalar_bc = bc;
+    c->scalar_sig = sig;
+  }
+};
+
+// the wide-ghost Schur preconditioner applies when the slabs are thick enough for the widest exchange
+bool wide_ok(const pfh_ctx* c, const PcLayout& L, int nM, int nA) {
+  return c->cfg.nranks > 1 && c->use_wide && pfh_fast3_ok(c) && c->prob.id == PFH_PROBLEM_CH && L.has_ch && c->pc_opts.pc_variant == 1 &&
+         nM >= 2 && nA >= 2 && std::max(nM, nA) <= std::min(c->gw, c->min_slab);
+}
+
+// Block upper-triangular Schur preconditioner of the (c, mu) pair with three wide exchanges (r_mu, q, M y) instead of
+// one per sweep:  t = M^-1 r_mu ;  q = dt r_c - dt Mob K t ;  dc = A^-1 M A^-1 q ;  dmu = t
+void precond_apply_ch_wide(pfh_ctx* c, const PcLayout& L, int nM, int nA, const double* r, double* z) {
+  const long long n = c->n_owned;
+  const double dt = c->dt, alpha = c->pc_alpha;
+  const double *r1 = r, *r2 = r + n;
+  double *S0 = c->S[0], *S1 = c->S[1], *S2 = c->S[2], *S3 = c->S[3], *S4 = c->S[4];
+  // t = M^-1 r_mu to depth 1 (K t is needed on the owned planes): r_mu travels at width nM
+  wide_exchange(c, r2, false, nM);
+  cheb_solve_wide(c, 1.0, 0.0, c->lmin_m, c->lmax_m, nM, WideOperand{r2, false, c->gR_lo, c->gR_hi, nM}, 1, S1, S3, S0);
+  // q = dt r_c - dt Mob K t on the owned planes; the same pass copies t into z_mu (dmu = t)
+  wide_launch(c, T_LIN_APPLY, 32.0, 0, 0.0, -dt * L.Mob, dt, 0.0, 0.0, ext_op(S0), ext_op(r1), nullptr, S2, z + n, win_of(c, 0));
+  // y = A^-1 q to depth 1 (M y is needed on the owned planes): q travels at width nA
+  wide_exchange(c, S2, true, nA);
+  cheb_solve_wide(c, 1.0, alpha, c->lmin_a, c->lmax_a, nA, ext_op(S2), 1, S3, S4, S1);
+  wide_launch(c, T_LIN_APPLY, 16.0, 0, 1.0, 0.0, 0.0, 0.0, 0.0, ext_op(S1), kNoOperand, nullptr, S2, nullptr, win_of(c, 0));
+  // dc = A^-1 (M y) on the owned planes: M y travels at width nA - 1
+  wide_exchange(c, S2, true, nA - 1);
+  cheb_solve_wide(c, 1.0, alpha, c->lmin_a, c->lmax_a, nA, ext_op(S2), 0, S3, S4, z);
+}
+
 }  // namespace
+
+// Extreme values of the symbol of D^-1 (am M + ak K) on the interior rows of the Kuhn mesh: the spectrum of the
+// Jacobi-scaled operator up to boundary effects of a fraction of a per cent (checked against the assembled operator in
+// tests/test_oracle_properties.py).  The generic bounds, (d + 2)/2 from above and the Rayleigh quotient of the constant
+// from below, are up to 30 % wide of this interval for am M + ak K with ak > 0.
+static void symbol_bounds3(const Mesh3& m, double am, double ak, double& lo, double& hi) {
+  static const int DX[PFH_NOFF3] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1};
+  static const int DY[PFH_NOFF3] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1};
+  static const int DZ[PFH_NOFF3] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1};
+  double cf[PFH_NOFF3];
+  for (int o = 0; o < PFH_NOFF3; ++o) cf[o] = am * m.mI[o] + (o < PFH_NKOFF3 ? ak * m.kI[o] : 0.0);
+  const int ng = 24;
+  const double pi = 3.14159265358979323846;
+  lo = 1e300;
+  hi = -1e300;
+  for (int i = 0; i <= ng; ++i)
+    for (int j = -ng; j <= ng; ++j)
+      for (int k = -ng; k <= ng; ++k) {
+        const double tx = pi * i / ng, ty = pi * j / ng, tz = pi * k / ng;
+        double s = 0.0;
+        for (int o = 0; o < PFH_NOFF3; ++o) s += cf[o] * std::cos(DX[o] * tx + DY[o] * ty + DZ[o] * tz);
+        lo = std::fmin(lo, s);
+        hi = std::fmax(hi, s);
+      }
+  lo /= cf[0];
+  hi /= cf[0];
+}
 
 void s_precond_setup(pfh_ctx* c, const pfh_solver_opts* o) {
   c->pc_opts = *o;
+  ensure_host_tables(c);
   const PcLayout L = pc_layout(c);
   c->lmax = 0.5 * (c->dim + 2);
   c->lmin_m = 0.5;
+  c->lmax_m = c->lmax_a = c->lmax;
   if (L.has_ch) {
     c->pc_alpha = std::sqrt(c->dt * L.Mob * L.kappa);
-    const HostTables t = host_tables(c);
-    c->lmin_a = std::fmin(0.5, lmin_estimate(c, 1.0, c->pc_alpha, t.mT, t.kT));
+    c->lmin_a = std::fmin(0.5, lmin_estimate(c, 1.0, c->pc_alpha, c->h_mT, c->h_kT));
+    if (c->dim == 3 && c->cheb_bounds == 1) {
+      // upper end from the symbol; the lower end stays at the Rayleigh estimate (about 0.76 of the symbol's minimum):
+      // scanned on the CPU solver leg, this pair needs one sweep less per solve than the generic interval
+      double lo, hi;
+      symbol_bounds3(c->m3, 1.0, c->pc_alpha, lo, hi);
+      c->lmax_a = c->cheb_fhi * hi;
+      if (c->cheb_flo > 0.0) c->lmin_a = c->cheb_flo * lo;
+    }
   }
+  for (int k = 0; k < L.n_spd; ++k)
+    // with the clipped reaction shift the constant mode's Rayleigh quotient is at least half the unshifted one
+    c->lmin_spd[k] = 0.5 * std::fmin(0.5, lmin_estimate(c, L.spd_am[k], L.spd_ak[k], c->h_mT, c->h_kT));
   // lumped reaction term d g_a / d u_a of the parabolic fields' diagonal blocks at the linearisation point
   // (Allen-Cahn eta_i of bench2, U and phi of bench3); clipped at -1/2 of the block's mass coefficient
   if (c->jac_point != nullptr)
@@ -323,43 +394,43 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
     return;
   }
   const int nM = o.pc_sweeps_mass > 0 ? o.pc_sweeps_mass : 3;
-  const int nA = o.pc_sweeps_shifted > 0 ? o.pc_sweeps_shifted : 5;
-  if (L.has_ch) {
+  const int nA = o.pc_sweeps_shifted > 0 ? o.pc_sweeps_shifted : ((c->dim == 3 && c->cheb_bounds == 1) ? 4 : 5);
+  ScalarModGuard guard(c);
+  if (L.has_ch && wide_ok(c, L, nM, nA)) {
+    precond_apply_ch_wide(c, L, nM, nA, r, z);
+  } else if (L.has_ch) {
     const double dt = c->dt, alpha = c->pc_alpha;
     const double *r1 = r, *r2 = r + n;
     double *S0 = c->S[0], *S1 = c->S[1], *S2 = c->S[2], *S3 = c->S[3], *S4 = c->S[4];
     // t = M^-1 r2   (block upper-triangular variant: t IS dmu, so it is solved straight into z_mu)
     double* T = o.pc_variant == 1 ? z + n : S0;
-    cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, r2, T, S1, true);
+    cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax_m, nM, r2, T, S1);
     // q = dt r1 - dt Mob K t
     k_lin_apply(c, 0.0, -dt * L.Mob, scalar_ref(c, T), dt, r1, S2);
     // dc = A^-1 M A^-1 q,  A = M + alpha K
-    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, S3, S4, true, S1);
+    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax_a, nA, S2, S3, S4);
     k_lin_apply(c, 1.0, 0.0, scalar_ref(c, S3), 0.0, nullptr, S2);
-    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax, nA, S2, z, S4, o.pc_variant != 1, S1);
+    cheb_solve(c, 1.0, alpha, c->lmin_a, c->lmax_a, nA, S2, z, S4);
     if (o.pc_variant != 1) {
       // dmu = t + M^-1 (kappa K + M_f'') dc = t - M^-1 [J (dc, 0, ..)]_mu
       if (k_ch_crow(c, c->jac_point, scalar_ref(c, z), S2)) {
         // fused (mu, c) block apply: reads c and dc only, writes the mu row only
-        cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, S2, S3, S1);
+        cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax_m, nM, S2, S3, S1);
         v_axpby(c, 1.0, S0, -1.0, S3, z + n, n);
       } else {
         double *PX = c->W2, *PY = c->R;  // free during a linear solve (see gmres below)
         v_zero(c, PX, c->nf * n);
         v_copy(c, PX, z, n);
         s_jac_apply(c, PX, PY);
-        cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax, nM, PY + n, S2, S1);
+        cheb_solve(c, 1.0, 0.0, c->lmin_m, c->lmax_m, nM, PY + n, S2, S1);
         v_axpby(c, 1.0, S0, -1.0, S2, z + n, n);
       }
     }
   }
   for (int k = 0; k < L.n_spd; ++k) {
     const int f = L.spd_field[k];
-    const HostTables t = host_tables(c);
-    // with the clipped reaction shift the constant mode's Rayleigh quotient is at least half the unshifted one
-    const double lmin = 0.5 * std::fmin(0.5, lmin_estimate(c, L.spd_am[k], L.spd_ak[k], t.mT, t.kT));
     c->scalar_sig = (c->SIG[k] != nullptr && c->jac_point != nullptr) ? c->SIG[k] : nullptr;
-    cheb_solve(c, L.spd_am[k], L.spd_ak[k], lmin, c->lmax, nA, r + f * n, z + f * n, c->S[1]);
+    cheb_solve(c, L.spd_am[k], L.spd_ak[k], c->lmin_spd[k], c->lmax, nA, r + f * n, z + f * n, c->S[1]);
     c->scalar_sig = nullptr;
     if (L.spd_sign[k] < 0.0) v_scale(c, -1.0, z + f * n, z + f * n, n);
   }
@@ -377,7 +448,6 @@ void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
     const double pi = 3.14159265358979323846;
     const double lmin = 0.5 * (pi / c->m2.nx) * (pi / c->m2.nx) / 8.0;
     cheb_solve(c, 0.0, 1.0, lmin, 2.0, 240, rhs, z + 2 * n, tmp);
-    c->scalar_bc = 0;
   }
 }
 

@@ -66,21 +66,11 @@ __global__ void __launch_bounds__(BX* BY) k3_op(P prob, Mesh3 m, LinCoefs L, Fie
 // MODE 0: out = s*add + A in ; MODE 1: z = b Dinv r ; MODE 2: zprev <- z + a (z - zprev) + b Dinv (r - A z)
 template <int MODE>
 __global__ void __launch_bounds__(BX* BY) k3_scalar(Mesh3 m, double am, double ak, double a, double b, FieldRef in,
-                                                    const double* __restrict__ r, double* __restrict__ out, bool out_is_zero,
-                                                    int zpart) {
+                                                    const double* __restrict__ r, double* __restrict__ out, bool out_is_zero) {
   const int ix = blockIdx.x * BX + threadIdx.x, iy = blockIdx.y * BY + threadIdx.y;
   if (ix >= m.nxv || iy >= m.nyv) return;
-  // zpart 0: all planes; 1: slab-boundary planes {0, nzl-1}; 2: interior planes [1, nzl-1)
-  int z_beg, z_end;
-  if (zpart == 1) {
-    z_beg = blockIdx.z == 0 ? 0 : m.nzl - 1;
-    z_end = z_beg + 1;
-  } else {
-    const int zoff = zpart == 2 ? 1 : 0, zlim = zpart == 2 ? m.nzl - 1 : m.nzl;
-    z_beg = zoff + blockIdx.z * ZCHUNK;
-    z_end = min(zlim, z_beg + ZCHUNK);
-  }
-  for (int zl = z_beg; zl < z_end; ++zl) {
+  const int z_end = min(m.nzl, (int)(blockIdx.z + 1) * ZCHUNK);
+  for (int zl = blockIdx.z * ZCHUNK; zl < z_end; ++zl) {
     const long long i = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
     if (MODE == 1) {
       out[i] = b / vtx::scalar_diag3(m, am, ak, ix, iy, zl) * r[i];
@@ -312,11 +302,19 @@ __global__ void __launch_bounds__(TPB) k2_dirichlet_copy(Mesh2 m, const double* 
   if (ix == 0 || ix == m.nxv - 1) dst[i] = src[i];
 }
 
-// fraction of the owned planes a scalar-operator launch covers under the current z-range restriction
-double zfrac(const pfh_ctx* c) {
-  if (c->dim != 3 || c->zpart == 0) return 1.0;
-  const double nz = (double)c->m3.nzl;
-  return c->zpart == 1 ? 2.0 / nz : (nz - 2.0) / nz;
+// the scalar operator on the owned planes of a slab through the staged kernel (pfh_scalar3_tma.cu): `in` with its
+// one-plane ghost arrays
+void scalar_owned(pfh_ctx* c, int mode, double am, double ak, double a, double b, double b0, FieldRef in, const double* r,
+                  const double* o, double* out, double* out1) {
+  const Mesh3& m = c->m3;
+  ScalarOp op;
+  op.mode = mode; op.am = am; op.ak = ak; op.a = a; op.b = b; op.b0 = b0;
+  op.in = in.p; op.in_off = 0; op.in_n = m.nzl;
+  if (in.glo != nullptr && c->cfg.rank > 0) { op.in_lo = in.glo; op.n_lo = 1; }
+  if (in.ghi != nullptr && c->cfg.rank < c->cfg.nranks - 1) { op.in_hi = in.ghi; op.n_hi = 1; }
+  op.r = r; op.o = o; op.out = out; op.out1 = out1;
+  op.gz0 = m.z0; op.nzo = m.nzl;
+  k3_scalar_launch(c, op);
 }
 
 // sig_i = clip(d g_a / d u_a (u_i)) * rowsum(M)_i : lumped reaction term of the diagonal Jacobian block of field a
@@ -365,10 +363,6 @@ Coef2 coef2(const Mesh2& m, double am, double ak) {
 dim3 grid2_tiled(const Mesh2& m) { return dim3((m.nxv + T2X - 1) / T2X, (m.nyv + T2Y - 1) / T2Y); }
 
 dim3 grid3(const Mesh3& m) { return dim3((m.nxv + BX - 1) / BX, (m.nyv + BY - 1) / BY, (m.nzl + ZCHUNK - 1) / ZCHUNK); }
-dim3 grid3_part(const Mesh3& m, int zpart) {
-  const int nz = zpart == 1 ? 2 * ZCHUNK : (zpart == 2 ? (m.nzl - 2 > 0 ? m.nzl - 2 : 1) : m.nzl);
-  return dim3((m.nxv + BX - 1) / BX, (m.nyv + BY - 1) / BY, (nz + ZCHUNK - 1) / ZCHUNK);
-}
 int grid1(long long n) { return (int)((n + TPB - 1) / TPB); }
 int grid_red(long long n) {
   long long g = (n + TPB - 1) / TPB;
@@ -467,18 +461,21 @@ void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
 }
 
 bool k_ch_crow(pfh_ctx* c, const double* ulin, FieldRef xc, double* out) {
-  if (c->dim != 3 || c->prob.id != PFH_PROBLEM_CH || !pfh_tma_ok(c)) return false;
+  if (!pfh_fast3_ok(c) || c->prob.id != PFH_PROBLEM_CH) return false;
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
   ProfScope ps(c, T_JAC_APPLY, 24.0 * c->n_owned);
   return k3_ch_crow_tma_launch(c, L, ulin, xc, out);
 }
 
 void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out) {
-  ProfScope ps(c, T_LIN_APPLY, 8.0 * (s != 0.0 ? 3 : 2) * c->n_owned * zfrac(c));
+  ProfScope ps(c, T_LIN_APPLY, 8.0 * (s != 0.0 ? 3 : 2) * c->n_owned);
   PFH_CHECK(s == 0.0 || add != nullptr, "k_lin_apply: add operand missing");
-  if (c->dim == 3 && k3_scalar_tma_launch(c, 0, am, ak, s, 0.0, in, add, out, false)) return;
+  if (pfh_fast3_ok(c)) {
+    scalar_owned(c, 0, am, ak, s, 0.0, 0.0, in, add, nullptr, out, nullptr);
+    return;
+  }
   if (c->dim == 3)
-    k3_scalar<0><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false, c->zpart);
+    k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false);
   else
     k2_scalar_tiled<0><<<grid2_tiled(c->m2), dim3(T2X, T2Y), 0, c->stream>>>(c->m2, am, ak, coef2(c->m2, am, ak), s, 0.0, in.p, add, out, 0,
                                                                                   c->scalar_bc, c->scalar_sig);
@@ -486,26 +483,30 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
 }
 
 void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z) {
-  ProfScope ps(c, T_CHEB_FIRST, 16.0 * c->n_owned * zfrac(c));
+  ProfScope ps(c, T_CHEB_FIRST, 16.0 * c->n_owned);
   if (c->dim == 3)
-    k3_scalar<1><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z, false, c->zpart);
+    k3_scalar<1><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z, false);
   else
     k2_scalar<1><<<grid1(c->n_owned), TPB, 0, c->stream>>>(c->m2, am, ak, 0.0, b, nullptr, r, z, false, c->scalar_bc, c->scalar_sig);
   PFH_CUDA(cudaGetLastError());
 }
 
 bool k_cheb_first2(pfh_ctx* c, double am, double ak, double b0, double a1, double b1, FieldRef r, double* z1, double* z2) {
-  if (c->dim != 3 || !pfh_tma_ok(c) || c->scalar_variant != 0) return false;
-  ProfScope ps(c, T_CHEB_FIRST, 24.0 * c->n_owned * zfrac(c));
-  return k3_cheb_first2_tma_launch(c, am, ak, b0, a1, b1, r, z1, z2);
+  if (!pfh_fast3_ok(c)) return false;
+  ProfScope ps(c, T_CHEB_FIRST, 24.0 * c->n_owned);
+  scalar_owned(c, 3, am, ak, a1, b1, b0, r, nullptr, nullptr, z2, z1);
+  return true;
 }
 
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev,
                   bool zprev_is_zero) {
-  ProfScope ps(c, T_CHEB_SWEEP, (zprev_is_zero ? 24.0 : 32.0) * c->n_owned * zfrac(c));
-  if (c->dim == 3 && k3_scalar_tma_launch(c, 2, am, ak, a, b, z, r, zprev, zprev_is_zero)) return;
+  ProfScope ps(c, T_CHEB_SWEEP, (zprev_is_zero ? 24.0 : 32.0) * c->n_owned);
+  if (pfh_fast3_ok(c)) {
+    scalar_owned(c, 2, am, ak, a, b, 0.0, z, r, zprev_is_zero ? nullptr : zprev, zprev, nullptr);
+    return;
+  }
   if (c->dim == 3)
-    k3_scalar<2><<<grid3_part(c->m3, c->zpart), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero, c->zpart);
+    k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero);
   else
     k2_scalar_tiled<2><<<grid2_tiled(c->m2), dim3(T2X, T2Y), 0, c->stream>>>(c->m2, am, ak, coef2(c->m2, am, ak), a, b, z.p, r, zprev,
                                                                                   zprev_is_zero ? 1 : 0, c->scalar_bc, c->scalar_sig);

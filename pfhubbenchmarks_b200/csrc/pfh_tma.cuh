@@ -1,4 +1,4 @@
-// Shared TMA / mbarrier plumbing of the TMA-staged kernels (pfh_stencil3_tma.cu, pfh_cheb2_tma.cu).
+// Shared TMA / mbarrier plumbing of the TMA-staged kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu).
 #pragma once
 #include <cuda.h>
 
@@ -42,6 +42,16 @@ static __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap*
       : "memory");
 }
 
+// 8-byte asynchronous copy (LDGSTS); src_bytes = 0 zero-fills the destination
+static __device__ __forceinline__ void cp_async8(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+// the executing thread arrives on `bar` once all its earlier cp.async copies have landed (the arrival is part of the
+// barrier's expected count: initialise it with the number of arriving threads)
+static __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 static constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // ---------------------------------------------------------------------------------------------
@@ -78,6 +88,8 @@ static inline CUtensorMap make_map(const double* ptr, int nxv, int nyv, int nz, 
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-// fp64 tensor (nxv, nyv, nz) with a (bx, by, 1) box: same as make_map, kept for readability at call sites with nz == 2 ghosts
 }  // namespace tma
+
+// make_map through a per-ctx cache keyed on (pointer, shape, box): the operands of the solver's launches are a handful
+// of fixed work vectors, so the driver call is paid once per operand instead of five times per launch
+CUtensorMap pfh_tensor_map(pfh_ctx* c, const double* ptr, int nxv, int nyv, int nz, int bx, int by);

@@ -152,9 +152,8 @@ LinCoefs pfh_lin_coefs(const pfh_ctx* c, double dt) {
   EMUL_DISPATCH(c, L = lin_of<P>(c, dt));
   return L;
 }
-bool pfh_tma_ok(const pfh_ctx*) { return false; }
-bool k3_cheb2_launch(pfh_ctx*, bool, double, double, double, double, double, double, double, const double*, const double*, const double*,
-                     double*, double*) { return false; }
+bool pfh_fast3_ok(const pfh_ctx*) { return false; }
+void k3_scalar_launch(pfh_ctx*, const ScalarOp&) { throw PfhError("emul: staged scalar kernel is not emulated"); }
 bool k_cheb_first2(pfh_ctx*, double, double, double, double, double, FieldRef, double*, double*) { return false; }
 bool k_ch_crow(pfh_ctx*, const double*, FieldRef, double*) { return false; }
 

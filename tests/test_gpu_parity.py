@@ -187,47 +187,41 @@ def _b13d_steps(eng, ncell, length):
 
 
 def test_tma_kernels_match_gather_kernels():
-    """Fast path (TMA-staged, cube-centric J.v) against the simple gather kernels on a mid-size grid."""
+    """Fast path (staged scalar kernel with the z-march register reuse, cube-centric J.v) against the simple gather
+    kernels: TMA loader (even vertex count in x), cp.async loader (odd count, e.g. the reference's 51^3 mesh) and the
+    cp.async loader forced onto the even mesh; every tile-shape variant of the scalar kernel."""
     eng = _engine()
-    ncell, length = (127, 70, 45), (254.0, 140.0, 90.0)
     rng = np.random.default_rng(11)
-    ctx = eng.Context("b13d", ncell, length)
-    n = ctx.n_owned
-    U = ctx.initial_condition()
-    U += 0.05 * torch.from_numpy(rng.standard_normal(2 * n)).cuda()
-    X = torch.from_numpy(rng.standard_normal(2 * n)).cuda()
-    ctx.dt = 0.8
-    out = {}
-    for tma in (0, 1):
-        ctx.set_option("use_tma", tma)
-        ctx.jac_setup(U)
-        y = ctx.jac_apply(X)
-        ctx.precond_setup(pc_variant=0, pc_sweeps_mass=3, pc_sweeps_shifted=6)
-        z = ctx.precond_apply(X)
-        out[tma] = (y.cpu().numpy(), z.cpu().numpy())
-    assert rel_max(out[1][0], out[0][0]) < 1e-13
-    assert rel_max(out[1][1], out[0][1]) < 1e-12
-    ctx.close()
-
-
-def test_fused_chebyshev_kernels_match_per_sweep_path():
-    """Opt-in temporally blocked Chebyshev kernels (pfh_cheb2_tma.cu) give the same preconditioner as the per-sweep kernels."""
-    eng = _engine()
-    ncell, length = (127, 70, 45), (254.0, 140.0, 90.0)
-    rng = np.random.default_rng(13)
-    ctx = eng.Context("b13d", ncell, length)
-    U = ctx.initial_condition()
-    X = torch.from_numpy(rng.standard_normal(2 * ctx.n_owned)).cuda()
-    ctx.dt = 1.6
-    ctx.jac_setup(U)
-    out = {}
-    for variant in (0, 1):
-        for fused in (0, 1):
-            ctx.set_option("use_fused", fused)
-            ctx.precond_setup(pc_variant=variant, pc_sweeps_mass=3, pc_sweeps_shifted=5)
-            out[(variant, fused)] = ctx.precond_apply(X).cpu().numpy()
-        assert rel_max(out[(variant, 1)], out[(variant, 0)]) < 1e-12
-    ctx.close()
+    for ncell, length in [((127, 70, 45), (254.0, 140.0, 90.0)), ((50, 50, 50), (100.0, 100.0, 100.0)), ((70, 9, 5), (140.0, 18.0, 10.0))]:
+        ctx = eng.Context("b13d", ncell, length)
+        n = ctx.n_owned
+        U = ctx.initial_condition()
+        U += 0.05 * torch.from_numpy(rng.standard_normal(2 * n)).cuda()
+        X = torch.from_numpy(rng.standard_normal(2 * n)).cuda()
+        ctx.dt = 0.8
+        out = {}
+        for key, (tma, loader, variant, jvar) in {"gather": (0, 1, 0, 0), "tma": (1, 1, 0, 0), "cpasync": (1, 0, 0, 0), "v1": (1, 1, 1, 1),
+                                                  "v2": (1, 1, 2, 0), "v3": (1, 0, 3, 1), "v4": (1, 1, 4, 0)}.items():
+            ctx.set_option("use_tma", tma)
+            ctx.set_option("use_tma_loader", loader)
+            ctx.set_option("scalar_variant", variant)
+            ctx.set_option("jac_variant", jvar)
+            ctx.jac_setup(U)
+            y = ctx.jac_apply(X)
+            R = ctx.residual(U, X)
+            res = []
+            for pcv in (0, 1):
+                ctx.precond_setup(pc_variant=pcv, pc_sweeps_mass=3, pc_sweeps_shifted=6)
+                res.append(ctx.precond_apply(X).cpu().numpy())
+            out[key] = (y.cpu().numpy(), R.cpu().numpy(), res[0], res[1])
+        for key in out:
+            if key == "gather":
+                continue
+            assert rel_max(out[key][0], out["gather"][0]) < 1e-13, (ncell, key)
+            assert rel_max(out[key][1], out["gather"][1]) < 1e-13, (ncell, key)
+            assert rel_max(out[key][2], out["gather"][2]) < 1e-12, (ncell, key)
+            assert rel_max(out[key][3], out["gather"][3]) < 1e-12, (ncell, key)
+        ctx.close()
 
 
 def test_step_host_equals_device_path():
