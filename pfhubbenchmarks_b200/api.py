@@ -109,7 +109,16 @@ class Function:
         self.tensor.copy_(other.tensor)
 
     def interpolate(self, ic):                    # w.interpolate(w_ic)  (bench1.py:134-135)
-        self._p.ctx.initial_condition(ic.args, out=self.tensor)
+        ctx = self._p.ctx
+        if ctx.problem in ic.kernel_problems:
+            ctx.initial_condition(ic.args, out=self.tensor)
+            return
+        # an expression of another benchmark: its closed form on the host, never this problem's kernel formula
+        import torch
+        if ic.nvalues != ctx.nf or ctx.nranks != 1:
+            raise ValueError("%s (%d components) does not fit this problem (%d fields)" % (type(ic).__name__, ic.nvalues, ctx.nf))
+        vals = ic.values(ctx.vertex_coordinates())
+        self.tensor.copy_(torch.from_numpy(np.ascontiguousarray(vals).reshape(-1)).to(self.tensor.device))
 
     def split(self):                              # c, _ = w.split()  (bench1.py:188)
         return self._p.ctx.fields(self.tensor)
@@ -122,24 +131,72 @@ class Function:
 
 
 class _IC:
+    """The reference's initial-condition expressions (dolfin/pfbase.py:177-339).  On a shipped problem of the matching
+    benchmark they are evaluated by the library's kernel (`kernel_problems`); anywhere else -- a generated model, or an
+    expression of another benchmark -- `values(xy)` evaluates the same closed form on the host, vertex by vertex as
+    DOLFIN's interpolate does."""
+    kernel_problems = ()
+    nvalues = 0
+
     def __init__(self, *args, **kwargs):
         self.args = [float(a) for a in args]
 
+    def value_shape(self):
+        return (self.nvalues,)
+
+    def values(self, xy):
+        raise NotImplementedError
+
+    def eval(self, values, x):                       # UserExpression.eval signature, one point
+        values[:self.nvalues] = self.values(np.asarray(x, dtype=float)[None, :])[:, 0]
+
+
+def _spinodal_c(x, y, c0, eps, kx=0.105):
+    return c0 + eps * (np.cos(kx * x) * np.cos(0.11 * y) + (np.cos(0.13 * x) * np.cos(0.087 * y)) ** 2
+                       + np.cos(0.025 * x - 0.15 * y) * np.cos(0.07 * x - 0.02 * y))
+
 
 class InitialConditionsBench1(_IC):   # pfbase.py:177-193
-    pass
+    kernel_problems, nvalues = ("bench1", "b13d"), 2
+
+    def values(self, xy):
+        c0, eps = self.args[:2]
+        return np.stack([_spinodal_c(xy[:, 0], xy[:, 1], c0, eps), np.zeros(len(xy))])
 
 
 class InitialConditionsBench2(_IC):   # pfbase.py:262-291
-    pass
+    kernel_problems, nvalues = ("bench2",), 6
+
+    def values(self, xy):
+        c0, eps, eps_eta, psi = self.args[:4]
+        x, y = xy[:, 0], xy[:, 1]
+        out = [_spinodal_c(x, y, c0, eps), np.zeros(len(xy))]
+        for i in range(4):
+            ii = i + 1.0
+            # the squared term uses i, not ii (pfbase.py:285-286); the reference's committed fields confirm it
+            sq = (np.cos((0.046 + 0.001 * i) * x - (0.0405 + 0.001 * i) * y) * np.cos((0.031 + 0.001 * i) * x - (0.004 + 0.001 * i) * y)) ** 2
+            out.append(eps_eta * (np.cos(0.01 * ii * x - 4.0) * np.cos((0.007 + 0.01 * ii) * y)
+                                  + np.cos((0.11 + 0.01 * ii) * x) * np.cos((0.11 + 0.01 * ii) * y) + psi * sq) ** 2)
+        return np.stack(out)
 
 
 class InitialConditionsBench3(_IC):   # pfbase.py:293-320
-    pass
+    kernel_problems, nvalues = ("bench3",), 2
+
+    def values(self, xy):
+        delta, r0, wd, vin, vout = self.args[:5]
+        r = np.hypot(xy[:, 0], xy[:, 1])
+        ramp = vout + 0.5 * (vin - vout) * (1.0 + np.cos(np.pi * (r - r0 + 0.5 * wd) / wd))
+        phi = np.where(r < r0 - 0.5 * wd, vin, np.where(r > r0 + 0.5 * wd, vout, ramp))
+        return np.stack([np.full(len(xy), delta), phi])
 
 
 class InitialConditionsBench6(_IC):   # pfbase.py:322-339
-    pass
+    kernel_problems, nvalues = ("bench6",), 3
+
+    def values(self, xy):
+        c0, c1 = self.args[:2]
+        return np.stack([_spinodal_c(xy[:, 0], xy[:, 1], c0, c1, kx=0.2), np.zeros(len(xy)), np.zeros(len(xy))])
 
 
 class NonlinearVariationalProblem:

@@ -51,6 +51,8 @@ struct ScalarParams {
 };
 
 // next to the boundary the neighbours' rows have different diagonals: scale operand by operand
+// (only on the two planes next to each z boundary: kept out of line, working on a copy in local memory, so that it
+// does not cost the main loop registers)
 __device__ __noinline__ void first2_scale_boundary(double* v, const InvDiag27& invd, double b0, int ix, int iy, int gz,
                                                    const Mesh3& m) {
   constexpr int DX[PFH_NOFF3] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1};
@@ -70,7 +72,7 @@ __device__ __noinline__ void first2_scale_boundary(double* v, const InvDiag27& i
 }
 
 template <int MODE, int TX, int TY, int RY, int NS, bool TMA>
-__global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
+__global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 128 ? 8 : (TX * TY / RY <= 256 ? 4 : 2)))
     k3_scalar_tma(const __grid_constant__ ScalarMaps M, const __grid_constant__ ScalarParams P) {
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2: the TMA box start (x0-2) must be 16-byte aligned
   constexpr int NT = TX * (TY / RY), ROWS = TY / RY;
@@ -179,8 +181,15 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
   bool valid[RY], deep_xy[RY];
   int txy[RY], cidx[RY];
   long long idx[RY];
-  double pa[RY][4];  // plane k-1: c, c-W, c-1, c-W-1
-  double pb[RY][4];  // plane k  : c, c+W, c+1, c+W+1
+  // z-march register reuse (MODE 0, 2): the operands of planes k-1 and k a thread has already loaded.  MODE 3 spends
+  // the registers on its operand scales instead and reads all 15 operands from shared memory.
+  constexpr bool REUSE = MODE != 3;
+  double pa[REUSE ? RY : 1][4];  // plane k-1: c, c-W, c-1, c-W-1
+  double pb[REUSE ? RY : 1][4];  // plane k  : c, c+W, c+1, c+W+1
+  // MODE 3: scale b0 / diag of the row of each of the 7 distinct x-y neighbours (0,0) (1,0) (-1,0) (0,1) (0,-1) (1,1) (-1,-1)
+  // on a plane away from the z boundaries; fixed per thread, so the vertices next to an x or y boundary cost 15
+  // multiplications instead of a table walk per plane
+  double sc[MODE == 3 ? RY : 1][7];
   mbar_wait(&bars[0], 0);
   mbar_wait(&bars[1 % NS], (1 / NS) & 1);
   {
@@ -196,14 +205,28 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
       idx[rr] = (long long)zb * m.nxy + (long long)iy * m.nxv + ix;
       const int c = (ly + 1) * W + threadIdx.x + 2;
       cidx[rr] = c;
-      pa[rr][0] = S0[c]; pa[rr][1] = S0[c - W]; pa[rr][2] = S0[c - 1]; pa[rr][3] = S0[c - W - 1];
-      pb[rr][0] = S1[c]; pb[rr][1] = S1[c + W]; pb[rr][2] = S1[c + 1]; pb[rr][3] = S1[c + W + 1];
+      if constexpr (REUSE) {
+        pa[rr][0] = S0[c]; pa[rr][1] = S0[c - W]; pa[rr][2] = S0[c - 1]; pa[rr][3] = S0[c - W - 1];
+        pb[rr][0] = S1[c]; pb[rr][1] = S1[c + W]; pb[rr][2] = S1[c + 1]; pb[rr][3] = S1[c + W + 1];
+      }
+      if constexpr (MODE == 3) {
+        constexpr int DX7[7] = {0, 1, -1, 0, 0, 1, -1}, DY7[7] = {0, 0, 0, 1, -1, 1, -1};
+        auto cls = [](int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); };
+#pragma unroll
+        for (int j = 0; j < 7; ++j) sc[rr][j] = P.b0 * P.invd.v[9 + 3 * cls(iy + DY7[j], m.nyv) + cls(ix + DX7[j], m.nxv)];
+      }
     }
   }
 
   for (int k = 0; k < nout; ++k) {
-    __syncthreads();  // every thread has read plane k (kept in registers from here on): its stage may be refilled
-    if (k + NS < nplanes) issue(k + NS);
+    // REUSE: every thread has read plane k (kept in registers from here on), its stage may be refilled; otherwise plane k
+    // is still read in this iteration and the stage of plane k-1 is the free one
+    __syncthreads();
+    if constexpr (REUSE) {
+      if (k + NS < nplanes) issue(k + NS);
+    } else {
+      if (k >= 1 && k - 1 + NS < nplanes) issue(k - 1 + NS);
+    }
     if (k + NR - 1 < nout) issue_ro(k + NR - 1);
     mbar_wait(&bars[(k + 2) % NS], ((k + 2) / NS) & 1);
     if (has_ro) mbar_wait(&bars_ro[k % NR], (k / NR) & 1);
@@ -223,22 +246,38 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
       const double rv = P.has_r ? Rt[pc] : 0.0;
       const double ov = P.has_o ? Ot[pc] : 0.0;
       double v[PFH_NOFF3];
-      v[0] = pb[rr][0]; v[3] = pb[rr][1]; v[1] = pb[rr][2]; v[7] = pb[rr][3];
-      v[2] = S1[c - 1]; v[4] = S1[c - W]; v[8] = S1[c - W - 1];
-      v[6] = pa[rr][0]; v[10] = pa[rr][1]; v[12] = pa[rr][2]; v[14] = pa[rr][3];
-      v[5] = S2[c]; v[9] = S2[c + W]; v[11] = S2[c + 1]; v[13] = S2[c + W + 1];
-      // the march: plane k becomes plane k-1, plane k+1 becomes plane k
-      pa[rr][0] = v[0]; pa[rr][1] = v[4]; pa[rr][2] = v[2]; pa[rr][3] = v[8];
-      pb[rr][0] = v[5]; pb[rr][1] = v[9]; pb[rr][2] = v[11]; pb[rr][3] = v[13];
+      double self;
+      if constexpr (REUSE) {
+        v[0] = pb[rr][0]; v[3] = pb[rr][1]; v[1] = pb[rr][2]; v[7] = pb[rr][3];
+        v[2] = S1[c - 1]; v[4] = S1[c - W]; v[8] = S1[c - W - 1];
+        v[6] = pa[rr][0]; v[10] = pa[rr][1]; v[12] = pa[rr][2]; v[14] = pa[rr][3];
+        v[5] = S2[c]; v[9] = S2[c + W]; v[11] = S2[c + 1]; v[13] = S2[c + W + 1];
+        // the march: plane k becomes plane k-1, plane k+1 becomes plane k
+        pa[rr][0] = v[0]; pa[rr][1] = v[4]; pa[rr][2] = v[2]; pa[rr][3] = v[8];
+        pb[rr][0] = v[5]; pb[rr][1] = v[9]; pb[rr][2] = v[11]; pb[rr][3] = v[13];
+      } else {
+        const double* S0 = ztile(k);
+        v[0] = S1[c]; v[1] = S1[c + 1]; v[2] = S1[c - 1]; v[3] = S1[c + W]; v[4] = S1[c - W];
+        v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
+        v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
+        v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
+      }
+      self = v[0];
       const int type = tzt * 9 + txy[rr];
       double Av, bd;
       double rc = 0.0, s1 = 0.0;  // MODE 3: r at this vertex; uniform operand scale b0 / diag when every neighbour is an interior row
-      if (MODE == 3) {
+      if constexpr (MODE == 3) {
         rc = v[0];
         if (deep_z && deep_xy[rr]) {
-          s1 = P.b0 * P.invd.v[13];
+          s1 = sc[rr][0];
+        } else if (deep_z) {
+          // next to an x or y boundary, away from the z boundaries: the per-thread scales of the 7 x-y neighbours
+          constexpr int J7[PFH_NOFF3] = {0, 1, 2, 3, 4, 0, 0, 5, 6, 3, 4, 1, 2, 5, 6};
+#pragma unroll
+          for (int o = 0; o < PFH_NOFF3; ++o) v[o] *= sc[rr][J7[o]];
+          s1 = 1.0;
         } else {
-          double t[PFH_NOFF3];  // the slow path works on a copy in local memory so that v stays in registers
+          double t[PFH_NOFF3];
 #pragma unroll
           for (int o = 0; o < PFH_NOFF3; ++o) t[o] = v[o];
           first2_scale_boundary(t, P.invd, P.b0, ix, y0 + ly, gz, m);
@@ -266,9 +305,9 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
       if (valid[rr]) {
         if (MODE == 0) {
           P.out[idx[rr]] = P.a * rv + Av;
-          if (P.out1 != nullptr) P.out1[idx[rr]] = v[0];
+          if (P.out1 != nullptr) P.out1[idx[rr]] = self;
         } else if (MODE == 2) {
-          P.out[idx[rr]] = pa[rr][0] + P.a * (pa[rr][0] - ov) + bd * (rv - Av);
+          P.out[idx[rr]] = self + P.a * (self - ov) + bd * (rv - Av);
         } else {
           const double z1 = s1 * v[0];
           P.out1[idx[rr]] = z1;
@@ -280,7 +319,7 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 256 ? 4 : 2))
   }
 }
 
-constexpr int S_TX = 64, S_TY = 8, S_RY = 1, S_NS = 4;
+constexpr int S_TX = 64, S_TY = 4, S_RY = 1, S_NS = 4;   // 256 threads, 4 CTAs per SM: the fastest of the variants at 512^3
 
 template <int TX, int TY, int NS>
 constexpr size_t scalar_smem() {
@@ -364,9 +403,15 @@ void pfh_scalar3_init_device() {
   scalar_set_attr<0, 64, 8, 1, 3>();
   scalar_set_attr<2, 64, 8, 1, 3>();
   scalar_set_attr<3, 64, 8, 1, 3>();
-  scalar_set_attr<0, 64, 4, 1, 4>();
-  scalar_set_attr<2, 64, 4, 1, 4>();
-  scalar_set_attr<3, 64, 4, 1, 4>();
+  scalar_set_attr<0, 64, 8, 1, 4>();
+  scalar_set_attr<2, 64, 8, 1, 4>();
+  scalar_set_attr<3, 64, 8, 1, 4>();
+  scalar_set_attr<0, 64, 4, 1, 5>();
+  scalar_set_attr<2, 64, 4, 1, 5>();
+  scalar_set_attr<3, 64, 4, 1, 5>();
+  scalar_set_attr<0, 64, 2, 1, 4>();
+  scalar_set_attr<2, 64, 2, 1, 4>();
+  scalar_set_attr<3, 64, 2, 1, 4>();
   scalar_set_attr<0, 128, 4, 1, 4>();
   scalar_set_attr<2, 128, 4, 1, 4>();
   scalar_set_attr<3, 128, 4, 1, 4>();
@@ -418,8 +463,10 @@ void k3_scalar_launch(pfh_ctx* c, const ScalarOp& op) {
   switch (c->scalar_variant) {
     case 1: scalar_launch<64, 8, 2, 4>(c, op, P, use_tma); break;   // two rows per thread: spills at 64 registers
     case 2: scalar_launch<64, 8, 1, 3>(c, op, P, use_tma); break;
-    case 3: scalar_launch<64, 4, 1, 4>(c, op, P, use_tma); break;
+    case 3: scalar_launch<64, 8, 1, 4>(c, op, P, use_tma); break;
     case 4: scalar_launch<128, 4, 1, 4>(c, op, P, use_tma); break;
+    case 5: scalar_launch<64, 4, 1, 5>(c, op, P, use_tma); break;
+    case 6: scalar_launch<64, 2, 1, 4>(c, op, P, use_tma); break;
     default: scalar_launch<S_TX, S_TY, S_RY, S_NS>(c, op, P, use_tma); break;
   }
 }

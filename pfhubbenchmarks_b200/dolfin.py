@@ -222,8 +222,18 @@ class Function:
             self._pending = ic
             return
         ctx = self._problem.ctx
-        if isinstance(ic, _IC):
-            ctx.initial_condition(ic.args, out=self._tensor)
+        if isinstance(ic, _IC) and ctx.problem in ic.kernel_problems:
+            ctx.initial_condition(ic.args, out=self._tensor)      # the problem's own expression: evaluated by its kernel
+        elif isinstance(ic, _IC):
+            # another benchmark's expression, or a generated model (whose kernel has no initial condition): the closed
+            # form on the host at the vertex coordinates, as DOLFIN's interpolate evaluates the UserExpression
+            import torch
+            if ctx.nranks != 1:
+                raise NotImplementedError("host-evaluated initial condition on a slab-decomposed mesh")
+            if ic.nvalues != ctx.nf:
+                raise ValueError("%s has %d components, the function space %d" % (type(ic).__name__, ic.nvalues, ctx.nf))
+            vals = ic.values(ctx.vertex_coordinates())
+            self._tensor.copy_(torch.from_numpy(np.ascontiguousarray(vals).reshape(-1)).to(self._tensor.device))
         elif isinstance(ic, UserExpression):
             self._tensor.copy_(_eval_user_expression(ic, ctx))
         else:

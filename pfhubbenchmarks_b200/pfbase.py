@@ -124,3 +124,8 @@ def euler_bwd_weak_form(u, u_, u0, dt, f):
 def h(u):
     """Interpolation polynomial u^3 (6u^2 - 15u + 10) of benchmark 2 (bench2.py:83-87)."""
     return u ** 3 * (6 * u ** 2 - 15 * u + 10)
+
+
+def dh(u):
+    """h'(u) = 30 u^2 (u - 1)^2, written as the reference writes it (pfbase.py:470-472): non-zero only in the interface."""
+    return 3 * u ** 2 * (6 * u ** 2 - 15 * u + 10) + u ** 3 * (12 * u - 15)

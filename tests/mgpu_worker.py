@@ -24,6 +24,9 @@ def main():
     n = grid - 1
     ncell, length = (n, n + 3, n), (2.0 * n, 2.0 * (n + 3), 2.0 * n)
     ctx = engine.Context("b13d", ncell, length, device=local, rank=rank, nranks=world, nccl_id=buf.cpu().numpy().tobytes())
+    # argv[2] = 0: one ghost-plane exchange per sweep instead of the wide-ghost preconditioner (both must equal 1 GPU)
+    wide = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    ctx.set_option("use_wide", wide)
     nxy = (ncell[0] + 1) * (ncell[1] + 1)
     assert ctx.n_owned == nxy * (ctx.z_range[1] - ctx.z_range[0])
     w = ctx.initial_condition()
@@ -71,9 +74,14 @@ def main():
         err = [np.linalg.norm(got[f] - ref[f]) / np.linalg.norm(ref[f]) for f in range(2)]
         de = abs(hist[-1][2] / ref_hist[-1][2] - 1)
         dm = abs(hist[-1][3] / ref_hist[-1][3] - 1)
-        print("mgpu world=%d grid=%d  rel L2 (c, mu) = %.2e %.2e  dE %.1e dM %.1e  its %s vs %s" % (
-            world, grid, err[0], err[1], de, dm, hist, ref_hist), flush=True)
-        ok = err[0] < 1e-10 and err[1] < 1e-8 and de < 1e-11 and dm < 1e-13
+        print("mgpu world=%d grid=%d wide=%d  rel L2 (c, mu) = %.2e %.2e  dE %.1e dM %.1e  its %s vs %s" % (
+            world, grid, wide, err[0], err[1], de, dm, [h[:2] for h in hist], [h[:2] for h in ref_hist]), flush=True)
+        # N-GPU == 1-GPU to 1e-12 (the two runs differ only in the summation order of the
+        # allreduced dot products); identical Newton counts, Krylov counts within one iteration per Newton step (the last
+        # Newton iteration solves to 1e-9 of a residual that is itself at round-off level, where the stopping test is
+        # decided by the last bits)
+        ok = err[0] < 1e-12 and err[1] < 1e-10 and de < 1e-12 and dm < 1e-13
+        ok = ok and all(a[0] == b[0] and abs(a[1] - b[1]) <= a[0] + 1 for a, b in zip(hist, ref_hist))
         dv = float(np.max(np.abs(vals - one.eval_points(v, 0, pts))))
         q1 = one.bilinear(v, 0, 1, 0.5, 2.0)
         v0 = v.clone()

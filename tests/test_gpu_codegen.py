@@ -67,6 +67,35 @@ def test_generated_model_steps_match_oracle():
     problem.ctx.close()
 
 
+def test_shipped_initial_condition_on_a_generated_model():
+    """A reference _IC class handed to a generated model is interpolated on the host from its closed form (the generated
+    kernel has no initial condition of its own); on a shipped problem of ANOTHER benchmark it is evaluated the same way
+    instead of silently running that problem's kernel formula; a component-count mismatch raises."""
+    import pfhubbenchmarks_b200.dolfin as df
+    from pfhubbenchmarks_b200 import api
+    from pfhubbenchmarks_b200.drivers import custom_model as cm
+    from pfhubbenchmarks_b200.pfbase import InitialConditionsBench1, InitialConditionsBench6
+    ncell, length = (12, 10), (24.0, 20.0)
+    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(*length), *ncell, "crossed")
+    problem, solver, _, _ = cm.setup(mesh)                                  # three fields, generated
+    ic6 = InitialConditionsBench6(0.5, 0.04, degree=2)
+    problem.w.interpolate(ic6)
+    xy = omesh.crossed2d(*ncell, *length).coords
+    got = problem.w.to_numpy()
+    assert np.array_equal(got, ic6.values(xy)) and np.abs(got[0] - 0.5).max() > 0.01
+    with pytest.raises(ValueError):
+        problem.w.interpolate(InitialConditionsBench1(0.5, 0.05, degree=2))  # two components into three fields
+    problem.ctx.close()
+    # thin API: benchmark 1's expression on a bench1 problem runs the kernel; benchmark 6's does not fit two fields
+    p1 = api.NonlinearVariationalProblem("bench1", api.RectangleMesh(api.Point(0.0, 0.0), api.Point(*length), *ncell, "crossed"), api.Constant(0.1))
+    ic1 = InitialConditionsBench1(0.5, 0.05)
+    p1.w.interpolate(ic1)
+    assert np.allclose(p1.w.to_numpy(), ic1.values(xy), rtol=0, atol=1e-14)
+    with pytest.raises(ValueError):
+        p1.w.interpolate(ic6)
+    p1.ctx.close()
+
+
 def test_reduced_ostwald_driver(tmp_path):
     """`python -m pfhubbenchmarks_b200.drivers.bench2_eta --num-eta 1`: the reference's bench2_eta1 model end to end as a
     generated model with the host-evaluated ICB2_jank1 initial data: converges, solute conserved, energy decays."""
