@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PFH_ABI_VERSION 1
+#define PFH_ABI_VERSION 2
 
 /* mesh kinds: df.RectangleMesh(..., 'crossed') (dolfin/bench1.py:23), df.BoxMesh (dolfin/b13d.py:26) */
 enum { PFH_MESH_CROSSED2D = 2, PFH_MESH_KUHN3D = 3 };
@@ -83,6 +83,7 @@ typedef struct {
   int pc_sweeps_mass;            /* Chebyshev sweeps per mass solve */
   int pc_sweeps_shifted;         /* Chebyshev sweeps per (M + alpha K) solve; 0 = automatic (5; 4 in 3-D) */
   int verbose;                   /* 1: print Newton/Krylov history to stderr */
+  int linear_solver;             /* 0 = 'gmres' (drivers, bench1.py:98), 1 = 'bicgstab' (bench2_eta1.py:113); ABI 2 */
 } pfh_solver_opts;
 
 typedef struct {

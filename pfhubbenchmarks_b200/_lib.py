@@ -26,7 +26,8 @@ class SolverOpts(C.Structure):
                 ("solution_tolerance", C.c_double), ("maximum_iterations", C.c_int), ("line_search", C.c_int),
                 ("krylov_rtol", C.c_double), ("krylov_atol", C.c_double), ("krylov_maximum_iterations", C.c_int),
                 ("krylov_restart", C.c_int), ("preconditioner", C.c_int), ("pc_variant", C.c_int),
-                ("pc_sweeps_mass", C.c_int), ("pc_sweeps_shifted", C.c_int), ("verbose", C.c_int)]
+                ("pc_sweeps_mass", C.c_int), ("pc_sweeps_shifted", C.c_int), ("verbose", C.c_int),
+                ("linear_solver", C.c_int)]
 
 
 class SolveReport(C.Structure):
@@ -38,6 +39,7 @@ class SolveReport(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+ABI_VERSION = 2      # PFH_ABI_VERSION of include/pfh_b200.h (2: pfh_solver_opts.linear_solver)
 _P = C.c_void_p
 # name -> (restype, argtypes); every symbol include/pfh_b200.h declares
 SIGNATURES = {
@@ -95,7 +97,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.pfh_abi_version() != 1:
+    if lib.pfh_abi_version() != ABI_VERSION:
         raise PfhError("ABI version mismatch")
     _lib = lib
     return lib
@@ -114,7 +116,7 @@ def load_user(path):
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.pfh_abi_version() != 1:
+    if lib.pfh_abi_version() != ABI_VERSION:
         raise PfhError("ABI version mismatch")
     _user_libs[path] = lib
     return lib

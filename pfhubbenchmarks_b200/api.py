@@ -250,8 +250,10 @@ class NonlinearVariationalSolver:
         ls = p["line_search"]
         if ls not in _LINE_SEARCH:
             warnings.warn("line_search %r is not implemented; using 'basic' (full Newton step)" % (ls,))
-        if p["linear_solver"] not in ("gmres", "default"):
+        lin = {"gmres": 0, "default": 0, "bicgstab": 1}.get(p["linear_solver"])      # bench1.py:98, bench2_eta1.py:113
+        if lin is None:
             warnings.warn("linear_solver %r is not implemented; using gmres" % (p["linear_solver"],))
+            lin = 0
         pc = {"schur_chebyshev": 0, "sor": 0, "default": 0, "jacobi": 1, "none": 2}.get(p["preconditioner"])
         if pc is None:
             warnings.warn("preconditioner %r is not implemented; using the Schur/Chebyshev preconditioner" % (p["preconditioner"],))
@@ -261,7 +263,8 @@ class NonlinearVariationalSolver:
             solution_tolerance=float(p["solution_tolerance"]), maximum_iterations=int(p["maximum_iterations"]),
             krylov_rtol=float(k["relative_tolerance"]), krylov_atol=float(k["absolute_tolerance"]),
             krylov_maximum_iterations=int(k["maximum_iterations"]),
-            krylov_restart=min(int(k["restart"]), 30), preconditioner=pc, line_search=_LINE_SEARCH.get(ls, 0), verbose=0)
+            krylov_restart=min(int(k["restart"]), 30), preconditioner=pc, line_search=_LINE_SEARCH.get(ls, 0), verbose=0,
+            linear_solver=lin)
 
     def solve(self):
         """niters, converged = solver.solve()  (bench1.py:162). In place on problem.w; never raises on non-convergence

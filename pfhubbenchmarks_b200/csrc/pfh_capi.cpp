@@ -88,6 +88,7 @@ void pfh_default_solver_opts(pfh_solver_opts* o) {
   o->pc_sweeps_mass = 3;
   o->pc_sweeps_shifted = 0;   // automatic: 5, or 4 in 3-D where the Chebyshev interval comes from the operator's symbol (pfh_solver.cpp)
   o->verbose = 0;
+  o->linear_solver = 0;
 }
 
 int pfh_nccl_unique_id(void* out) {
@@ -296,6 +297,7 @@ int pfh_precond_apply_dev(pfh_ctx* c, const double* r, double* z) {
   PFH_CUDA(cudaSetDevice(c->cfg.device));
   s_precond_apply(c, r, z);
   PFH_CUDA(cudaStreamSynchronize(c->stream));
+  c->gX_prefetched = nullptr;   // the caller owns z from here on: its ghost planes are exchanged again when it is used
   PFH_API_END
 }
 

@@ -111,20 +111,21 @@ void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, d
   ck(api().GroupEnd(), "ncclGroupEnd");
 }
 
-void comm_halo_n(pfh_ctx* c, const double* base, int nplanes, double* glo, double* ghi) {
+void comm_halo_n(pfh_ctx* c, const double* base, int nplanes, double* glo, double* ghi, cudaStream_t stream) {
   if (!c->comm) return;
-  ProfScope ps(c, T_HALO);
+  cudaStream_t st = stream ? stream : c->stream;
+  ProfScope ps(c, T_HALO, 0.0, st);
   const Comm* cm = c->comm;
   const size_t cnt = (size_t)nplanes * c->nplane;
   const long long last = (long long)(c->m3.nzl - nplanes) * c->nplane;
   ck(api().GroupStart(), "ncclGroupStart");
   if (cm->rank > 0) {
-    ck(api().Send(base, cnt, ncclDouble, cm->rank - 1, cm->comm, c->stream), "ncclSend");
-    ck(api().Recv(glo, cnt, ncclDouble, cm->rank - 1, cm->comm, c->stream), "ncclRecv");
+    ck(api().Send(base, cnt, ncclDouble, cm->rank - 1, cm->comm, st), "ncclSend");
+    ck(api().Recv(glo, cnt, ncclDouble, cm->rank - 1, cm->comm, st), "ncclRecv");
   }
   if (cm->rank < cm->nranks - 1) {
-    ck(api().Send(base + last, cnt, ncclDouble, cm->rank + 1, cm->comm, c->stream), "ncclSend");
-    ck(api().Recv(ghi, cnt, ncclDouble, cm->rank + 1, cm->comm, c->stream), "ncclRecv");
+    ck(api().Send(base + last, cnt, ncclDouble, cm->rank + 1, cm->comm, st), "ncclSend");
+    ck(api().Recv(ghi, cnt, ncclDouble, cm->rank + 1, cm->comm, st), "ncclRecv");
   }
   ck(api().GroupEnd(), "ncclGroupEnd");
 }

@@ -141,6 +141,8 @@ struct pfh_ctx {
   cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr;
   bool overlap = true;
   const double* gS_prefetched = nullptr;  // scalar field whose ghost planes are already travelling into gS (ev_halo)
+  const double* gX_prefetched = nullptr;  // state vector whose ghost planes are already travelling into gX (ev_halo): the
+                                          // wide-ghost preconditioner ships its result for the J.v that follows
   double* d_tables = nullptr;
 
   // workspaces (device)
@@ -241,10 +243,12 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
 // z = b * Dinv r,  D = diag(am M + ak K)
 void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z);
 // first two Chebyshev iterates from r alone (3-D TMA path): z1 = b0 D^-1 r, z2 = z1 + a1 z1 + b1 D^-1 (r - A z1); false = not available
+// (z1 may be null: the third iterate can recompute it from r, see k_cheb_sweep)
 bool k_cheb_first2(pfh_ctx* c, double am, double ak, double b0, double a1, double b1, FieldRef r, double* z1, double* z2);
 // zprev <- z + a (z - zprev) + b Dinv (r - (am M + ak K) z)
+// zprev_is_zero: zprev is write-only, z_{k-1} = 0; or, with zprev_b0 != 0 (staged 3-D kernel only), z_{k-1} = zprev_b0 Dinv r
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z,
-                  double* zprev, bool zprev_is_zero);  // zprev_is_zero: zprev is write-only (z_{k-1} = 0)
+                  double* zprev, bool zprev_is_zero, double zprev_b0 = 0.0);
 // point-Jacobi on the Jacobian diagonal blocks: z_a = r_a / diag_a
 void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z);
 void k_eval_points(pfh_ctx* c, FieldRef f, const double* pts, long long npts, double* out);  // pfh_sample.cu
@@ -269,6 +273,7 @@ struct ScalarOp {
   int mode = 0;                    // 0: out = a r + A in [out1 = in]; 2: out = in + a (in - o) + b D^-1 (r - A in);
                                    // 3: out1 = b0 D^-1 in, out = out1 + a out1 + b D^-1 (in - A out1)
   double am = 0, ak = 0, a = 0, b = 0, b0 = 0;
+  double ob0 = 0;                  // mode 2 with o == nullptr: o = ob0 D^-1 r, recomputed from r (0: o = 0)
   const double* in = nullptr;
   int in_off = 0, in_n = 0;
   const double* in_lo = nullptr;
@@ -328,7 +333,7 @@ void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, d
                cudaStream_t stream = nullptr);  // stream == nullptr: the ctx stream
 // exchange the first / last `nplanes` planes of one scalar field (ghost width nplanes): glo receives the lower
 // neighbour's last planes, ghi the upper neighbour's first planes
-void comm_halo_n(pfh_ctx* c, const double* base, int nplanes, double* glo, double* ghi);
+void comm_halo_n(pfh_ctx* c, const double* base, int nplanes, double* glo, double* ghi, cudaStream_t stream = nullptr);
 int comm_unique_id(void* out);
 
 // ---- solver (pfh_solver.cpp) ----

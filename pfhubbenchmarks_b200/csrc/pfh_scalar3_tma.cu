@@ -4,6 +4,7 @@
 //
 //   MODE 0  out = a*add + A in   [out1 = in]                          (lin_apply)                16-24 B/vertex
 //   MODE 2  out = z + a (z - zprev) + b D^-1 (r - A z)                  (Jacobi-Chebyshev sweep)   32 B/vertex
+//           (zprev either loaded, or -- third iterate -- recomputed as b0 D^-1 r from the r it reads anyway: 24 B/vertex)
 //   MODE 3  z1 = b0 D^-1 r ; z2 = z1 + a z1 + b D^-1 (r - A z1)         (first two iterates from r alone) 24 B/vertex
 //
 // One CTA owns a TX x TY tile of the x-y plane and marches along z over `zchunk` planes.  Every plane of the stencil
@@ -43,6 +44,7 @@ struct ScalarParams {
   int has_r, has_o;
   int r_off, r_n, r_nlo, r_nhi;  // pointwise operand r: same addressing as the stencil operand
   double am, ak, a, b, bdI, b0;
+  double ob0;                  // MODE 2 without a zprev operand: zprev = ob0 D^-1 r (0: zprev = 0)
   Coef15 cI;
   InvDiag27 invd;
   double* out;                 // launch-local plane 0
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 128 ? 8 : (TX *
       const int c = cidx[rr];
       const int pc = ly * TX + threadIdx.x;
       const double rv = P.has_r ? Rt[pc] : 0.0;
-      const double ov = P.has_o ? Ot[pc] : 0.0;
+      double ov = P.has_o ? Ot[pc] : 0.0;
       double v[PFH_NOFF3];
       double self;
       if constexpr (REUSE) {
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 128 ? 8 : (TX *
       }
       self = v[0];
       const int type = tzt * 9 + txy[rr];
+      if (MODE == 2 && P.ob0 != 0.0) ov = (P.ob0 * P.invd.v[type]) * rv;  // the first iterate, exactly as MODE 3 stores it
       double Av, bd;
       double rc = 0.0, s1 = 0.0;  // MODE 3: r at this vertex; uniform operand scale b0 / diag when every neighbour is an interior row
       if constexpr (MODE == 3) {
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(TX*(TY / RY), (TX * TY / RY <= 128 ? 8 : (TX *
           P.out[idx[rr]] = self + P.a * (self - ov) + bd * (rv - Av);
         } else {
           const double z1 = s1 * v[0];
-          P.out1[idx[rr]] = z1;
+          if (P.out1 != nullptr) P.out1[idx[rr]] = z1;
           P.out[idx[rr]] = z1 + P.a * z1 + bd * (rc - s1 * Av);
         }
       }
@@ -440,8 +443,8 @@ void k3_scalar_launch(pfh_ctx* c, const ScalarOp& op) {
   P.am = op.am; P.ak = op.ak; P.a = op.a; P.b = op.b; P.b0 = op.b0;
   for (int o = 0; o < PFH_NOFF3; ++o) P.cI.c[o] = op.am * m.mI[o] + (o < PFH_NKOFF3 ? op.ak * m.kI[o] : 0.0);
   P.bdI = op.b / P.cI.c[0];
-  if (op.mode == 3) {
-    PFH_CHECK(op.out1 != nullptr, "scalar operator: first-two launch needs both outputs");
+  P.ob0 = (op.mode == 2 && op.o == nullptr) ? op.ob0 : 0.0;
+  if (op.mode == 3 || P.ob0 != 0.0) {
     if (c->h_mT.empty()) {  // host copy of the type tables, for the inverse diagonals
       Mesh3 mm = m;
       pfh_build_tables3(mm, c->h_mT, c->h_kT);

@@ -63,7 +63,13 @@ void s_jac_setup(pfh_ctx* c, const double* u) {
 
 void s_jac_apply(pfh_ctx* c, const double* x, double* y) {
   PFH_CHECK(c->jac_point != nullptr, "jac_apply before jac_setup");
-  s_exchange_state(c, x, c->gX_lo, c->gX_hi);
+  if (c->cfg.nranks > 1 && c->gX_prefetched == x) {
+    // the producer (wide-ghost preconditioner) already sent these ghost planes on comm_stream: order the consumer after them
+    PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  } else {
+    s_exchange_state(c, x, c->gX_lo, c->gX_hi);
+  }
+  c->gX_prefetched = nullptr;
   k_jac_apply(c, c->jac_point, x, y);
 }
 
@@ -124,14 +130,17 @@ void cheb_solve(pfh_ctx* c, double am, double ak, double lmin, double lmax, int 
   // 3-D fast path: the first two iterates come out of one pass over r (k_cheb_first2), the loop then starts at k = 2
   const bool first2 = nsweeps >= 2 && c->use_first2 && pfh_fast3_ok(c);
   int k0 = 1;
-  if (first2 && k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, scalar_ref(c, r), cur, prev)) {
+  // with more than two sweeps the first iterate is never stored: the third one recomputes it from r (which it reads anyway)
+  const bool skip_z1 = nsweeps >= 3;
+  if (first2 && k_cheb_first2(c, am, ak, cf[0].b, cf[1].a, cf[1].b, scalar_ref(c, r), skip_z1 ? nullptr : cur, prev)) {
     std::swap(cur, prev);
     k0 = 2;
   } else {
     k_cheb_first(c, am, ak, cf[0].b, r, cur);
   }
   for (int k = k0; k < nsweeps; ++k) {
-    k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev, k == 1);
+    const bool from_r = k0 == 2 && k == 2;
+    k_cheb_sweep(c, am, ak, cf[k].a, cf[k].b, r, scalar_ref(c, cur), prev, k == 1 || from_r, from_r ? cf[0].b : 0.0);
     std::swap(cur, prev);
   }
   PFH_CHECK(cur == target, "internal: chebyshev ping-pong parity");
@@ -168,11 +177,11 @@ WideOperand ext_op(const double* p) { return WideOperand{p, true, nullptr, nullp
 const WideOperand kNoOperand{nullptr, true, nullptr, nullptr, 0};
 
 void wide_launch(pfh_ctx* c, int timer, double bytes_per_vertex, int mode, double am, double ak, double a, double b, double b0,
-                 const WideOperand& in, const WideOperand& r, const double* o, double* out, double* out1, Win w) {
+                 const WideOperand& in, const WideOperand& r, const double* o, double* out, double* out1, Win w, double ob0 = 0.0) {
   const Mesh3& m = c->m3;
   const bool has_lo = c->cfg.rank > 0, has_hi = c->cfg.rank < c->cfg.nranks - 1;
   ScalarOp op;
-  op.mode = mode; op.am = am; op.ak = ak; op.a = a; op.b = b; op.b0 = b0;
+  op.mode = mode; op.am = am; op.ak = ak; op.a = a; op.b = b; op.b0 = b0; op.ob0 = ob0;
   if (in.ext) {
     const int elo = has_lo ? c->gw : 0, ehi = has_hi ? c->gw : 0;
     op.in = in.p - (long long)elo * m.nxy;
@@ -214,21 +223,56 @@ void wide_exchange(pfh_ctx* c, const double* p, bool ext, int w) {
   else comm_halo_n(c, p, w, c->gR_lo, c->gR_hi);
 }
 
+// Halo/compute overlap of the wide path: a producer whose result must travel computes the `bw` planes next to each
+// slab face first; their exchange runs on the high-priority comm_stream while the interior planes are computed on the
+// ctx stream; the consumer is ordered after the exchange (ev_halo).  `launch(Win)` computes a window of the result,
+// `exchange(stream)` ships it.
+template <class Launch, class Exchange>
+void produce_and_ship(pfh_ctx* c, int bw, Launch launch, Exchange exchange) {
+  const Mesh3& m = c->m3;
+  if (!c->overlap || c->comm_stream == nullptr || m.nzl < 2 * bw + 2) {
+    launch(Win{0, m.nzl});
+    exchange(c->stream);
+    return;
+  }
+  launch(Win{0, bw});
+  launch(Win{m.nzl - bw, m.nzl});
+  PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+  PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+  exchange(c->comm_stream);
+  PFH_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+  launch(Win{bw, m.nzl - bw});
+  PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+}
+
 // z_n = p_{n-1}(D^-1 A) D^-1 rhs on the window of depth d_out.  `rhs` must be valid to depth d_out + n - 1; iterates
 // alternate between the ext vectors bufA / bufB; the last sweep writes `out` (any vector that covers the window).
+// `last(Win)`, when given, replaces the plain launch of the last sweep: the caller splits it to ship the result early.
+struct LastSweep {
+  double am, ak, a, b, ob0;
+  WideOperand z, rhs;
+  const double* zprev;
+  double* out;
+};
 void cheb_solve_wide(pfh_ctx* c, double am, double ak, double lmin, double lmax, int n, const WideOperand& rhs, int d_out,
-                     double* bufA, double* bufB, double* out) {
+                     double* bufA, double* bufB, double* out, LastSweep* defer_last = nullptr) {
   PFH_CHECK(n >= 2, "internal: wide Chebyshev solve needs at least two sweeps");
   const std::vector<ChebCoef> cf = cheb_coeffs(lmin, lmax, n);
-  // first two iterates on the window of depth d_out + n - 2; if n == 2 the second one is the result
+  // first two iterates on the window of depth d_out + n - 2; if n == 2 the second one is the result.  With n >= 3 the
+  // first iterate is not stored: the third one recomputes it from the right-hand side it reads anyway.
   double* z1 = bufA;
   double* z2 = n == 2 ? out : bufB;
-  wide_launch(c, T_CHEB_FIRST, 24.0, 3, am, ak, cf[1].a, cf[1].b, cf[0].b, rhs, kNoOperand, nullptr, z2, z1, win_of(c, d_out + n - 2));
+  wide_launch(c, T_CHEB_FIRST, n == 2 ? 24.0 : 16.0, 3, am, ak, cf[1].a, cf[1].b, cf[0].b, rhs, kNoOperand, nullptr, z2, n == 2 ? z1 : nullptr,
+              win_of(c, d_out + n - 2));
   double *cur = z2, *prev = z1;
   for (int k = 2; k < n; ++k) {
     double* dst = k == n - 1 ? out : prev;  // in place over z_{k-1} except for the last sweep
-    wide_launch(c, T_CHEB_SWEEP, 32.0, 2, am, ak, cf[k].a, cf[k].b, 0.0, ext_op(cur), rhs, prev, dst, nullptr,
-                win_of(c, d_out + n - 1 - k));
+    if (k == n - 1 && defer_last != nullptr) {
+      *defer_last = LastSweep{am, ak, cf[k].a, cf[k].b, k == 2 ? cf[0].b : 0.0, ext_op(cur), rhs, k == 2 ? nullptr : prev, dst};
+      return;
+    }
+    wide_launch(c, T_CHEB_SWEEP, k == 2 ? 24.0 : 32.0, 2, am, ak, cf[k].a, cf[k].b, 0.0, ext_op(cur), rhs, k == 2 ? nullptr : prev, dst, nullptr,
+                win_of(c, d_out + n - 1 - k), k == 2 ? cf[0].b : 0.0);
     prev = cur;
     cur = dst;
   }
@@ -297,7 +341,7 @@ struct ScalarModGuard {
 // the wide-ghost Schur preconditioner applies when the slabs are thick enough for the widest exchange
 bool wide_ok(const pfh_ctx* c, const PcLayout& L, int nM, int nA) {
   return c->cfg.nranks > 1 && c->use_wide && pfh_fast3_ok(c) && c->prob.id == PFH_PROBLEM_CH && L.has_ch && c->pc_opts.pc_variant == 1 &&
-         nM >= 2 && nA >= 2 && std::max(nM, nA) <= std::min(c->gw, c->min_slab);
+         nM >= 2 && nA >= 3 && std::max(nM, nA) <= std::min(c->gw, c->min_slab);
 }
 
 // Block upper-triangular Schur preconditioner of the (c, mu) pair with three wide exchanges (r_mu, q, M y) instead of
@@ -310,15 +354,30 @@ void precond_apply_ch_wide(pfh_ctx* c, const PcLayout& L, int nM, int nA, const 
   // t = M^-1 r_mu to depth 1 (K t is needed on the owned planes): r_mu travels at width nM
   wide_exchange(c, r2, false, nM);
   cheb_solve_wide(c, 1.0, 0.0, c->lmin_m, c->lmax_m, nM, WideOperand{r2, false, c->gR_lo, c->gR_hi, nM}, 1, S1, S3, S0);
-  // q = dt r_c - dt Mob K t on the owned planes; the same pass copies t into z_mu (dmu = t)
-  wide_launch(c, T_LIN_APPLY, 32.0, 0, 0.0, -dt * L.Mob, dt, 0.0, 0.0, ext_op(S0), ext_op(r1), nullptr, S2, z + n, win_of(c, 0));
-  // y = A^-1 q to depth 1 (M y is needed on the owned planes): q travels at width nA
-  wide_exchange(c, S2, true, nA);
+  // q = dt r_c - dt Mob K t on the owned planes; the same pass copies t into z_mu (dmu = t).
+  // y = A^-1 q to depth 1 (M y is needed on the owned planes): q travels at width nA, under the interior planes of its producer
+  const Mesh3& m = c->m3;
+  auto ship_S2 = [&](int w) {
+    return [c, S2, w, &m](cudaStream_t st) {
+      comm_halo_n(c, S2, w, S2 - (long long)w * m.nxy, S2 + (long long)m.nzl * m.nxy, st);
+    };
+  };
+  produce_and_ship(c, nA, [&](Win w) {
+    wide_launch(c, T_LIN_APPLY, 32.0, 0, 0.0, -dt * L.Mob, dt, 0.0, 0.0, ext_op(S0), ext_op(r1), nullptr, S2, z + n, w);
+  }, ship_S2(nA));
   cheb_solve_wide(c, 1.0, alpha, c->lmin_a, c->lmax_a, nA, ext_op(S2), 1, S3, S4, S1);
-  wide_launch(c, T_LIN_APPLY, 16.0, 0, 1.0, 0.0, 0.0, 0.0, 0.0, ext_op(S1), kNoOperand, nullptr, S2, nullptr, win_of(c, 0));
   // dc = A^-1 (M y) on the owned planes: M y travels at width nA - 1
-  wide_exchange(c, S2, true, nA - 1);
-  cheb_solve_wide(c, 1.0, alpha, c->lmin_a, c->lmax_a, nA, ext_op(S2), 0, S3, S4, z);
+  produce_and_ship(c, nA - 1, [&](Win w) {
+    wide_launch(c, T_LIN_APPLY, 16.0, 0, 1.0, 0.0, 0.0, 0.0, 0.0, ext_op(S1), kNoOperand, nullptr, S2, nullptr, w);
+  }, ship_S2(nA - 1));
+  // the last sweep writes dc = z_c; its slab-face planes go first and the ghost planes of z = (dc, dmu) travel into gX under
+  // the interior planes, for the J.v that follows a preconditioner application in GMRES
+  LastSweep ls;
+  cheb_solve_wide(c, 1.0, alpha, c->lmin_a, c->lmax_a, nA, ext_op(S2), 0, S3, S4, z, &ls);
+  produce_and_ship(c, 1, [&](Win w) {
+    wide_launch(c, T_CHEB_SWEEP, ls.zprev ? 32.0 : 24.0, 2, ls.am, ls.ak, ls.a, ls.b, 0.0, ls.z, ls.rhs, ls.zprev, ls.out, nullptr, w, ls.ob0);
+  }, [c, z](cudaStream_t st) { comm_halo(c, z, c->n_owned, c->nf, c->gX_lo, c->gX_hi, st); });
+  c->gX_prefetched = z;
 }
 
 }  // namespace
@@ -382,6 +441,7 @@ void s_precond_setup(pfh_ctx* c, const pfh_solver_opts* o) {
 
 void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
   PFH_CHECK(c->pc_ready, "precond_apply before precond_setup");
+  c->gX_prefetched = nullptr;
   const long long n = c->n_owned;
   const pfh_solver_opts& o = c->pc_opts;
   if (o.preconditioner == 2) {
@@ -662,6 +722,69 @@ KspResult gmres_compressed(pfh_ctx* c, const double* b, double* x, const pfh_sol
   }
 }
 
+// Right-preconditioned BiCGStab (PETSc KSPBCGS, the reduced Ostwald drivers' choice: dolfin/bench2_eta1.py:113).  Two J.v and
+// two preconditioner applications per iteration, no growing basis: the orthogonalisation passes of GMRES are traded for
+// a second operator apply.  Work vectors live in the (otherwise idle) Krylov-basis allocation.  Dots are the fused
+// two-stage reductions of pfh_vec.cu (r^.v and v.v, t.s and t.t come out of one pass each).
+KspResult bicgstab(pfh_ctx* c, const double* b, double* x, const pfh_solver_opts& o, pfh_solve_report* rep) {
+  const long long N = c->nf * c->n_owned;
+  const long long vs = (N + 31) / 32 * 32;
+  PFH_CHECK(c->cfg.krylov_basis + 1 >= 6, "bicgstab needs a ctx created with krylov_basis >= 5 (six work vectors)");
+  double *r = c->V, *rhat = c->V + vs, *p = c->V + 2 * vs, *v = c->V + 3 * vs, *phat = c->V + 4 * vs, *shat = c->V + 5 * vs;
+  double* t = c->W1;
+  double d[2];
+  v_zero(c, x, N);
+  v_copy(c, r, b, N);
+  v_copy(c, rhat, b, N);
+  const double bnorm = std::sqrt(v_norm2(c, b, N));
+  if (bnorm == 0.0) return {0, 0.0, true};
+  const double tol = std::fmax(o.krylov_rtol * bnorm, o.krylov_atol);
+  double rho = 1.0, alpha = 1.0, omega = 1.0, rnorm = bnorm;
+  v_zero(c, p, N);
+  v_zero(c, v, N);
+  int its = 0;
+  while (its < o.krylov_maximum_iterations) {
+    v_multidot(c, rhat, 0, 1, r, N, d);                 // rhat . r
+    const double rho_new = d[0];
+    if (rho_new == 0.0 || !(rho_new == rho_new)) return {its, rnorm / bnorm, false};   // breakdown
+    const double beta = (rho_new / rho) * (alpha / omega);
+    v_axpby(c, 1.0, p, -omega, v, p, N);                // p = r + beta (p - omega v)
+    v_axpby(c, 1.0, r, beta, p, p, N);
+    s_precond_apply(c, p, phat);
+    rep->pc_applies++;
+    s_jac_apply(c, phat, v);
+    rep->jac_applies++;
+    v_multidot(c, rhat, 0, 1, v, N, d);                 // rhat . v
+    if (d[0] == 0.0 || !(d[0] == d[0])) return {its, rnorm / bnorm, false};
+    alpha = rho_new / d[0];
+    v_axpby(c, 1.0, r, -alpha, v, r, N);                // s = r - alpha v   (kept in r)
+    const double snorm = std::sqrt(v_norm2(c, r, N));
+    ++its;
+    if (snorm <= tol) {                                 // half step already converged
+      v_axpy(c, alpha, phat, x, N);
+      if (o.verbose > 1) fprintf(stderr, "      bicgstab it %3d  |s|/|b| = %.3e\n", its, snorm / bnorm);
+      return {its, snorm / bnorm, true};
+    }
+    s_precond_apply(c, r, shat);
+    rep->pc_applies++;
+    s_jac_apply(c, shat, t);
+    rep->jac_applies++;
+    v_multidot(c, r, 0, 1, t, N, d);                    // s . t and t . t in one pass
+    if (d[1] == 0.0) return {its, snorm / bnorm, false};
+    omega = d[0] / d[1];
+    v_axpy(c, alpha, phat, x, N);                       // x += alpha phat + omega shat
+    v_axpy(c, omega, shat, x, N);
+    v_axpy(c, -omega, t, r, N);                         // r = s - omega t
+    rnorm = std::sqrt(v_norm2(c, r, N));
+    if (o.verbose > 1) fprintf(stderr, "      bicgstab it %3d  |r|/|b| = %.3e\n", its, rnorm / bnorm);
+    if (!(rnorm == rnorm)) return {its, NAN, false};
+    if (rnorm <= tol) return {its, rnorm / bnorm, true};
+    if (omega == 0.0) return {its, rnorm / bnorm, false};
+    rho = rho_new;
+  }
+  return {its, rnorm / bnorm, false};
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -703,7 +826,7 @@ void s_newton(pfh_ctx* c, double* w, const double* w0, const pfh_solver_opts* op
     c->jac_point = U;  // ghosts of U are current from s_residual
     s_precond_setup(c, opts);
     v_scale(c, -1.0, c->R, c->B, N);
-    const KspResult ks = gmres(c, c->B, c->DX, o, rep);
+    const KspResult ks = o.linear_solver == 1 ? bicgstab(c, c->B, c->DX, o, rep) : gmres(c, c->B, c->DX, o, rep);
     rep->krylov_its += ks.its;
     rep->last_krylov_relres = ks.relres;
     if (o.verbose) fprintf(stderr, "    gmres: %d its, relres %.3e%s\n", ks.its, ks.relres, ks.converged ? "" : " (NOT converged)");

@@ -305,10 +305,10 @@ __global__ void __launch_bounds__(TPB) k2_dirichlet_copy(Mesh2 m, const double* 
 // the scalar operator on the owned planes of a slab through the staged kernel (pfh_scalar3_tma.cu): `in` with its
 // one-plane ghost arrays
 void scalar_owned(pfh_ctx* c, int mode, double am, double ak, double a, double b, double b0, FieldRef in, const double* r,
-                  const double* o, double* out, double* out1) {
+                  const double* o, double* out, double* out1, double ob0 = 0.0) {
   const Mesh3& m = c->m3;
   ScalarOp op;
-  op.mode = mode; op.am = am; op.ak = ak; op.a = a; op.b = b; op.b0 = b0;
+  op.mode = mode; op.am = am; op.ak = ak; op.a = a; op.b = b; op.b0 = b0; op.ob0 = ob0;
   op.in = in.p; op.in_off = 0; op.in_n = m.nzl;
   if (in.glo != nullptr && c->cfg.rank > 0) { op.in_lo = in.glo; op.n_lo = 1; }
   if (in.ghi != nullptr && c->cfg.rank < c->cfg.nranks - 1) { op.in_hi = in.ghi; op.n_hi = 1; }
@@ -493,18 +493,19 @@ void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, d
 
 bool k_cheb_first2(pfh_ctx* c, double am, double ak, double b0, double a1, double b1, FieldRef r, double* z1, double* z2) {
   if (!pfh_fast3_ok(c)) return false;
-  ProfScope ps(c, T_CHEB_FIRST, 24.0 * c->n_owned);
+  ProfScope ps(c, T_CHEB_FIRST, (z1 ? 24.0 : 16.0) * c->n_owned);
   scalar_owned(c, 3, am, ak, a1, b1, b0, r, nullptr, nullptr, z2, z1);
   return true;
 }
 
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev,
-                  bool zprev_is_zero) {
+                  bool zprev_is_zero, double zprev_b0) {
   ProfScope ps(c, T_CHEB_SWEEP, (zprev_is_zero ? 24.0 : 32.0) * c->n_owned);
   if (pfh_fast3_ok(c)) {
-    scalar_owned(c, 2, am, ak, a, b, 0.0, z, r, zprev_is_zero ? nullptr : zprev, zprev, nullptr);
+    scalar_owned(c, 2, am, ak, a, b, 0.0, z, r, zprev_is_zero ? nullptr : zprev, zprev, nullptr, zprev_is_zero ? zprev_b0 : 0.0);
     return;
   }
+  PFH_CHECK(zprev_b0 == 0.0, "internal: recomputed first iterate needs the staged 3-D kernel");
   if (c->dim == 3)
     k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero);
   else

@@ -49,7 +49,7 @@ def main():
     args = parse_args("bench2_eta%d" % num_eta, 20.0)
     mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(200.0, 200.0), 100, 100, "crossed")
     problem, solver, total_free_energy, total_solute = setup(mesh, num_eta)
-    snes_setup(solver, args.atol, "cp", 1000)
+    snes_setup(solver, args.atol, "bt", 1000, linear_solver="bicgstab")      # bench2_eta1.py:107,113
     w_ic = (ICB2_jank1 if num_eta == 1 else ICB2_jank2)(0.5, 0.05, 0.1, 1.5, degree=2)
     return time_loop(problem, solver, w_ic, 1e-2, 1e-4, args.end_time, os.path.join(args.outdir, "bench2_eta%d_out.csv" % num_eta),
                      "time,total_free_energy,total_solute", args.max_steps, args.quiet, functionals=(total_free_energy, total_solute))

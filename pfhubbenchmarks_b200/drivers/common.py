@@ -47,7 +47,7 @@ def mixed_p1(mesh, nfields):
     return W, df.Function(W), df.Function(W), df.TestFunction(W), df.TrialFunction(W)
 
 
-def snes_setup(solver, atol, line_search, krylov_max_it):
+def snes_setup(solver, atol, line_search, krylov_max_it, linear_solver='gmres'):
     """The parameter block every reference driver repeats (bench1.py:82-110)."""
     solver.parameters['nonlinear_solver'] = 'snes'
     nl = solver.parameters['snes_solver']
@@ -56,7 +56,7 @@ def snes_setup(solver, atol, line_search, krylov_max_it):
     nl['absolute_tolerance'] = atol
     nl['maximum_iterations'] = 10
     nl['line_search'] = line_search
-    nl['linear_solver'] = 'gmres'
+    nl['linear_solver'] = linear_solver   # 'gmres' in bench1/2/3/6 and b13d (bench1.py:98), 'bicgstab' in bench2_eta1/2
     nl['preconditioner'] = 'sor'          # mapped to the Schur/Chebyshev preconditioner
     nl['krylov_solver']['maximum_iterations'] = krylov_max_it
     nl['krylov_solver']['error_on_nonconvergence'] = False

@@ -226,7 +226,7 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
 void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, double* z) {
   scalar_all<1>(c, am, ak, 0.0, b, FieldRef{nullptr, nullptr, nullptr}, r, z, false);
 }
-void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev, bool zprev_is_zero) {
+void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev, bool zprev_is_zero, double) {
   scalar_all<2>(c, am, ak, a, b, z, r, zprev, zprev_is_zero);
 }
 void k_jacobi(pfh_ctx* c, const double*, const double* r, double* z) {
@@ -339,7 +339,7 @@ void v_combine32(pfh_ctx*, const float* V, long long stride, int nv, const doubl
 // ---- communication: single rank ----
 void comm_allreduce_sum(pfh_ctx*, double*, int) {}
 void comm_halo(pfh_ctx*, const double*, long long, int, double*, double*, cudaStream_t) {}
-void comm_halo_n(pfh_ctx*, const double*, int, double*, double*) {}
+void comm_halo_n(pfh_ctx*, const double*, int, double*, double*, cudaStream_t) {}
 
 // the solver itself, unchanged
 #include "../../pfhubbenchmarks_b200/csrc/pfh_solver.cpp"

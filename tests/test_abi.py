@@ -32,7 +32,7 @@ def test_binding_covers_header(lib_path):
     from pfhubbenchmarks_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.pfh_abi_version() == 1
+    assert lib.pfh_abi_version() == _lib.ABI_VERSION == 2
     o = _lib.default_opts()
     assert o.absolute_tolerance == 1e-6 and o.maximum_iterations == 10 and o.krylov_restart == 30
 

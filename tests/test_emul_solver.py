@@ -33,6 +33,23 @@ def test_newton_krylov_step_matches_oracle(name, mk, pid, ncell, length, params,
         assert np.linalg.norm(w[f] - u[f]) / scale < 2e-8, (name, f, np.linalg.norm(w[f] - u[f]) / scale)
 
 
+@pytest.mark.parametrize("name,mk,pid,ncell,length,params,dt,ls", CASES)
+def test_bicgstab_step_matches_oracle(name, mk, pid, ncell, length, params, dt, ls):
+    """linear_solver = 1: right-preconditioned BiCGStab (the reduced Ostwald drivers' choice, bench2_eta1.py:113) lands on
+    the same Newton iterate as the oracle's direct solve; an iteration is two operator applies."""
+    D = discretization(name, ncell, length)
+    u0 = D.prob.ic(D.mesh)
+    w, rep = emul.newton_step(mk, pid, ncell, length, params, dt, u0, u0, absolute_tolerance=1e-10, krylov_rtol=1e-10,
+                              maximum_iterations=30, krylov_maximum_iterations=5000, line_search=ls, linear_solver=1)
+    assert rep["converged"] == 1 and rep["fnorm"] < 1e-10 * max(1.0, rep["fnorm0"]) + 1e-10, rep
+    assert rep["pc_applies"] <= 2 * rep["krylov_its"]
+    u, n, ok = D.solve_step(u0, u0, dt, atol=1e-11, linear="lu" if mk == 2 else krylov.make_linear(rtol=1e-12))
+    assert ok
+    for f in range(D.nf):
+        scale = max(np.linalg.norm(u[f]), 1e-3 * np.sqrt(u[f].size))
+        assert np.linalg.norm(w[f] - u[f]) / scale < 2e-8, (name, f, np.linalg.norm(w[f] - u[f]) / scale)
+
+
 @pytest.mark.parametrize("name,mk,pid,ncell,length,params,dt,ls", CASES[:1] + CASES[4:])
 def test_compressed_basis_is_equivalent(name, mk, pid, ncell, length, params, dt, ls):
     """Default tolerances (atol 1e-6, GMRES rtol 1e-5): the fp32-stored basis needs the same number of Krylov iterations

@@ -174,7 +174,7 @@ def test_problem_constructor_binds_functions(monkeypatch):
     class StubContext:
         def __init__(self, problem, ncell, length, **kw):
             calls.append(("ctx", problem, tuple(ncell), kw["params"]))
-            self.nf, self.params = 2, kw["params"]
+            self.nf, self.params, self.problem = 2, kw["params"], problem
 
         def new_vector(self):
             return object()
@@ -233,7 +233,7 @@ def test_module_level_script_runs_through_the_aliases(monkeypatch, tmp_path):
 
         def __init__(self, problem, ncell, length, **kw):
             log.append(("ctx", problem, tuple(ncell), kw["params"]))
-            self.nf, self.params, self.dt = 2, kw["params"], None
+            self.nf, self.params, self.dt, self.problem = 2, kw["params"], None, problem
             self.n_owned = (ncell[0] + 1) * (ncell[1] + 1) + ncell[0] * ncell[1]
 
         def new_vector(self):

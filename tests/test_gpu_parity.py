@@ -225,6 +225,40 @@ def test_tma_kernels_match_gather_kernels():
         ctx.close()
 
 
+def test_backtracking_line_search_on_the_gpu():
+    """'bt' (PETSc's default backtracking; csrc/pfh_solver.cpp) through the C ABI on the device: the same iterates as 'basic'
+    when the full Newton step is accepted, and a converged step of benchmark 2 from its initial condition at dt = 0.64,
+    where the full step ('basic') and the secant step ('cp') both diverge -- the CPU solver leg's test, on the real kernels."""
+    eng = _engine()
+    ctx = eng.Context("bench1", (10, 8), (20.0, 16.0))
+    w0 = ctx.initial_condition()
+    ctx.dt = 0.1
+    out = {}
+    for ls in (0, 2):
+        w = w0.clone()
+        rep = ctx.newton_solve(w, w0, line_search=ls)
+        out[ls] = (w.cpu().numpy(), rep)
+    assert np.array_equal(out[0][0], out[2][0]) and out[0][1]["niters"] == out[2][1]["niters"]
+    assert out[0][1]["krylov_its"] == out[2][1]["krylov_its"]
+    ctx.close()
+    ncell, length = (12, 10), (24.0, 20.0)
+    D2 = discretization("bench2", ncell, length)
+    ctx = eng.Context("bench2", ncell, length)
+    v0 = ctx.initial_condition()
+    ctx.dt = 0.64
+    reps = {}
+    for ls in (0, 1, 2):
+        w = v0.clone()
+        reps[ls] = (ctx.newton_solve(w, v0, line_search=ls, maximum_iterations=25), w.cpu().numpy().reshape(6, -1))
+    assert not reps[0][0]["converged"] and not reps[1][0]["converged"]
+    rep, w = reps[2]
+    assert rep["converged"] and rep["fnorm"] < 1e-6 and rep["residual_evals"] > rep["niters"] + 1   # it did backtrack
+    u0 = v0.cpu().numpy().reshape(6, -1)
+    u, n, ok = D2.solve_step(w, u0, 0.64, atol=1e-11)            # the oracle's Newton/LU started from that solution stays there
+    assert ok and max(np.linalg.norm(w[f] - u[f]) / max(np.linalg.norm(u[f]), 1.0) for f in range(6)) < 1e-6
+    ctx.close()
+
+
 def test_step_host_equals_device_path():
     eng = _engine()
     ncell, length = (40, 30), (80.0, 60.0)
