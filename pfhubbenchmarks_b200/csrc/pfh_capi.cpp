@@ -130,6 +130,7 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     PFH_CHECK(c->dim == 3 || cfg->nranks == 1, "2-D problems do not shard (replicas only)");
 
     PFH_CUDA(cudaSetDevice(cfg->device));
+    PFH_CUDA(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     if (c->dim == 3) {  // kernel attributes are per device: set them for the device this ctx lives on
       pfh_scalar3_init_device();
       pfh_jac3_init_device();

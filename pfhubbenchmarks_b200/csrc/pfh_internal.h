@@ -201,6 +201,7 @@ struct pfh_ctx {
   int jac_zchunk = 0;      // planes per CTA of the cube-centric J.v / residual kernel (0 = default 32; tuning)
   bool use_wide = true;    // nranks > 1: wide-ghost Schur preconditioner (false: one ghost-plane exchange per sweep)
   void* tmap_cache = nullptr;  // tensor-map cache (pfh_scalar3_tma.cu)
+  int n_sm = 0;                // multiprocessors of the device (grid sizing)
   // Krylov J.v of the 3-D TMA path: quadrature block in single precision (elem::cube_jac_quartic_f32).  Opt-in: validated
   // numerically on the CPU solver leg, not yet measured on hardware.
   bool jac_quadrature_fp32 = false;

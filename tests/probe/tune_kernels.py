@@ -22,8 +22,8 @@ def fam(t, k):
 
 for loader in (1,):
     ctx.set_option("use_tma_loader", loader)
-    for v in (0, 2, 3, 4, 5, 6):
-        for zc in (32, 48):
+    for v in (0, 1, 2, 3, 4, 5):
+        for zc in (32, 64):
             ctx.set_option("scalar_variant", v)
             ctx.set_option("scalar_zchunk", zc)
             ctx.precond_setup(pc_variant=1, pc_sweeps_mass=3, pc_sweeps_shifted=4)

@@ -92,3 +92,21 @@ def test_3d_cahn_hilliard_step_conserves_mass_and_dissipates_energy():
         E1, M1 = D.energy(u), D.mass(u)
         assert E1 < E0 and abs(M1 - M0) < 1e-11 * abs(M0)
         E0 = E1
+
+
+def test_symbol_bound_of_the_shifted_operator_matches_the_assembled_spectrum():
+    """The Chebyshev interval of the product's shifted solves takes its upper end from the symbol of D^-1 (M + alpha K) on
+    the interior rows of the Kuhn mesh (csrc/pfh_solver.cpp symbol_bounds3; oracle.krylov.symbol_lmax is its CPU statement).
+    Against the assembled operator: the symbol's maximum is the largest eigenvalue to a fraction of a per cent (boundary
+    rows), so 1.015 x symbol is a safe upper bound, where the generic bound (d+2)/2 = 2.5 is 30 % too wide."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from oracle import krylov
+    m = omesh.kuhn3d(9, 8, 7, 18.0, 16.0, 14.0)
+    D = stepper.Discretization(m, problems.CahnHilliard())
+    for alpha in (1.0, 4.0, 8.0):
+        A = (D.V.M + alpha * D.V.K).tocsr()
+        S = sp.diags(1.0 / np.sqrt(A.diagonal()))
+        lmax = spl.eigsh(S @ A @ S, k=1, which="LA", return_eigenvectors=False)[0]
+        sym = krylov.symbol_lmax(A, m)
+        assert abs(sym / lmax - 1.0) < 5e-3 and 1.015 * sym > lmax and lmax < 2.0 < 2.5, (alpha, sym, lmax)
