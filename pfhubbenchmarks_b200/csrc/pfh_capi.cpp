@@ -134,6 +134,9 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     if (c->dim == 3) {  // kernel attributes are per device: set them for the device this ctx lives on
       pfh_scalar3_init_device();
       pfh_jac3_init_device();
+      PFH_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+      PFH_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      PFH_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     }
     if (cfg->stream) {
       c->stream = (cudaStream_t)cfg->stream;
@@ -225,6 +228,10 @@ int pfh_destroy(pfh_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   comm_destroy(c->comm);
+  if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -444,6 +451,8 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->jac_zchunk = (int)value;
   } else if (k == "jac_variant") {
     c->jac_variant = (int)value;
+  } else if (k == "shell_async") {
+    c->shell_async = value != 0.0;
   } else if (k == "use_wide") {
     c->use_wide = value != 0.0;
   } else if (k == "use_tma_loader") {

@@ -202,6 +202,10 @@ struct pfh_ctx {
   bool use_wide = true;    // nranks > 1: wide-ghost Schur preconditioner (false: one ghost-plane exchange per sweep)
   void* tmap_cache = nullptr;  // tensor-map cache (pfh_scalar3_tma.cu)
   int n_sm = 0;                // multiprocessors of the device (grid sizing)
+  // the boundary-shell kernel of a scalar-operator launch runs on aux_stream, concurrently with the staged kernel
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool shell_async = true;
   // Krylov J.v of the 3-D TMA path: quadrature block in single precision (elem::cube_jac_quartic_f32).  Opt-in: validated
   // numerically on the CPU solver leg, not yet measured on hardware.
   bool jac_quadrature_fp32 = false;

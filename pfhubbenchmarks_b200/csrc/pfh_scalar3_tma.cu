@@ -17,10 +17,18 @@
 // Along the z-march every thread keeps the four operands of plane k-1 and four of plane k that it already loaded
 // in registers, so a vertex costs 7 shared-memory loads instead of 15.
 //
+// The staged kernel treats EVERY vertex as an interior row (constant 15-point stencil, uniform Jacobi scale): no row
+// tables, no boundary-type logic in the z-march.  It skips the stores of the vertices whose result that would get
+// wrong -- the boundary vertices, and for MODE 3 also their neighbours (their operand b0 D^-1 r needs the neighbour's own
+// diagonal) -- and a small gather kernel (k3_scalar_shell) computes those from global memory with the general
+// per-type rows: 1-2 % of the vertices, ~5 % of the time.
+//
 // A launch works on an arbitrary window of planes: output planes are launch-local zl = 0 .. nzo-1 (global plane
 // gz0 + zl); the stencil operand is addressed through a main array plus optional lower / upper ghost arrays of any
 // width.  This serves both the classic one-ghost-plane layout and the wide-ghost preconditioner of the multi-GPU
 // path, where Chebyshev sweeps run redundantly on a shrinking halo instead of exchanging a plane per sweep.
+#include <algorithm>
+
 #include "pfh_tma.cuh"
 #include "pfh_vertex.cuh"
 
@@ -29,6 +37,10 @@ using namespace tma;
 
 struct Coef15 {
   double c[PFH_NOFF3];
+};
+// interior row of am M + ak K by symmetric pair: self, +-x, +-y, +-z, +-(x+y), +-(y+z), +-(x+z), +-(x+y+z)
+struct Coef8 {
+  double c[8];
 };
 struct InvDiag27 {
   double v[27];  // 1 / diagonal of (am M + ak K) by boundary type
@@ -45,33 +57,14 @@ struct ScalarParams {
   int r_off, r_n, r_nlo, r_nhi;  // pointwise operand r: same addressing as the stencil operand
   double am, ak, a, b, bdI, b0;
   double ob0;                  // MODE 2 without a zprev operand: zprev = ob0 D^-1 r (0: zprev = 0)
-  Coef15 cI;
+  double s1I, ob0I;            // b0 / diag and ob0 / diag of the interior row
+  int shell;                   // depth of the boundary shell the staged kernel leaves to k3_scalar_shell (1; MODE 3: 2)
+  Coef8 cS;
   InvDiag27 invd;
   double* out;                 // launch-local plane 0
   double* out1;                // MODE 3: z1; MODE 0: optional copy of the operand
   const double *in, *in_lo, *in_hi, *r, *r_lo, *r_hi, *o;  // raw operand pointers (CPASYNC loader); o at launch-local plane 0
 };
-
-// next to the boundary the neighbours' rows have different diagonals: scale operand by operand
-// (only on the two planes next to each z boundary: kept out of line, working on a copy in local memory, so that it
-// does not cost the main loop registers)
-__device__ __noinline__ void first2_scale_boundary(double* v, const InvDiag27& invd, double b0, int ix, int iy, int gz,
-                                                   const Mesh3& m) {
-  constexpr int DX[PFH_NOFF3] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1};
-  constexpr int DY[PFH_NOFF3] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1};
-  constexpr int DZ[PFH_NOFF3] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1};
-  auto cls = [](int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); };
-  int tX[3], tY[3], tZ[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    tX[d] = cls(ix + d - 1, m.nxv);
-    tY[d] = 3 * cls(iy + d - 1, m.nyv);
-    tZ[d] = 9 * cls(gz + d - 1, m.nzv);
-  }
-  // out-of-domain operands are zeros, whatever scale they get
-#pragma unroll
-  for (int o = 0; o < PFH_NOFF3; ++o) v[o] *= b0 * invd.v[tZ[DZ[o] + 1] + tY[DY[o] + 1] + tX[DX[o] + 1]];
-}
 
 // One CTA = TX*TY consumer threads (one vertex column each) + one producer warp.  The producer fills a ring of NS stages
 // -- each stage holds one plane of the stencil operand (tile + halo) and the r / zprev tiles of the output plane two
@@ -80,14 +73,13 @@ __device__ __noinline__ void first2_scale_boundary(double* v, const InvDiag27& i
 // apart by up to NS-2 planes, which hides the latency of the loads.  The march is unrolled NS-fold so that stage
 // addresses and barrier parities are compile-time constants and the register rotation of the z-reuse needs no moves.
 template <int MODE, int TX, int TY, int NS, int MINB, bool TMA>
-__global__ void __launch_bounds__(TX* TY + 32, (MODE == 3 && MINB > 2) ? MINB - 1 : MINB)  // MODE 3 needs ~100 registers
+__global__ void __launch_bounds__(TX* TY + 32, MINB)
     k3_scalar_tma(const __grid_constant__ ScalarMaps M, const __grid_constant__ ScalarParams P) {
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2: the TMA box start (x0-2) must be 16-byte aligned
   constexpr int NC = TX * TY, NCW = NC / 32;  // consumer threads / warps
   constexpr int ZT_BYTES = W * H * 8, PT_BYTES = TX * TY * 8;
   constexpr int ZT_STRIDE = round_up(ZT_BYTES, 128);
   constexpr int STAGE = ZT_STRIDE + 2 * PT_BYTES;  // stencil tile | r tile | zprev tile
-  constexpr bool REUSE = MODE != 3;                // z-march register reuse (MODE 3 spends the registers on its operand scales)
   static_assert(NC % 32 == 0 && NS >= 3, "tile must be whole warps; the march reads three planes");
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * STAGE);
@@ -180,9 +172,9 @@ __global__ void __launch_bounds__(TX* TY + 32, (MODE == 3 && MINB > 2) ? MINB - 
   // -------------------------------------------------- consumer warps --------------------------------------------------
   const int lx = tid % TX, ly = tid / TX;
   const int ix = x0 + lx, iy = y0 + ly;
-  const bool valid = ix < m.nxv && iy < m.nyv;
-  const bool deep_xy = ix >= 2 && ix <= m.nxv - 3 && iy >= 2 && iy <= m.nyv - 3;
-  const int txy = (iy == 0 ? 0 : (iy == m.nyv - 1 ? 2 : 1)) * 3 + (ix == 0 ? 0 : (ix == m.nxv - 1 ? 2 : 1));
+  const int d = P.shell;
+  // vertices this kernel stores: inside the mesh and not in the boundary shell (k3_scalar_shell computes those)
+  const bool store_xy = ix >= d && ix < m.nxv - d && iy >= d && iy < m.nyv - d;
   const int c = (ly + 1) * W + lx + 2;  // this vertex in a stencil tile
   const int pc = ly * TX + lx;          // and in a pointwise tile
   double* outp = P.out + ((long long)zb * m.nxy + (long long)iy * m.nxv + ix);
@@ -194,20 +186,11 @@ __global__ void __launch_bounds__(TX* TY + 32, (MODE == 3 && MINB > 2) ? MINB - 
     if (elect) mbar_arrive(&empty[s]);
   };
 
-  double pa[4], pb[4];  // REUSE: plane k-1: c, c-W, c-1, c-W-1; plane k: c, c+W, c+1, c+W+1
-  // MODE 3: scale b0 / diag of the row of each of the 7 distinct x-y neighbours (0,0) (1,0) (-1,0) (0,1) (0,-1) (1,1) (-1,-1)
-  // on a plane away from the z boundaries; fixed per thread, so the vertices next to an x or y boundary cost 15
-  // multiplications instead of a table walk per plane
-  double sc[MODE == 3 ? 7 : 1];
-  if constexpr (MODE == 3) {
-    constexpr int DX7[7] = {0, 1, -1, 0, 0, 1, -1}, DY7[7] = {0, 0, 0, 1, -1, 1, -1};
-    auto cls = [](int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); };
-#pragma unroll
-    for (int j = 0; j < 7; ++j) sc[j] = P.b0 * P.invd.v[9 + 3 * cls(iy + DY7[j], m.nyv) + cls(ix + DX7[j], m.nxv)];
-  }
+  // z-march register reuse: plane k-1: c, c-W, c-1, c-W-1; plane k: c, c+W, c+1, c+W+1
+  double pa[4], pb[4];
   mbar_wait(&full[0], 0);
   mbar_wait(&full[1], 0);
-  if constexpr (REUSE) {
+  {
     const double* S0 = ztile(0);
     const double* S1 = ztile(1);
     pa[0] = S0[c]; pa[1] = S0[c - W]; pa[2] = S0[c - 1]; pa[3] = S0[c - W - 1];
@@ -215,101 +198,160 @@ __global__ void __launch_bounds__(TX* TY + 32, (MODE == 3 && MINB > 2) ? MINB - 
     release(0);
   }
 
-  uint32_t ph = 0;  // parity of the ring pass the iteration's base plane k0 belongs to
-  for (int k0 = 0; k0 < nout; k0 += NS, ph ^= 1) {
-#pragma unroll
-    for (int u = 0; u < NS; ++u) {
-      const int k = k0 + u;
-      if (k >= nout) break;
-      const int s1i = (u + 1) % NS, s2i = (u + 2) % NS;
-      mbar_wait(&full[s2i], ph ^ ((u + 2) / NS));  // plane k+2 and the pointwise tiles of output plane k
-      const double* S1 = ztile(s1i);
-      const double* S2 = ztile(s2i);
-      const double* Rt = reinterpret_cast<const double*>(smem + s2i * STAGE + ZT_STRIDE);
-      const double* Ot = Rt + NC;
-      const int gz = P.gz0 + zb + k;
-      const int tzt = gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1);
-      const bool deep_z = gz >= 2 && gz <= m.nzv - 3;
-      const double rv = P.has_r ? Rt[pc] : 0.0;
-      double ov = P.has_o ? Ot[pc] : 0.0;
-      double v[PFH_NOFF3];
-      if constexpr (REUSE) {
-        v[0] = pb[0]; v[3] = pb[1]; v[1] = pb[2]; v[7] = pb[3];
-        v[2] = S1[c - 1]; v[4] = S1[c - W]; v[8] = S1[c - W - 1];
-        v[6] = pa[0]; v[10] = pa[1]; v[12] = pa[2]; v[14] = pa[3];
-        v[5] = S2[c]; v[9] = S2[c + W]; v[11] = S2[c + 1]; v[13] = S2[c + W + 1];
-        // the march: plane k becomes plane k-1, plane k+1 becomes plane k
-        pa[0] = v[0]; pa[1] = v[4]; pa[2] = v[2]; pa[3] = v[8];
-        pb[0] = v[5]; pb[1] = v[9]; pb[2] = v[11]; pb[3] = v[13];
-        release(s1i);  // the rest of plane k+1 lives in registers
+  // one output plane: `u` = k mod NS (compile-time in the unrolled groups), `ph` = parity of ring pass k / NS
+  auto plane = [&](const int k, const int u, const uint32_t ph) {
+    const int s1i = (u + 1) % NS, s2i = (u + 2) % NS;
+    mbar_wait(&full[s2i], ph ^ ((u + 2) / NS));  // plane k+2 and the pointwise tiles of output plane k
+    const double* S1 = ztile(s1i);
+    const double* S2 = ztile(s2i);
+    const double* Rt = reinterpret_cast<const double*>(smem + s2i * STAGE + ZT_STRIDE);
+    const double* Ot = Rt + NC;
+    const int gz = P.gz0 + zb + k;
+    const bool store = store_xy && gz >= d && gz < m.nzv - d;
+    const double rv = P.has_r ? Rt[pc] : 0.0;
+    double ov = P.has_o ? Ot[pc] : 0.0;
+    const double v0 = pb[0], v3 = pb[1], v1 = pb[2], v7 = pb[3];
+    const double v2 = S1[c - 1], v4 = S1[c - W], v8 = S1[c - W - 1];
+    const double v6 = pa[0], v10 = pa[1], v12 = pa[2], v14 = pa[3];
+    const double v5 = S2[c], v9 = S2[c + W], v11 = S2[c + 1], v13 = S2[c + W + 1];
+    // the march: plane k becomes plane k-1, plane k+1 becomes plane k
+    pa[0] = v0; pa[1] = v4; pa[2] = v2; pa[3] = v8;
+    pb[0] = v5; pb[1] = v9; pb[2] = v11; pb[3] = v13;
+    release(s1i);  // the rest of plane k+1 lives in registers
+    // the interior row is symmetric: one coefficient per +- pair (8 constants), two partial sums
+    double s0 = P.cS.c[0] * v0;
+    double t1 = P.cS.c[1] * (v1 + v2);
+    s0 += P.cS.c[2] * (v3 + v4);
+    t1 += P.cS.c[3] * (v5 + v6);
+    s0 += P.cS.c[4] * (v7 + v8);
+    t1 += P.cS.c[5] * (v9 + v10);
+    s0 += P.cS.c[6] * (v11 + v12);
+    t1 += P.cS.c[7] * (v13 + v14);
+    const double Av = s0 + t1;
+    if (store) {
+      if (MODE == 0) {
+        *outp = P.a * rv + Av;
+        if (out1p != nullptr) *out1p = v0;
+      } else if (MODE == 2) {
+        if (P.ob0I != 0.0) ov = P.ob0I * rv;  // the first iterate recomputed from r, exactly as MODE 3 would store it
+        *outp = v0 + P.a * (v0 - ov) + P.bdI * (rv - Av);
       } else {
-        const double* S0 = ztile(u % NS);
-        v[0] = S1[c]; v[1] = S1[c + 1]; v[2] = S1[c - 1]; v[3] = S1[c + W]; v[4] = S1[c - W];
-        v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
-        v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
-        v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
-        release(u % NS);
+        const double z1 = P.s1I * v0;
+        if (out1p != nullptr) *out1p = z1;
+        *outp = z1 + P.a * z1 + P.bdI * (v0 - P.s1I * Av);
       }
-      const double self = v[0];
-      const int type = tzt * 9 + txy;
-      if (MODE == 2 && P.ob0 != 0.0) ov = (P.ob0 * P.invd.v[type]) * rv;  // the first iterate, exactly as MODE 3 stores it
-      double Av, bd;
-      double rc = 0.0, s1 = 0.0;  // MODE 3: r at this vertex; uniform operand scale b0 / diag when every neighbour is an interior row
-      if constexpr (MODE == 3) {
-        rc = v[0];
-        if (deep_z && deep_xy) {
-          s1 = sc[0];
-        } else if (deep_z) {
-          // next to an x or y boundary, away from the z boundaries: the per-thread scales of the 7 x-y neighbours
-          constexpr int J7[PFH_NOFF3] = {0, 1, 2, 3, 4, 0, 0, 5, 6, 3, 4, 1, 2, 5, 6};
-#pragma unroll
-          for (int o = 0; o < PFH_NOFF3; ++o) v[o] *= sc[J7[o]];
-          s1 = 1.0;
-        } else {
-          double t[PFH_NOFF3];
-#pragma unroll
-          for (int o = 0; o < PFH_NOFF3; ++o) t[o] = v[o];
-          first2_scale_boundary(t, P.invd, P.b0, ix, iy, gz, m);
-#pragma unroll
-          for (int o = 0; o < PFH_NOFF3; ++o) v[o] = t[o];
-          s1 = 1.0;
-        }
-      }
-      if (type == 13) {
-        // four independent partial sums: the 15 fused multiply-adds are not one dependent chain
-        double s0 = P.cI.c[0] * v[0], t1 = P.cI.c[1] * v[1], t2 = P.cI.c[2] * v[2], t3 = P.cI.c[3] * v[3];
-        s0 += P.cI.c[4] * v[4]; t1 += P.cI.c[5] * v[5]; t2 += P.cI.c[6] * v[6]; t3 += P.cI.c[7] * v[7];
-        s0 += P.cI.c[8] * v[8]; t1 += P.cI.c[9] * v[9]; t2 += P.cI.c[10] * v[10]; t3 += P.cI.c[11] * v[11];
-        s0 += P.cI.c[12] * v[12]; t1 += P.cI.c[13] * v[13]; t2 += P.cI.c[14] * v[14];
-        Av = (s0 + t1) + (t2 + t3);
-        bd = P.bdI;
-      } else {
-        vtx::Row3 row;
-        vtx::get_row3(m, type, row);
-        double Ms, Ks;
-        vtx::mk_sums3(row, v, Ms, Ks);
-        Av = P.am * Ms + P.ak * Ks;
-        bd = MODE >= 2 ? P.b / (P.am * row.m[0] + P.ak * row.k[0]) : 0.0;
-      }
-      if (valid) {
-        if (MODE == 0) {
-          *outp = P.a * rv + Av;
-          if (out1p != nullptr) *out1p = self;
-        } else if (MODE == 2) {
-          *outp = self + P.a * (self - ov) + bd * (rv - Av);
-        } else {
-          const double z1 = s1 * v[0];
-          if (out1p != nullptr) *out1p = z1;
-          *outp = z1 + P.a * z1 + bd * (rc - s1 * Av);
-        }
-      }
-      outp += m.nxy;
-      if (out1p != nullptr) out1p += m.nxy;
     }
+    outp += m.nxy;
+    if (out1p != nullptr) out1p += m.nxy;
+  };
+  // full groups of NS planes, unrolled: stage addresses and parities are constants and the z-reuse registers rotate by
+  // renaming; then the remaining planes one by one
+  int k0 = 0;
+  uint32_t ph = 0;
+  for (; k0 + NS <= nout; k0 += NS, ph ^= 1) {
+#pragma unroll
+    for (int u = 0; u < NS; ++u) plane(k0 + u, u, ph);
+  }
+  for (int k = k0; k < nout; ++k) plane(k, k - k0, ph);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Boundary shell: the vertices within `shell` layers of the mesh boundary, computed from global memory with the general
+// per-type rows (vtx::get_row3) and, for MODE 3, the operand scaled by each neighbour's own b0 / diag.  One thread per
+// shell vertex; the index space is [z-shell planes: whole planes | other planes: y-shell rows | x-shell columns].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int shell_index(int j, int n, int d) { return (2 * d >= n || j < d) ? j : n - 2 * d + j; }
+
+// plane `z` (index in the main array, may lie in a ghost array) of an operand addressed like the stencil operand
+__device__ __forceinline__ const double* operand_plane(const double* main, int n_main, const double* lo, int n_lo, const double* hi,
+                                                       int n_hi, int z, long long nxy) {
+  if (z >= 0 && z < n_main) return main + (long long)z * nxy;
+  if (z < 0 && z + n_lo >= 0) return lo + (long long)(z + n_lo) * nxy;
+  if (z >= n_main && z - n_main < n_hi) return hi + (long long)(z - n_main) * nxy;
+  return nullptr;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k3_scalar_shell(const __grid_constant__ ScalarParams P, int nzs, int zs0, int zs1, int zs2, int zs3,
+                                                       int zi0, int nzi, long long n_threads) {
+  const Mesh3& m = P.m;
+  const int d = P.shell;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_threads) return;
+  const int csx = min(2 * d, m.nxv), csy = min(2 * d, m.nyv);
+  const long long n1 = (long long)nzs * m.nxy, n2 = (long long)nzi * csy * m.nxv;
+  int ix, iy, zl;
+  if (t < n1) {  // a plane of the z shell
+    const int j = (int)(t / m.nxy);
+    const long long r = t - (long long)j * m.nxy;
+    zl = j == 0 ? zs0 : (j == 1 ? zs1 : (j == 2 ? zs2 : zs3));
+    iy = (int)(r / m.nxv);
+    ix = (int)(r - (long long)iy * m.nxv);
+  } else if (t < n1 + n2) {  // a row of the y shell
+    const long long r = t - n1;
+    const long long per = (long long)csy * m.nxv;
+    zl = zi0 + (int)(r / per);
+    const long long q = r % per;
+    iy = shell_index((int)(q / m.nxv), m.nyv, d);
+    ix = (int)(q % m.nxv);
+  } else {  // a column of the x shell, rows outside the y shell
+    const long long r = t - n1 - n2;
+    const int ny_in = m.nyv - csy;
+    const long long per = (long long)ny_in * csx;
+    zl = zi0 + (int)(r / per);
+    const long long q = r % per;
+    iy = d + (int)(q / csx);
+    ix = shell_index((int)(q % csx), m.nxv, d);
+  }
+  const int gz = P.gz0 + zl;
+  const double* pl[3];
+#pragma unroll
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int g = gz + dz;
+    pl[dz + 1] = (g < 0 || g >= m.nzv) ? nullptr : operand_plane(P.in, P.in_n, P.in_lo, P.n_lo, P.in_hi, P.n_hi, zl + dz + P.in_off, m.nxy);
+  }
+  const vtx::Planes3 PL{pl[0], pl[1], pl[2]};
+  double v[PFH_NOFF3];
+  vtx::gather15<true>(PL, m, ix, iy, v);
+  const int type = vtx::type3(m, ix, iy, gz);
+  const long long i = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
+  double rv = 0.0, ov = 0.0;
+  if (P.has_r) {
+    const double* rp = operand_plane(P.r, P.r_n, P.r_lo, P.r_nlo, P.r_hi, P.r_nhi, zl + P.r_off, m.nxy);
+    rv = rp ? rp[(long long)iy * m.nxv + ix] : 0.0;
+  }
+  if (P.has_o) ov = P.o[i];
+  if (MODE == 2 && P.ob0 != 0.0) ov = (P.ob0 * P.invd.v[type]) * rv;
+  const double rc = v[0], self = v[0];
+  if (MODE == 3) {
+    constexpr int DX[PFH_NOFF3] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1};
+    constexpr int DY[PFH_NOFF3] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1};
+    constexpr int DZ[PFH_NOFF3] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1};
+    auto cls = [](int q, int n) { return q == 0 ? 0 : (q == n - 1 ? 2 : 1); };
+    // operand o is r at the neighbour times b0 / diag of the NEIGHBOUR's row; out-of-domain operands are zero anyway
+#pragma unroll
+    for (int o = 0; o < PFH_NOFF3; ++o)
+      v[o] *= P.b0 * P.invd.v[9 * cls(gz + DZ[o], m.nzv) + 3 * cls(iy + DY[o], m.nyv) + cls(ix + DX[o], m.nxv)];
+  }
+  vtx::Row3 row;
+  vtx::get_row3(m, type, row);
+  double Ms, Ks;
+  vtx::mk_sums3(row, v, Ms, Ks);
+  const double Av = P.am * Ms + P.ak * Ks;
+  const double bd = MODE >= 2 ? P.b / (P.am * row.m[0] + P.ak * row.k[0]) : 0.0;
+  if (MODE == 0) {
+    P.out[i] = P.a * rv + Av;
+    if (P.out1 != nullptr) P.out1[i] = self;
+  } else if (MODE == 2) {
+    P.out[i] = self + P.a * (self - ov) + bd * (rv - Av);
+  } else {
+    const double z1 = v[0];  // already scaled by b0 / diag of this row
+    if (P.out1 != nullptr) P.out1[i] = z1;
+    P.out[i] = z1 + P.a * z1 + bd * (rc - Av);
   }
 }
 
-constexpr int S_TX = 64, S_TY = 4, S_NS = 4, S_MINB = 3;
+constexpr int S_TX = 64, S_TY = 4, S_NS = 8, S_MINB = 3;   // 59 KB per CTA, three CTAs per SM
 
 template <int TX, int TY, int NS>
 constexpr size_t scalar_smem() {
@@ -392,10 +434,10 @@ void pfh_tmap_cache_free(pfh_ctx* c) {
 void pfh_scalar3_init_device() {
   scalar_set_attr_all<S_TX, S_TY, S_NS, S_MINB>();
   scalar_set_attr_all<64, 4, 6, 3>();
-  scalar_set_attr_all<64, 4, 4, 4>();
-  scalar_set_attr_all<64, 8, 4, 2>();
-  scalar_set_attr_all<64, 2, 6, 6>();
-  scalar_set_attr_all<128, 2, 5, 3>();
+  scalar_set_attr_all<64, 4, 4, 3>();
+  scalar_set_attr_all<64, 4, 10, 3>();
+  scalar_set_attr_all<64, 8, 6, 2>();
+  scalar_set_attr_all<128, 2, 8, 3>();
 }
 
 bool pfh_fast3_ok(const pfh_ctx* c) { return c->dim == 3 && c->use_tma; }
@@ -419,16 +461,21 @@ void k3_scalar_launch(pfh_ctx* c, const ScalarOp& op) {
     P.r_nhi = op.r_hi ? op.n_rhi : 0;
   }
   P.am = op.am; P.ak = op.ak; P.a = op.a; P.b = op.b; P.b0 = op.b0;
-  for (int o = 0; o < PFH_NOFF3; ++o) P.cI.c[o] = op.am * m.mI[o] + (o < PFH_NKOFF3 ? op.ak * m.kI[o] : 0.0);
-  P.bdI = op.b / P.cI.c[0];
+  double cI[PFH_NOFF3];
+  for (int o = 0; o < PFH_NOFF3; ++o) cI[o] = op.am * m.mI[o] + (o < PFH_NKOFF3 ? op.ak * m.kI[o] : 0.0);
+  for (int o = 1; o < PFH_NOFF3; o += 2) PFH_CHECK(cI[o] == cI[o + 1], "internal: interior stencil row is not symmetric");
+  P.cS.c[0] = cI[0];
+  for (int j = 1; j < 8; ++j) P.cS.c[j] = cI[2 * j - 1];
+  P.bdI = op.b / cI[0];
   P.ob0 = (op.mode == 2 && op.o == nullptr) ? op.ob0 : 0.0;
-  if (op.mode == 3 || P.ob0 != 0.0) {
-    if (c->h_mT.empty()) {  // host copy of the type tables, for the inverse diagonals
-      Mesh3 mm = m;
-      pfh_build_tables3(mm, c->h_mT, c->h_kT);
-    }
-    for (int t = 0; t < 27; ++t) P.invd.v[t] = 1.0 / (op.am * c->h_mT[t * PFH_NOFF3] + op.ak * c->h_kT[t * PFH_NKOFF3]);
+  if (c->h_mT.empty()) {  // host copy of the type tables, for the inverse diagonals
+    Mesh3 mm = m;
+    pfh_build_tables3(mm, c->h_mT, c->h_kT);
   }
+  for (int t = 0; t < 27; ++t) P.invd.v[t] = 1.0 / (op.am * c->h_mT[t * PFH_NOFF3] + op.ak * c->h_kT[t * PFH_NKOFF3]);
+  P.s1I = op.b0 * P.invd.v[13];
+  P.ob0I = P.ob0 * P.invd.v[13];
+  P.shell = op.mode == 3 ? 2 : 1;
   P.out = op.out; P.out1 = op.out1;
   P.in = op.in; P.in_lo = op.in_lo; P.in_hi = op.in_hi; P.r = op.r; P.r_lo = op.r_lo; P.r_hi = op.r_hi; P.o = op.o;
   // planes per CTA: balanced chunks of at most `scalar_zchunk` planes; on a short window (a slab of a multi-GPU run) the
@@ -455,12 +502,46 @@ void k3_scalar_launch(pfh_ctx* c, const ScalarOp& op) {
   if (P.n_hi > 0) use_tma = use_tma && aligned16(op.in_hi);
   if (P.has_r) use_tma = use_tma && aligned16(op.r) && (P.r_nlo == 0 || aligned16(op.r_lo)) && (P.r_nhi == 0 || aligned16(op.r_hi));
   if (P.has_o) use_tma = use_tma && aligned16(op.o);
+  // the boundary shell of the window
+  const int d = P.shell;
+  int zs[4] = {0, 0, 0, 0}, nzs = 0, zi0 = 0, nzi = 0;
+  for (int zl = 0; zl < op.nzo; ++zl) {
+    const int gz = op.gz0 + zl;
+    if (gz < d || gz >= m.nzv - d) {
+      PFH_CHECK(nzs < 4, "internal: more than four shell planes in a window");
+      zs[nzs++] = zl;
+    } else {
+      if (nzi == 0) zi0 = zl;
+      ++nzi;
+    }
+  }
+  const long long csx = std::min(2 * d, m.nxv), csy = std::min(2 * d, m.nyv);
+  const long long n_threads = (long long)nzs * m.nxy + (long long)nzi * (csy * m.nxv + (m.nyv - csy) * csx);
+  // The shell kernel reads what the staged kernel reads and stores the vertices it skips: the two are independent, so
+  // the (latency-bound, partly uncoalesced) gather runs on aux_stream underneath the staged kernel.
+  const bool fork = c->shell_async && c->aux_stream != nullptr && n_threads > 0;
+  cudaStream_t sst = fork ? c->aux_stream : c->stream;
+  if (fork) {
+    PFH_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    PFH_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+  }
+  if (n_threads > 0) {
+    const unsigned nb = (unsigned)((n_threads + 127) / 128);
+    if (op.mode == 0) k3_scalar_shell<0><<<nb, 128, 0, sst>>>(P, nzs, zs[0], zs[1], zs[2], zs[3], zi0, nzi, n_threads);
+    else if (op.mode == 2) k3_scalar_shell<2><<<nb, 128, 0, sst>>>(P, nzs, zs[0], zs[1], zs[2], zs[3], zi0, nzi, n_threads);
+    else k3_scalar_shell<3><<<nb, 128, 0, sst>>>(P, nzs, zs[0], zs[1], zs[2], zs[3], zi0, nzi, n_threads);
+    PFH_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  if (fork) PFH_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
   switch (c->scalar_variant) {
-    case 1: scalar_launch<64, 4, 6, 3>(c, op, P, use_tma); break;    // deeper ring
-    case 2: scalar_launch<64, 4, 4, 4>(c, op, P, use_tma); break;    // 4 CTAs per SM at 56 registers
-    case 3: scalar_launch<64, 8, 4, 2>(c, op, P, use_tma); break;    // 544 threads, 2 CTAs per SM
-    case 4: scalar_launch<64, 2, 6, 6>(c, op, P, use_tma); break;    // 160 threads, 6 CTAs per SM
-    case 5: scalar_launch<128, 2, 5, 3>(c, op, P, use_tma); break;
+    case 1: scalar_launch<64, 4, 6, 3>(c, op, P, use_tma); break;
+    case 2: scalar_launch<64, 4, 4, 3>(c, op, P, use_tma); break;
+    case 3: scalar_launch<64, 4, 10, 3>(c, op, P, use_tma); break;
+    case 4: scalar_launch<64, 8, 6, 2>(c, op, P, use_tma); break;    // 544 threads, 2 CTAs per SM
+    case 5: scalar_launch<128, 2, 8, 3>(c, op, P, use_tma); break;
     default: scalar_launch<S_TX, S_TY, S_NS, S_MINB>(c, op, P, use_tma); break;
   }
+  if (fork) PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+
 }
