@@ -211,6 +211,7 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
       PFH_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi_prio));
       PFH_CUDA(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
       PFH_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+      PFH_CUDA(cudaEventCreateWithFlags(&c->ev_rhs, cudaEventDisableTiming));
     }
     PFH_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
@@ -234,6 +235,7 @@ int pfh_destroy(pfh_ctx* c) {
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+  if (c->ev_rhs) cudaEventDestroy(c->ev_rhs);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   pfh_tmap_cache_free(c);
   for (double* p : c->allocs) cudaFree(p);

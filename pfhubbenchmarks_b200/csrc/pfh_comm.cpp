@@ -25,6 +25,7 @@ struct Api {
   ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;  // optional (NCCL >= 2.18)
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -43,6 +44,7 @@ Api& api() {
   L(GetUniqueId); L(CommInitRank); L(CommDestroy); L(AllReduce); L(Send); L(Recv); L(GroupStart); L(GroupEnd);
   L(GetErrorString);
 #undef L
+  *(void**)(&a.CommSplit) = dlsym(a.h, "ncclCommSplit");
   return a;
 }
 
@@ -52,7 +54,9 @@ void ck(ncclResult_t r, const char* what) {
 }  // namespace
 
 struct Comm {
-  ncclComm_t comm = nullptr;
+  ncclComm_t comm = nullptr;   // reductions (ctx stream)
+  ncclComm_t halo = nullptr;   // ghost-plane exchanges: a duplicate of `comm` (ncclCommSplit), so that an exchange on
+                               // comm_stream may run while a reduction is in flight on the ctx stream; == comm if unavailable
   int rank = 0, nranks = 1;
 };
 
@@ -72,11 +76,17 @@ Comm* comm_create(const pfh_config& cfg, cudaStream_t) {
   ncclUniqueId id;
   memcpy(&id, cfg.nccl_unique_id, PFH_NCCL_ID_BYTES);
   ck(api().CommInitRank(&c->comm, cfg.nranks, id, cfg.rank), "ncclCommInitRank");
+  c->halo = c->comm;
+  if (api().CommSplit != nullptr) {
+    ncclComm_t dup = nullptr;
+    if (api().CommSplit(c->comm, 0, cfg.rank, &dup, nullptr) == 0 && dup != nullptr) c->halo = dup;
+  }
   return c;
 }
 
 void comm_destroy(Comm* c) {
   if (!c) return;
+  if (c->halo && c->halo != c->comm) api().CommDestroy(c->halo);
   if (c->comm) api().CommDestroy(c->comm);
   delete c;
 }
@@ -100,12 +110,12 @@ void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, d
   for (int f = 0; f < nfields; ++f) {
     const double* fb = base + f * fstride;
     if (cm->rank > 0) {
-      ck(api().Send(fb, (size_t)np, ncclDouble, cm->rank - 1, cm->comm, st), "ncclSend");
-      ck(api().Recv(glo + f * np, (size_t)np, ncclDouble, cm->rank - 1, cm->comm, st), "ncclRecv");
+      ck(api().Send(fb, (size_t)np, ncclDouble, cm->rank - 1, cm->halo, st), "ncclSend");
+      ck(api().Recv(glo + f * np, (size_t)np, ncclDouble, cm->rank - 1, cm->halo, st), "ncclRecv");
     }
     if (cm->rank < cm->nranks - 1) {
-      ck(api().Send(fb + last, (size_t)np, ncclDouble, cm->rank + 1, cm->comm, st), "ncclSend");
-      ck(api().Recv(ghi + f * np, (size_t)np, ncclDouble, cm->rank + 1, cm->comm, st), "ncclRecv");
+      ck(api().Send(fb + last, (size_t)np, ncclDouble, cm->rank + 1, cm->halo, st), "ncclSend");
+      ck(api().Recv(ghi + f * np, (size_t)np, ncclDouble, cm->rank + 1, cm->halo, st), "ncclRecv");
     }
   }
   ck(api().GroupEnd(), "ncclGroupEnd");
@@ -120,12 +130,14 @@ void comm_halo_n(pfh_ctx* c, const double* base, int nplanes, double* glo, doubl
   const long long last = (long long)(c->m3.nzl - nplanes) * c->nplane;
   ck(api().GroupStart(), "ncclGroupStart");
   if (cm->rank > 0) {
-    ck(api().Send(base, cnt, ncclDouble, cm->rank - 1, cm->comm, st), "ncclSend");
-    ck(api().Recv(glo, cnt, ncclDouble, cm->rank - 1, cm->comm, st), "ncclRecv");
+    ck(api().Send(base, cnt, ncclDouble, cm->rank - 1, cm->halo, st), "ncclSend");
+    ck(api().Recv(glo, cnt, ncclDouble, cm->rank - 1, cm->halo, st), "ncclRecv");
   }
   if (cm->rank < cm->nranks - 1) {
-    ck(api().Send(base + last, cnt, ncclDouble, cm->rank + 1, cm->comm, st), "ncclSend");
-    ck(api().Recv(ghi, cnt, ncclDouble, cm->rank + 1, cm->comm, st), "ncclRecv");
+    ck(api().Send(base + last, cnt, ncclDouble, cm->rank + 1, cm->halo, st), "ncclSend");
+    ck(api().Recv(ghi, cnt, ncclDouble, cm->rank + 1, cm->halo, st), "ncclRecv");
   }
   ck(api().GroupEnd(), "ncclGroupEnd");
 }
+
+bool comm_halo_is_separate(const pfh_ctx* c) { return c->comm != nullptr && c->comm->halo != c->comm->comm; }

@@ -141,6 +141,9 @@ struct pfh_ctx {
   cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr;
   bool overlap = true;
   const double* gS_prefetched = nullptr;  // scalar field whose ghost planes are already travelling into gS (ev_halo)
+  const double* gR_prefetched = nullptr;  // right-hand side whose wide ghost planes are already travelling into gR (ev_rhs)
+  int gR_prefetched_w = 0;
+  cudaEvent_t ev_rhs = nullptr;
   const double* gX_prefetched = nullptr;  // state vector whose ghost planes are already travelling into gX (ev_halo): the
                                           // wide-ghost preconditioner ships its result for the J.v that follows
   double* d_tables = nullptr;
@@ -324,6 +327,9 @@ void v_combine(pfh_ctx* c, const double* V, long long stride, int nv, const doub
 void v_multidot32(pfh_ctx* c, const float* V, long long stride, int nv, const double* w, long long n, double* host_out);
 void v_multiaxpy32(pfh_ctx* c, const float* V, long long stride, int nv, const double* h, const double* w, double scale,
                    double* out, float* out32, long long n, double* norm2);
+// called by v_multiaxpy32 between the launch of its last kernel and the (blocking) read of the norm: lets the solver
+// start shipping the ghost planes of the new vector while the host waits for the reduction
+void s_after_vector_written(pfh_ctx* c, const double* vec);
 void v_combine32(pfh_ctx* c, const float* V, long long stride, int nv, const double* y, double* out, long long n);
 double v_norm2(pfh_ctx* c, const double* x, long long n);  // global ||x||_2^2 on the host
 // finish a two-stage reduction: sums d_partial[nblocks][nvals] -> allreduce -> host; returns h_red
@@ -340,6 +346,7 @@ void comm_halo(pfh_ctx* c, const double* base, long long fstride, int nfields, d
 // neighbour's last planes, ghi the upper neighbour's first planes
 void comm_halo_n(pfh_ctx* c, const double* base, int nplanes, double* glo, double* ghi, cudaStream_t stream = nullptr);
 int comm_unique_id(void* out);
+bool comm_halo_is_separate(const pfh_ctx* c);  // the halo exchanges have their own communicator (may overlap a reduction)
 
 // ---- solver (pfh_solver.cpp) ----
 void s_exchange_state(pfh_ctx* c, const double* u, double* glo, double* ghi);

@@ -28,6 +28,7 @@
 // width.  This serves both the classic one-ghost-plane layout and the wide-ghost preconditioner of the multi-GPU
 // path, where Chebyshev sweeps run redundantly on a shrinking halo instead of exchanging a plane per sweep.
 #include <algorithm>
+#include <unordered_map>
 
 #include "pfh_tma.cuh"
 #include "pfh_vertex.cuh"
@@ -404,25 +405,34 @@ void scalar_launch(pfh_ctx* c, const ScalarOp& op, ScalarParams& P, bool use_tma
 
 // ---- tensor-map cache ----
 namespace {
-struct TmapEntry {
+struct TmapKey {
   const void* p;
   int nxv, nyv, nz, bx, by;
-  CUtensorMap map;
+  bool operator==(const TmapKey& o) const { return p == o.p && nz == o.nz && bx == o.bx && by == o.by && nxv == o.nxv && nyv == o.nyv; }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.p) >> 4;
+    h = h * 1000003u ^ (size_t)k.nz;
+    h = h * 1000003u ^ (size_t)(k.bx * 64 + k.by);
+    return h;
+  }
 };
 struct TmapCache {
-  std::vector<TmapEntry> e;
+  std::unordered_map<TmapKey, CUtensorMap, TmapHash> e;
 };
 }  // namespace
 
 CUtensorMap pfh_tensor_map(pfh_ctx* c, const double* ptr, int nxv, int nyv, int nz, int bx, int by) {
   if (c->tmap_cache == nullptr) c->tmap_cache = new TmapCache;
   TmapCache* tc = static_cast<TmapCache*>(c->tmap_cache);
-  for (const TmapEntry& t : tc->e)
-    if (t.p == ptr && t.nz == nz && t.bx == bx && t.by == by && t.nxv == nxv && t.nyv == nyv) return t.map;
-  if (tc->e.size() >= 512) tc->e.clear();  // caller-owned buffers may come and go
-  TmapEntry t{ptr, nxv, nyv, nz, bx, by, tma::make_map(ptr, nxv, nyv, nz, bx, by)};
-  tc->e.push_back(t);
-  return t.map;
+  const TmapKey key{ptr, nxv, nyv, nz, bx, by};
+  auto it = tc->e.find(key);
+  if (it != tc->e.end()) return it->second;
+  if (tc->e.size() >= 4096) tc->e.clear();  // caller-owned buffers may come and go
+  const CUtensorMap map = tma::make_map(ptr, nxv, nyv, nz, bx, by);
+  tc->e.emplace(key, map);
+  return map;
 }
 
 void pfh_tmap_cache_free(pfh_ctx* c) {

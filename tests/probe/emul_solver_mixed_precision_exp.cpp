@@ -338,6 +338,7 @@ void v_combine32(pfh_ctx*, const float* V, long long stride, int nv, const doubl
 
 // ---- communication: single rank ----
 void comm_allreduce_sum(pfh_ctx*, double*, int) {}
+bool comm_halo_is_separate(const pfh_ctx*) { return false; }
 void comm_halo(pfh_ctx*, const double*, long long, int, double*, double*, cudaStream_t) {}
 void comm_halo_n(pfh_ctx*, const double*, int, double*, double*, cudaStream_t) {}
 
