@@ -32,7 +32,12 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
-    return _compile_all(os.path.join(HERE, "build"), LIB, [], verbose)
+    if force:
+        os.environ["PFH_FORCE_BUILD"] = "1"
+    try:
+        return _compile_all(os.path.join(HERE, "build"), LIB, [], verbose)
+    finally:
+        os.environ.pop("PFH_FORCE_BUILD", None)
 
 
 def build_user(source, tag, force=False):
@@ -49,12 +54,35 @@ def build_user(source, tag, force=False):
             f.write(source)
     if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in _deps() + [hdr]):
         return lib
-    return _compile_all(os.path.join(jit, "build_" + tag), lib,
-                        ['-DPFH_USER_PROBLEM_HEADER="%s"' % hdr, "-DPFH_ONLY_USER"], False, ["-Xlinker", "-Bsymbolic"])
+    if force:
+        os.environ["PFH_FORCE_BUILD"] = "1"
+    try:
+        return _compile_all(os.path.join(jit, "build_" + tag), lib,
+                            ['-DPFH_USER_PROBLEM_HEADER="%s"' % hdr, "-DPFH_ONLY_USER"], False, ["-Xlinker", "-Bsymbolic"])
+    finally:
+        os.environ.pop("PFH_FORCE_BUILD", None)
 
 
 def _compile_all(objdir, lib, defines, verbose, link_flags=()):
+    """Compile and link under an exclusive file lock (every rank of a torchrun job builds the same model at the same
+    time): the first process builds into a temporary name and renames it into place, the others wait and find it done."""
+    import fcntl
     os.makedirs(objdir, exist_ok=True)
+    with open(lib + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            deps = _deps() + [d.split('"')[1] for d in defines if d.startswith("-DPFH_USER_PROBLEM_HEADER=")]
+            if os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps) and not os.environ.get("PFH_FORCE_BUILD"):
+                return lib                           # another process built it while this one waited for the lock
+            tmp = lib + ".tmp%d" % os.getpid()
+            _compile_locked(objdir, tmp, defines, verbose, link_flags)
+            os.replace(tmp, lib)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return lib
+
+
+def _compile_locked(objdir, lib, defines, verbose, link_flags=()):
     flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH + list(defines)
     if verbose:
         flags += ["-Xptxas", "-v"]

@@ -19,6 +19,10 @@
 //          (the (kappa K + M_f'') block of the Cahn-Hilliard Jacobian for the full Schur preconditioner)    24 B/vertex
 //  KIND 2: residual R(u; u0): operand fields u, extra ring fields u0 of the fields in(.)                       40 (CH)
 //  F32Q  : KIND 0 of a QUARTIC problem with the quadrature block in single precision (opt-in experiment).
+//
+// Measured dead end (round 2, profiles/README.md): cube and vertex phases as different WARPS of one CTA (10 cube warps + 8
+// vertex warps + a producer warp, one CTA per SM because the cube threads want ~100 registers) is correct but slower,
+// 4.6 ms against 4.2 ms at 512^3: 19 warps per SM do not keep the fp64 pipe busier than three CTAs of this kernel.
 #include "pfh_tma.cuh"
 #include "pfh_vertex.cuh"
 

@@ -22,8 +22,8 @@ def fam(t, k):
 
 for loader in (1,):
     ctx.set_option("use_tma_loader", loader)
-    for v in (0, 1, 2, 3, 4, 5):
-        for zc in (32, 64):
+    for v in (0, 3):
+        for zc in (32,):
             ctx.set_option("scalar_variant", v)
             ctx.set_option("scalar_zchunk", zc)
             ctx.precond_setup(pc_variant=1, pc_sweeps_mass=3, pc_sweeps_shifted=4)
@@ -46,7 +46,7 @@ y = ctx.new_vector()
 for loader in (1,):
     ctx.set_option("use_tma_loader", loader)
     for jv in (0, 1):
-        for zc in (32, 64):
+        for zc in (32, 64, 128):
             ctx.set_option("jac_variant", jv); ctx.set_option("jac_zchunk", zc)
             ctx.jac_apply(X, out=y)
             ctx.residual(U, X, out=z)

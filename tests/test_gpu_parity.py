@@ -202,7 +202,7 @@ def test_tma_kernels_match_gather_kernels():
         ctx.dt = 0.8
         out = {}
         for key, (tma, loader, variant, jvar) in {"gather": (0, 1, 0, 0), "tma": (1, 1, 0, 0), "cpasync": (1, 0, 0, 0), "v1": (1, 1, 1, 1),
-                                                  "v2": (1, 1, 2, 0), "v3": (1, 0, 3, 1), "v4": (1, 1, 4, 0)}.items():
+                                                  "v2": (1, 1, 2, 1), "v3": (1, 0, 3, 0), "v4": (1, 1, 4, 0), "v5": (1, 1, 5, 1)}.items():
             ctx.set_option("use_tma", tma)
             ctx.set_option("use_tma_loader", loader)
             ctx.set_option("scalar_variant", variant)
