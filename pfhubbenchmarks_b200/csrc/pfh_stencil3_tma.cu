@@ -23,6 +23,8 @@
 // Measured dead end (round 2, profiles/README.md): cube and vertex phases as different WARPS of one CTA (10 cube warps + 8
 // vertex warps + a producer warp, one CTA per SM because the cube threads want ~100 registers) is correct but slower,
 // 4.6 ms against 4.2 ms at 512^3: 19 warps per SM do not keep the fp64 pipe busier than three CTAs of this kernel.
+#include <algorithm>
+
 #include "pfh_tma.cuh"
 #include "pfh_vertex.cuh"
 
@@ -49,6 +51,10 @@ __global__ void __launch_bounds__(NT, OCC)
     k3_jac_tma(const __grid_constant__ MapSet<(KIND == 1 ? 1 : P::NF) + P::NIN> maps,
                const __grid_constant__ JacParams<(KIND == 1 ? 1 : P::NF) + P::NIN> A, P prob) {
   constexpr bool CROW = KIND == 1, RES = KIND == 2;
+  // KIND 0 / 2: every vertex is treated as an interior row here (symmetric-pair sums, constants from the parameter bank,
+  // no row registers); the stores of the boundary vertices are skipped and k3_jac_shell computes them.  KIND 1 keeps the
+  // general rows in the kernel.
+  constexpr bool SHELL = !CROW;
   constexpr int NX = CROW ? 1 : P::NF;  // ring-buffered operand fields x, followed by NIN fields (u for J.v, u0 for RES)
   constexpr int NFLD = NX + P::NIN;
   constexpr int W = TX + 4, H = TY + 2;  // x halo of 2 (16-byte aligned TMA box start)
@@ -197,13 +203,9 @@ __global__ void __launch_bounds__(NT, OCC)
       }
       if (it >= 1) {
         const int gz = m.z0 + l;
-        const int type = (gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1)) * 9 + txy;
-        vtx::Row3 row;
-        vtx::get_row3(m, type, row);
         const int c = (vtx_y + 1) * W + vtx_x + 2;
-        double Ms[NX], Ks[NX];
-#pragma unroll
-        for (int f = 0; f < NX; ++f) {
+        // (M v)_i and (K v)_i of the field staged as ring field f
+        auto lin_sums = [&](int f, const vtx::Row3& row, double& Ms, double& Ks) {
           const double* S0 = stage(f, it - 1);
           const double* S1 = stage(f, it);
           const double* S2 = stage(f, it + 1);
@@ -212,8 +214,26 @@ __global__ void __launch_bounds__(NT, OCC)
           v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
           v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
           v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
-          vtx::mk_sums3(row, v, Ms[f], Ks[f]);
+          if constexpr (SHELL) {
+            // interior row: symmetric, one coefficient per +- pair; K has no diagonal-neighbour entries
+            const double px = v[1] + v[2], py = v[3] + v[4], pz = v[5] + v[6];
+            Ms = (m.mI[0] * v[0] + m.mI[1] * px + m.mI[3] * py + m.mI[5] * pz) +
+                 (m.mI[7] * (v[7] + v[8]) + m.mI[9] * (v[9] + v[10]) + m.mI[11] * (v[11] + v[12]) + m.mI[13] * (v[13] + v[14]));
+            Ks = m.kI[0] * v[0] + m.kI[1] * px + m.kI[3] * py + m.kI[5] * pz;
+          } else {
+            vtx::mk_sums3(row, v, Ms, Ks);
+          }
+        };
+        vtx::Row3 row;
+        bool store = true;
+        if constexpr (SHELL) {
+          store = ix >= 1 && ix <= m.nxv - 2 && iy >= 1 && iy <= m.nyv - 2 && gz >= 1 && gz <= m.nzv - 2;
+        } else {
+          vtx::get_row3(m, (gz == 0 ? 0 : (gz == m.nzv - 1 ? 2 : 1)) * 9 + txy, row);
         }
+        double Ms[NX], Ks[NX];
+#pragma unroll
+        for (int f = 0; f < NX; ++f) lin_sums(f, row, Ms[f], Ks[f]);
         const long long i = (long long)l * m.nxy + (long long)iy * m.nxv + ix;
         if (CROW) {
           A.out[i] = L.Mc[P::out(0)][P::in(0)] * Ms[0] + L.Kc[P::out(0)][P::in(0)] * Ks[0] + acc_hi[0] + lo[0];
@@ -231,26 +251,63 @@ __global__ void __launch_bounds__(NT, OCC)
           if (RES) {  // - Mp_a M u0_a for the fields with a time derivative
 #pragma unroll
             for (int f = 0; f < P::NIN; ++f) {
-              const double* S0 = stage(NX + f, it - 1);
-              const double* S1 = stage(NX + f, it);
-              const double* S2 = stage(NX + f, it + 1);
-              double v[PFH_NOFF3], ms0, ks0;
-              v[0] = S1[c]; v[1] = S1[c + 1]; v[2] = S1[c - 1]; v[3] = S1[c + W]; v[4] = S1[c - W];
-              v[5] = S2[c]; v[6] = S0[c]; v[7] = S1[c + W + 1]; v[8] = S1[c - W - 1];
-              v[9] = S2[c + W]; v[10] = S0[c - W]; v[11] = S2[c + 1]; v[12] = S0[c - 1];
-              v[13] = S2[c + W + 1]; v[14] = S0[c - W - 1];
-              vtx::mk_sums3(row, v, ms0, ks0);
+              double ms0, ks0;
+              lin_sums(NX + f, row, ms0, ks0);
               y[P::in(f)] -= L.Mp[P::in(f)] * ms0;
             }
           }
+          if (store) {
 #pragma unroll
-          for (int aa = 0; aa < P::NF; ++aa) A.out[aa * m.n_owned + i] = y[aa];
+            for (int aa = 0; aa < P::NF; ++aa) A.out[aa * m.n_owned + i] = y[aa];
+          }
         }
       }
 #pragma unroll
       for (int o = 0; o < P::NOUT; ++o) acc_hi[o] = hi[o];
     }
   }
+}
+
+// Boundary vertices of the owned slab (one layer) through the general per-vertex operator of pfh_vertex.cuh, gathered
+// from global memory: what the cube-centric kernel skips.  Index space as in k3_scalar_shell.
+template <int NF>
+struct ShellFields {
+  FieldRef U[NF], X[NF], U0[NF];
+};
+__device__ __forceinline__ int jshell_index(int j, int n) { return (2 >= n || j < 1) ? j : n - 2 + j; }
+
+template <class P, bool JAC>
+__global__ void __launch_bounds__(128) k3_jac_shell(P prob, Mesh3 m, LinCoefs L, ShellFields<P::NF> F, double* __restrict__ out, int nzs,
+                                                    int zs0, int zs1, int zi0, int nzi, long long n_threads) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_threads) return;
+  const int csx = min(2, m.nxv), csy = min(2, m.nyv);
+  const long long n1 = (long long)nzs * m.nxy, n2 = (long long)nzi * csy * m.nxv;
+  int ix, iy, zl;
+  if (t < n1) {
+    const int j = (int)(t / m.nxy);
+    const long long r = t - (long long)j * m.nxy;
+    zl = j == 0 ? zs0 : zs1;
+    iy = (int)(r / m.nxv);
+    ix = (int)(r - (long long)iy * m.nxv);
+  } else if (t < n1 + n2) {
+    const long long r = t - n1, per = (long long)csy * m.nxv;
+    zl = zi0 + (int)(r / per);
+    const long long q = r % per;
+    iy = jshell_index((int)(q / m.nxv), m.nyv);
+    ix = (int)(q % m.nxv);
+  } else {
+    const long long r = t - n1 - n2, per = (long long)(m.nyv - csy) * csx;
+    zl = zi0 + (int)(r / per);
+    const long long q = r % per;
+    iy = 1 + (int)(q / csx);
+    ix = jshell_index((int)(q % csx), m.nxv);
+  }
+  double o[P::NF];
+  vtx::vertex_op3<P, JAC>(prob, m, L, F.U, F.X, F.U0, ix, iy, zl, o);
+  const long long i = (long long)zl * m.nxy + (long long)iy * m.nxv + ix;
+#pragma unroll
+  for (int a = 0; a < P::NF; ++a) out[a * m.n_owned + i] = o[a];
 }
 
 constexpr int J_TX = 32, J_TY = 8, J_NT = 320;
@@ -317,11 +374,53 @@ bool jac_launch(pfh_ctx* c, const LinCoefs& L, const JacOperand* ops, double* ou
       maps.hi[f] = hi ? pfh_tensor_map(c, ops[f].ghi, m.nxv, m.nyv, 1, J_TX + 4, J_TY + 2) : maps.main[f];
     }
   }
+  // boundary shell of the slab (KIND 0 / 2), on aux_stream underneath the cube-centric kernel
+  bool fork = false;
+  if constexpr (KIND != 1) {
+    ShellFields<P::NF> F;
+    memset(&F, 0, sizeof F);
+    auto ref = [&](const JacOperand& o) { return FieldRef{o.base, lo ? o.glo : nullptr, hi ? o.ghi : nullptr}; };
+    for (int b = 0; b < P::NF; ++b) {
+      F.U[b] = F.X[b] = F.U0[b] = ref(ops[b]);          // operand fields: x for J.v, u for the residual
+    }
+    for (int f = 0; f < P::NIN; ++f) {
+      if (KIND == 0) F.U[P::in(f)] = ref(ops[P::NF + f]);  // linearisation point
+      else F.U0[P::in(f)] = ref(ops[P::NF + f]);           // previous step
+    }
+    int zs[2] = {0, 0}, nzs = 0, zi0 = 0, nzi = 0;
+    for (int zl = 0; zl < m.nzl; ++zl) {
+      const int gz = m.z0 + zl;
+      if (gz == 0 || gz == m.nzv - 1) {
+        if (nzs < 2) zs[nzs] = zl;
+        ++nzs;
+      } else {
+        if (nzi == 0) zi0 = zl;
+        ++nzi;
+      }
+    }
+    PFH_CHECK(nzs <= 2, "internal: more than two boundary planes in a slab");
+    const long long csx = std::min(2, m.nxv), csy = std::min(2, m.nyv);
+    const long long n_threads = (long long)nzs * m.nxy + (long long)nzi * (csy * m.nxv + (m.nyv - csy) * csx);
+    if (n_threads > 0) {
+      fork = c->shell_async && c->aux_stream != nullptr;
+      cudaStream_t sst = fork ? c->aux_stream : c->stream;
+      if (fork) {
+        PFH_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        PFH_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+      }
+      const unsigned nb = (unsigned)((n_threads + 127) / 128);
+      k3_jac_shell<P, KIND == 0><<<nb, 128, 0, sst>>>(prob, m, L, F, out, nzs, zs[0], zs[1], zi0, nzi, n_threads);
+      PFH_CUDA(cudaGetLastError());
+      c->launches++;
+      if (fork) PFH_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+    }
+  }
   const dim3 grid((m.nxv + J_TX - 1) / J_TX, (m.nyv + J_TY - 1) / J_TY, (m.nzl + A.zchunk - 1) / A.zchunk);
   constexpr size_t smem = jac_smem<P, KIND, NS>();
   if (use_tma) k3_jac_tma<P, KIND, J_TX, J_TY, J_NT, NS, OCC, true, F32Q><<<grid, J_NT, smem, c->stream>>>(maps, A, prob);
   else k3_jac_tma<P, KIND, J_TX, J_TY, J_NT, NS, OCC, false, F32Q><<<grid, J_NT, smem, c->stream>>>(maps, A, prob);
   PFH_CUDA(cudaGetLastError());
+  if (fork) PFH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   return true;
 }
 

@@ -50,3 +50,22 @@ REFERENCE_MESH = {  # the meshes the reference drivers build
 
 def oracle_step_3d(D, u, u0, dt, rtol=1e-11, atol=1e-10):
     return D.solve_step(u, u0, dt, atol=atol, linear=krylov.make_linear(rtol=rtol, n_m=4, n_a=8))
+
+
+def lu_once():
+    """linear= callback for Discretization.solve_step that factors the FIRST Jacobian of a step and solves the later
+    Newton systems by GMRES on the exact Jacobian preconditioned with that factorisation (a handful of iterations to
+    1e-13): the same Newton iterates to solver tolerance, one sparse LU per step instead of one per Newton iteration."""
+    import scipy.sparse.linalg as spla
+    cache = {}
+
+    def linear(disc, J, rhs, u, dt):
+        Jc = J.tocsc()
+        if "lu" not in cache:
+            cache["lu"] = spla.splu(Jc)
+            return cache["lu"].solve(rhs)
+        M = spla.LinearOperator(Jc.shape, matvec=cache["lu"].solve)
+        x, info = spla.gmres(Jc, rhs, M=M, rtol=1e-13, atol=0.0, restart=30, maxiter=10)
+        assert info == 0, info
+        return x
+    return linear

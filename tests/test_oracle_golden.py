@@ -3,7 +3,7 @@ by oracle/make_golden.py from /root/reference/results).  CPU only."""
 import numpy as np
 import pytest
 
-from helpers import REFERENCE_MESH, discretization, rel_l2
+from helpers import REFERENCE_MESH, discretization, lu_once, rel_l2
 from oracle import mesh as omesh
 
 
@@ -63,11 +63,11 @@ def test_bench2_ic_quirk_and_step_kat(golden):
     s1 = np.zeros((6, D.nv)); s1[rows] = g["fields"][1]
     assert abs(D.energy(s0) / csv[0, 1] - 1) < 1e-10 and abs(D.mass(s0) / csv[0, 2] - 1) < 1e-10
     u0 = D.prob.ic(D.mesh)
-    u, n, ok = D.solve_step(u0, u0, 0.01)            # IC -> snapshot 0 pins the i/ii quirk (pfbase.py:285-286)
+    u, n, ok = D.solve_step(u0, u0, 0.01, linear=lu_once())            # IC -> snapshot 0 pins the i/ii quirk (pfbase.py:285-286)
     assert ok
     for r in rows:
         assert rel_l2(u[r], s0[r]) < 1e-9
-    u, n, ok = D.solve_step(s0, s0, g["times"][1] - g["times"][0])
+    u, n, ok = D.solve_step(s0, s0, g["times"][1] - g["times"][0], linear=lu_once())
     assert ok
     for r in rows:
         assert rel_l2(u[r], s1[r]) < 1e-11
@@ -91,7 +91,25 @@ def test_bench3_first_csv_row(golden):
     D = discretization("bench3", *REFERENCE_MESH["bench3"])
     csv = golden["csv"]["bench3"]
     u0 = D.prob.ic(D.mesh)
-    u, n, ok = D.solve_step(u0, u0, csv[0, 0])
+    u, n, ok = D.solve_step(u0, u0, csv[0, 0], linear=lu_once())     # one 491k x 491k sparse LU instead of one per Newton iteration
     assert ok
     assert abs(D.energy(u) / csv[0, 1] - 1) < 1e-11
     assert abs(D.mass(u) - csv[0, 2]) < 1e-10
+
+
+def test_b13d_trajectory_fixtures_are_consistent():
+    """tests/golden/b13d_{51,52}.npz (oracle/make_golden_b13d.py; the GPU suite compares the product with them): 100 steps
+    of the section-8(d) dt list, solute conserved to round-off, free energy decaying monotonically, fields of the right size
+    and within the double-well range."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    for nv in (51, 52):
+        g = np.load(os.path.join(here, "golden", "b13d_%d.npz" % nv))
+        n = int(g["ncell"])
+        assert n + 1 == nv and int(g["nsteps"]) == 100 and float(g["length"]) == 2.0 * n
+        dts = np.diff(np.concatenate([[0.0], g["time"]]))
+        assert np.allclose(dts[:5], [0.1, 0.2, 0.4, 0.8, 1.6]) and np.allclose(dts[5:], 1.6)
+        assert np.all(np.diff(g["energy"]) < 0.0)
+        assert np.max(np.abs(g["solute"] / g["solute"][0] - 1.0)) < 1e-13
+        for key in ("c_step10", "c_final"):
+            assert g[key].shape == (nv ** 3,) and 0.2 < g[key].min() < g[key].max() < 0.8
