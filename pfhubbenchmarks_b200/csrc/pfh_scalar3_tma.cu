@@ -59,6 +59,7 @@ struct ScalarParams {
   double am, ak, a, b, bdI, b0;
   double ob0;                  // MODE 2 without a zprev operand: zprev = ob0 D^-1 r (0: zprev = 0)
   double s1I, ob0I;            // b0 / diag and ob0 / diag of the interior row
+  double rowsB[9][PFH_NOFF3];  // MODE 0 / 2: rows of am M + ak K by x-y boundary type (ty*3+tx) on a plane away from the z boundaries
   int shell;                   // depth of the boundary shell the staged kernel leaves to k3_scalar_shell (1; MODE 3: 2)
   Coef8 cS;
   InvDiag27 invd;
@@ -174,8 +175,12 @@ __global__ void __launch_bounds__(TX* TY + 32, MINB)
   const int lx = tid % TX, ly = tid / TX;
   const int ix = x0 + lx, iy = y0 + ly;
   const int d = P.shell;
-  // vertices this kernel stores: inside the mesh and not in the boundary shell (k3_scalar_shell computes those)
-  const bool store_xy = ix >= d && ix < m.nxv - d && iy >= d && iy < m.nyv - d;
+  // Vertices this kernel stores.  MODE 3: inside the mesh and not within `shell` (2) layers of any boundary.  MODE 0 / 2: every
+  // vertex of the planes away from the z boundaries -- the vertices on an x or y face take their row from rowsB (fixed per
+  // thread along the march; only the warps that contain such a vertex diverge) -- k3_scalar_shell computes the rest.
+  const bool store_xy = MODE == 3 ? (ix >= d && ix < m.nxv - d && iy >= d && iy < m.nyv - d) : (ix < m.nxv && iy < m.nyv);
+  const int txy = (iy == 0 ? 0 : (iy == m.nyv - 1 ? 2 : 1)) * 3 + (ix == 0 ? 0 : (ix == m.nxv - 1 ? 2 : 1));
+  const bool face = MODE != 3 && txy != 4 && store_xy;
   const int c = (ly + 1) * W + lx + 2;  // this vertex in a stencil tile
   const int pc = ly * TX + lx;          // and in a pointwise tile
   double* outp = P.out + ((long long)zb * m.nxy + (long long)iy * m.nxv + ix);
@@ -209,6 +214,7 @@ __global__ void __launch_bounds__(TX* TY + 32, MINB)
     const double* Ot = Rt + NC;
     const int gz = P.gz0 + zb + k;
     const bool store = store_xy && gz >= d && gz < m.nzv - d;
+    double bd = P.bdI;
     const double rv = P.has_r ? Rt[pc] : 0.0;
     double ov = P.has_o ? Ot[pc] : 0.0;
     const double v0 = pb[0], v3 = pb[1], v1 = pb[2], v7 = pb[3];
@@ -228,14 +234,26 @@ __global__ void __launch_bounds__(TX* TY + 32, MINB)
     t1 += P.cS.c[5] * (v9 + v10);
     s0 += P.cS.c[6] * (v11 + v12);
     t1 += P.cS.c[7] * (v13 + v14);
-    const double Av = s0 + t1;
+    double Av = s0 + t1;
+    if (MODE != 3 && face) {
+      // a vertex on an x or y face (or a z-parallel edge): its own row, out-of-domain operands are the zeros TMA filled in
+      const double* row = P.rowsB[txy];
+      double a0 = row[0] * v0 + row[1] * v1, a1 = row[2] * v2 + row[3] * v3;
+      a0 += row[4] * v4; a1 += row[5] * v5; a0 += row[6] * v6; a1 += row[7] * v7;
+      a0 += row[8] * v8; a1 += row[9] * v9; a0 += row[10] * v10; a1 += row[11] * v11;
+      a0 += row[12] * v12; a1 += row[13] * v13; a0 += row[14] * v14;
+      Av = a0 + a1;
+      bd = P.b * P.invd.v[9 + txy];
+      if (MODE == 2 && P.ob0 != 0.0) ov = (P.ob0 * P.invd.v[9 + txy]) * rv;
+    } else if (MODE == 2 && P.ob0I != 0.0) {
+      ov = P.ob0I * rv;  // the first iterate recomputed from r, exactly as MODE 3 would store it
+    }
     if (store) {
       if (MODE == 0) {
         *outp = P.a * rv + Av;
         if (out1p != nullptr) *out1p = v0;
       } else if (MODE == 2) {
-        if (P.ob0I != 0.0) ov = P.ob0I * rv;  // the first iterate recomputed from r, exactly as MODE 3 would store it
-        *outp = v0 + P.a * (v0 - ov) + P.bdI * (rv - Av);
+        *outp = v0 + P.a * (v0 - ov) + bd * (rv - Av);
       } else {
         const double z1 = P.s1I * v0;
         if (out1p != nullptr) *out1p = z1;
@@ -483,6 +501,9 @@ void k3_scalar_launch(pfh_ctx* c, const ScalarOp& op) {
     pfh_build_tables3(mm, c->h_mT, c->h_kT);
   }
   for (int t = 0; t < 27; ++t) P.invd.v[t] = 1.0 / (op.am * c->h_mT[t * PFH_NOFF3] + op.ak * c->h_kT[t * PFH_NKOFF3]);
+  for (int t = 0; t < 9; ++t)
+    for (int o = 0; o < PFH_NOFF3; ++o)
+      P.rowsB[t][o] = op.am * c->h_mT[(9 + t) * PFH_NOFF3 + o] + (o < PFH_NKOFF3 ? op.ak * c->h_kT[(9 + t) * PFH_NKOFF3 + o] : 0.0);
   P.s1I = op.b0 * P.invd.v[13];
   P.ob0I = P.ob0 * P.invd.v[13];
   P.shell = op.mode == 3 ? 2 : 1;
@@ -526,7 +547,8 @@ void k3_scalar_launch(pfh_ctx* c, const ScalarOp& op) {
     }
   }
   const long long csx = std::min(2 * d, m.nxv), csy = std::min(2 * d, m.nyv);
-  const long long n_threads = (long long)nzs * m.nxy + (long long)nzi * (csy * m.nxv + (m.nyv - csy) * csx);
+  // MODE 0 / 2: the staged kernel does the x and y faces itself; only the planes on a z boundary are left
+  const long long n_threads = op.mode == 3 ? (long long)nzs * m.nxy + (long long)nzi * (csy * m.nxv + (m.nyv - csy) * csx) : (long long)nzs * m.nxy;
   // The shell kernel reads what the staged kernel reads and stores the vertices it skips: the two are independent, so
   // the (latency-bound, partly uncoalesced) gather runs on aux_stream underneath the staged kernel.
   const bool fork = c->shell_async && c->aux_stream != nullptr && n_threads > 0;
