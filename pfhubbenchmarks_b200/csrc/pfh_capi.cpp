@@ -200,7 +200,9 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     }
     c->d_partial = pfh_alloc(c, (size_t)PFH_RED_MAXBLOCKS * PFH_RED_MAXVALS);
     c->d_red = pfh_alloc(c, PFH_RED_MAXVALS);
-    PFH_CUDA(cudaMallocHost(&c->h_red, PFH_RED_MAXVALS * sizeof(double)));
+    PFH_CUDA(cudaHostAlloc(&c->h_red, (PFH_RED_MAXVALS + 8) * sizeof(double), cudaHostAllocMapped));
+    memset(c->h_red, 0, (PFH_RED_MAXVALS + 8) * sizeof(double));
+    c->h_seq = reinterpret_cast<unsigned long long*>(c->h_red + PFH_RED_MAXVALS);
     pfh_default_solver_opts(&c->pc_opts);
 
     pfh_config cc = *cfg;

@@ -172,7 +172,9 @@ struct pfh_ctx {
   // reductions
   double* d_partial = nullptr;  // [PFH_RED_MAXBLOCKS][PFH_RED_MAXVALS]
   double* d_red = nullptr;      // final values (device)
-  double* h_red = nullptr;      // pinned host mirror
+  double* h_red = nullptr;      // mapped pinned host memory the final reduction kernel writes into (zero copy)
+  unsigned long long* h_seq = nullptr;  // sequence number next to it, written after the values; the host polls it
+  unsigned long long red_seq = 0;
 
   // preconditioner state
   pfh_solver_opts pc_opts;

@@ -198,38 +198,72 @@ __global__ void __launch_bounds__(TPB) k_norm2(const double* __restrict__ x, lon
   }
 }
 
-// second stage: red[v] = sum_b partial[b][v], fixed order => deterministic
+// second stage: red[v] = sum_b partial[b][v], fixed order => deterministic.  One warp per value (8 at a time).  With
+// `host` given (single rank) the results also go straight into mapped pinned host memory, followed by a sequence number
+// the host polls: no device-to-host copy, no cudaStreamSynchronize on the Krylov iteration's critical path.
 __global__ void __launch_bounds__(TPB) k_reduce_final(const double* __restrict__ partial, int nblocks, int nvals,
-                                                      double* __restrict__ red) {
-  __shared__ double sh[TPB / 32];
-  for (int v = 0; v < nvals; ++v) {
+                                                      double* __restrict__ red, double* host, unsigned long long* host_seq,
+                                                      unsigned long long seq) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int v = wid; v < nvals; v += TPB / 32) {
     double acc = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += TPB) acc += partial[b * PFH_RED_MAXVALS + v];
+    for (int b = lane; b < nblocks; b += 32) acc += partial[b * PFH_RED_MAXVALS + v];
     acc = warp_sum(acc);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) sh[wid] = acc;
+    if (lane == 0) {
+      red[v] = acc;
+      if (host != nullptr) host[v] = acc;
+    }
+  }
+  if (host != nullptr) {
+    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-      double s = 0.0;
-#pragma unroll
-      for (int q = 0; q < TPB / 32; ++q) s += sh[q];
-      red[v] = s;
+      *reinterpret_cast<volatile unsigned long long*>(host_seq) = seq;
+      __threadfence_system();
     }
-    __syncthreads();
+  }
+}
+
+// after an allreduce: the reduced values from device memory into the mapped host buffer + sequence number
+__global__ void k_publish(const double* __restrict__ red, int nvals, double* host, unsigned long long* host_seq, unsigned long long seq) {
+  if (threadIdx.x < nvals) host[threadIdx.x] = red[threadIdx.x];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned long long*>(host_seq) = seq;
+    __threadfence_system();
   }
 }
 }  // namespace
 
 const double* pfh_reduce_finish(pfh_ctx* c, int nblocks, int nvals) {
   PFH_CHECK(nvals <= PFH_RED_MAXVALS && nblocks <= PFH_RED_MAXBLOCKS, "reduction scratch too small");
+  const bool multi = c->cfg.nranks > 1;
+  const unsigned long long seq = ++c->red_seq;
   {
     ProfScope ps(c, T_REDUCE);
-    k_reduce_final<<<1, TPB, 0, c->stream>>>(c->d_partial, nblocks, nvals, c->d_red);
+    k_reduce_final<<<1, TPB, 0, c->stream>>>(c->d_partial, nblocks, nvals, c->d_red, multi ? nullptr : c->h_red, c->h_seq, seq);
     PFH_CUDA(cudaGetLastError());
   }
-  if (c->cfg.nranks > 1) comm_allreduce_sum(c, c->d_red, nvals);
-  PFH_CUDA(cudaMemcpyAsync(c->h_red, c->d_red, nvals * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  PFH_CUDA(cudaStreamSynchronize(c->stream));
+  if (multi) {
+    comm_allreduce_sum(c, c->d_red, nvals);
+    k_publish<<<1, 64, 0, c->stream>>>(c->d_red, nvals, c->h_red, c->h_seq, seq);
+    PFH_CUDA(cudaGetLastError());
+  }
+  // wait for the sequence number in host memory; the stream is queried now and then so that a failed launch surfaces
+  const volatile unsigned long long* hs = c->h_seq;
+  for (unsigned long long spins = 1;; ++spins) {
+    if (*hs == seq) break;
+    if ((spins & 0x3fff) == 0) {
+      const cudaError_t e = cudaStreamQuery(c->stream);
+      if (e == cudaSuccess) {
+        if (*hs != seq) PFH_CUDA(cudaStreamSynchronize(c->stream));
+        PFH_CHECK(*hs == seq, "internal: reduction result did not arrive in host memory");
+        break;
+      }
+      if (e != cudaErrorNotReady) PFH_CUDA(e);
+    }
+  }
   return c->h_red;
 }
 
