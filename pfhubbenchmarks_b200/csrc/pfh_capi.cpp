@@ -1,6 +1,7 @@
 // extern "C" boundary (include/pfh_b200.h): argument checking, workspace ownership, error
 // translation.  No field data is owned here except internal workspaces and, for the *_host
 // entry points, device staging buffers for the caller's host arrays.
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 
@@ -214,6 +215,19 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
       PFH_CUDA(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
       PFH_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
       PFH_CUDA(cudaEventCreateWithFlags(&c->ev_rhs, cudaEventDisableTiming));
+    }
+    if (cfg->nranks > 1 && c->dim == 3 && cfg->nranks <= PFH_RED_MAXVALS) {
+      // smallest slab over the ranks, from the ranks themselves (the caller may have chosen any split): every rank adds
+      // its height at its own index
+      std::vector<double> h(cfg->nranks, 0.0);
+      h[cfg->rank] = (double)c->m3.nzl;
+      PFH_CUDA(cudaMemcpyAsync(c->d_red, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      comm_allreduce_sum(c, c->d_red, cfg->nranks);
+      PFH_CUDA(cudaMemcpyAsync(h.data(), c->d_red, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      PFH_CUDA(cudaStreamSynchronize(c->stream));
+      int mn = c->m3.nzl;
+      for (double v : h) mn = std::min(mn, (int)(v + 0.5));
+      c->min_slab = mn;
     }
     PFH_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
