@@ -62,7 +62,32 @@ __global__ void __launch_bounds__(TPB) k_multidot(const TV* __restrict__ V, long
 #pragma unroll
   for (int k = 0; k <= MD; ++k) acc[k] = 0.0;
   const long long nc = n / E;
-  for (long long i = blockIdx.x * (long long)TPB + threadIdx.x; i < nc; i += (long long)gridDim.x * TPB) {
+  const long long step = (long long)gridDim.x * TPB;
+  long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  // two chunks per trip: twice the loads in flight per thread (with one or two basis vectors the kernel is latency-bound)
+  for (; i + step < nc; i += 2 * step) {
+    double wa[E], wb[E];
+    load_w<E>(w, i, wa);
+    load_w<E>(w, i + step, wb);
+#pragma unroll
+    for (int k = 0; k < MD; ++k)
+      if (k < nb) {
+        double va[E], vb[E];
+        Chunk<TV>::load(V + (long long)k * stride, i, va);
+        Chunk<TV>::load(V + (long long)k * stride, i + step, vb);
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[k] += va[e] * wa[e];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[k] += vb[e] * wb[e];
+      }
+    if (WW) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[MD] += wa[e] * wa[e];
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[MD] += wb[e] * wb[e];
+    }
+  }
+  for (; i < nc; i += step) {
     double wi[E];
     load_w<E>(w, i, wi);
 #pragma unroll
