@@ -4,10 +4,11 @@
 // kernels + DOLFIN's assembler + PETSc MatMult on the reference's hot path
 // (dolfin/bench1.py:162 -> SNESSolve; SURVEY.md section 3.3, hot loops A-D).
 //
-// This file holds the general (any problem, any mesh size) gather kernels and the launch dispatch.  The 3-D
-// Cahn-Hilliard fast path -- TMA-staged scalar operators, cube-centric J.v / residual -- lives in
-// pfh_stencil3_tma.cu and is tried first; the kernels here serve the 2-D problems, odd vertex counts (TMA needs
-// 16-byte aligned rows) and as the reference the fast path is tested against.
+// This file holds the general (any problem, any mesh size) gather kernels and the launch dispatch.  The 3-D fast
+// path -- staged scalar operators (pfh_scalar3_tma.cu, any problem) and the cube-centric J.v / residual of
+// Cahn-Hilliard (pfh_stencil3_tma.cu), both with a TMA and a cp.async loader -- is tried first; the kernels here serve
+// the 2-D problems, generated models in 3-D, the boundary shells of the fast path (vtx::vertex_op3) and are the reference
+// the fast path is tested against (pfh_set_option "use_tma" 0).
 // Thread mapping: 3-D kernels use (BX x BY) tiles of an x-y plane and march along z so the three planes a vertex
 // reads stay in L1; 2-D kernels use 64 x 4 tiles with one corner vertex and one cell centre per thread.
 #include "pfh_vertex.cuh"
