@@ -214,8 +214,11 @@ def bench_case(args, workload, grid, steps, warmup, dist_env, e2e=True, fp64_pas
     stream = torch.cuda.ExternalStream(ctx.lib.pfh_stream(ctx._h), device=torch.device("cuda", local))
     dts = dt_schedule(warmup + steps)
     if workload in ("bench2", "bench3", "bench6"):      # these drivers start at dt = 1e-2 (bench2.py:222)
-        # capped at 0.08: the reference's own run rejects dt = 0.16 at t = 0.15 for bench2 (results/bench2_out.csv rows 4-5)
-        dts = [min(0.01 * 2 ** k, 0.08) for k in range(warmup + steps)]
+        # capped: the reference's own run rejects dt = 0.16 at t = 0.15 for bench2 (results/bench2_out.csv rows 4-5), and on a
+        # 2048^2 mesh Newton with the 'cp' search already fails at 0.08 (first step at that dt: 6 iterations at 512^2 and
+        # 1024^2, a stagnating linear solve at 2048^2, profiles/r2_logs/r2_21_bench2.log) -- the drivers' loop would halve dt there
+        cap = 0.04 if workload == "bench2" else 0.08
+        dts = [min(0.01 * 2 ** k, cap) for k in range(warmup + steps)]
 
     w = ctx.initial_condition()
     w0 = torch.empty_like(w)
