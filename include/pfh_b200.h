@@ -32,8 +32,9 @@ extern "C" {
 
 #define PFH_ABI_VERSION 2
 
-/* mesh kinds: df.RectangleMesh(..., 'crossed') (dolfin/bench1.py:23), df.BoxMesh (dolfin/b13d.py:26) */
-enum { PFH_MESH_CROSSED2D = 2, PFH_MESH_KUHN3D = 3 };
+/* mesh kinds: df.RectangleMesh(..., 'crossed') (dolfin/bench1.py:23), df.BoxMesh (dolfin/b13d.py:26),
+ * df.UnitSquareMesh(Nx, Ny) with DOLFIN's default right-diagonal split (dolfin/nl.py:20; grid vertices only, x fastest) */
+enum { PFH_MESH_RIGHT2D = 1, PFH_MESH_CROSSED2D = 2, PFH_MESH_KUHN3D = 3 };
 
 /* problems = the weak forms the drivers build from dolfin/pfbase.py:361-460 */
 enum {
@@ -41,6 +42,10 @@ enum {
   PFH_PROBLEM_BENCH2 = 2, /* bench2.py : (c, mu, eta1..4); params = {c_alpha, c_beta, rho^2, kappa_c, kappa_eta, M, w, alpha, L} */
   PFH_PROBLEM_BENCH3 = 3, /* bench3.py : (U, phi); params = {W0, tau0, D, lambda, Lx*Ly} */
   PFH_PROBLEM_BENCH6 = 6, /* bench6.py : (c, mu, phi); params = {c_alpha, c_beta, rho, kappa, M, k, epsilon} */
+  /* nl.py : one field u, STEADY (w0 and dt are ignored): F = int src v - int kc sqrt(u u) grad u . grad v - int reac u v
+   * (nl.py:37), u = g on x = 0 and x = Lx (nl.py:31-35); params = {src, kc, reac, g} = {5, 1, 1, 0.9}.  Only on
+   * PFH_MESH_RIGHT2D, and that mesh kind only carries this problem.  No energy functional (pfh_energy_* is an error). */
+  PFH_PROBLEM_NLDIFF = 7,
   /* A model generated from the driver's own weak form (pfhubbenchmarks_b200/codegen.py: sympy -> functor) and compiled
    * into its own copy of this library; only that copy accepts it.  No params: the coefficients are in the code. */
   PFH_PROBLEM_USER = 100

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpfh_b200.so")
-SOURCES = ["pfh_stencil.cu", "pfh_stencil3_tma.cu", "pfh_scalar3_tma.cu", "pfh_sample.cu", "pfh_vec.cu", "pfh_solver.cpp", "pfh_comm.cpp", "pfh_capi.cpp", "pfh_tables.cpp"]
+SOURCES = ["pfh_stencil.cu", "pfh_stencil3_tma.cu", "pfh_nl.cu", "pfh_scalar3_tma.cu", "pfh_sample.cu", "pfh_vec.cu", "pfh_solver.cpp", "pfh_comm.cpp", "pfh_capi.cpp", "pfh_tables.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -106,7 +106,10 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     c = new pfh_ctx;
     c->cfg = *cfg;
     c->cfg.nccl_unique_id = nullptr;
-    PFH_CHECK(cfg->mesh_kind == PFH_MESH_CROSSED2D || cfg->mesh_kind == PFH_MESH_KUHN3D, "unknown mesh kind");
+    PFH_CHECK(cfg->mesh_kind == PFH_MESH_CROSSED2D || cfg->mesh_kind == PFH_MESH_KUHN3D || cfg->mesh_kind == PFH_MESH_RIGHT2D,
+              "unknown mesh kind");
+    PFH_CHECK((cfg->mesh_kind == PFH_MESH_RIGHT2D) == (cfg->problem == PFH_PROBLEM_NLDIFF),
+              "the right-diagonal mesh carries PFH_PROBLEM_NLDIFF (dolfin/nl.py) and nothing else does");
     c->dim = cfg->mesh_kind == PFH_MESH_KUHN3D ? 3 : 2;
     for (int d = 0; d < c->dim; ++d) PFH_CHECK(cfg->ncell[d] >= 1 && cfg->length[d] > 0.0, "bad mesh size");
     memset(&c->prob, 0, sizeof c->prob);
@@ -117,6 +120,7 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
       case PFH_PROBLEM_BENCH2: c->nf = 6; need = 9; break;
       case PFH_PROBLEM_BENCH3: c->nf = 2; need = 5; break;
       case PFH_PROBLEM_BENCH6: c->nf = 3; need = 7; break;
+      case PFH_PROBLEM_NLDIFF: c->nf = 1; need = 4; break;
 #ifdef PFH_USER_PROBLEM_HEADER
       case PFH_PROBLEM_USER: c->nf = ProbUser::NF; need = 0; break;
 #endif
@@ -161,6 +165,15 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
       pfh_build_tables3(m, mT, kT);
       c->n_owned = m.n_owned; c->n_global = m.nxy * m.nzv;
       c->nplane = cfg->nranks > 1 ? m.nxy : 0;
+    } else if (cfg->mesh_kind == PFH_MESH_RIGHT2D) {
+      MeshR2& m = c->mr;
+      m.nx = cfg->ncell[0]; m.ny = cfg->ncell[1]; m.nxv = m.nx + 1; m.nyv = m.ny + 1;
+      m.n = (long long)m.nxv * m.nyv;
+      m.hx = cfg->length[0] / m.nx; m.hy = cfg->length[1] / m.ny;
+      c->nlp = NlParams{cfg->params[0], cfg->params[1], cfg->params[2], cfg->params[3]};
+      PFH_CHECK(c->nlp.kc > 0.0 && c->nlp.reac >= 0.0, "nl.py-type problem needs kc > 0 and reac >= 0");
+      memset(&c->m2, 0, sizeof c->m2);
+      c->n_owned = c->n_global = m.n;
     } else {
       Mesh2& m = c->m2;
       m.nx = cfg->ncell[0]; m.ny = cfg->ncell[1]; m.nxv = m.nx + 1; m.nyv = m.ny + 1;
@@ -279,6 +292,7 @@ double pfh_get_dt(const pfh_ctx* c) { return c ? c->dt : NAN; }
 int pfh_initial_condition_dev(pfh_ctx* c, const double* icp, int n, double* w) {
   PFH_API_BEGIN
   PFH_CHECK(c && icp && w, "null argument");
+  PFH_CHECK(!pfh_is_nl(c), "PFH_PROBLEM_NLDIFF has no initial-condition expression (nl.py:48 fills the vector with a constant)");
   PFH_CUDA(cudaSetDevice(c->cfg.device));
   k_initial_condition(c, icp, n, w);
   PFH_API_END
@@ -339,6 +353,7 @@ int pfh_newton_solve_dev(pfh_ctx* c, double* w, const double* w0, const pfh_solv
 int pfh_energy_dev(pfh_ctx* c, const double* w, double out[4]) {
   PFH_API_BEGIN
   PFH_CHECK(c && w && out, "null argument");
+  PFH_CHECK(!pfh_is_nl(c), "PFH_PROBLEM_NLDIFF has no energy functional");
   PFH_CUDA(cudaSetDevice(c->cfg.device));
   s_exchange_state(c, w, c->gU_lo, c->gU_hi);
   k_energy(c, w, out);
@@ -349,6 +364,7 @@ int pfh_bilinear_dev(pfh_ctx* c, const double* w, int fa, int fb, double am, dou
   PFH_API_BEGIN
   PFH_CHECK(c && w && out, "null argument");
   PFH_CHECK(fa >= 0 && fa < c->nf && fb >= 0 && fb < c->nf, "field index out of range");
+  PFH_CHECK(!pfh_is_nl(c), "no tabulated mass / stiffness operators on the right-diagonal mesh");
   PFH_CUDA(cudaSetDevice(c->cfg.device));
   const long long n = c->n_owned;
   const int bc = c->scalar_bc;
@@ -370,6 +386,7 @@ int pfh_eval_points_dev(pfh_ctx* c, const double* w, int field, const double* pt
   PFH_CHECK(c && w && (npts == 0 || (pts && out)), "null argument");
   PFH_CHECK(field >= 0 && field < c->nf && npts >= 0, "field index out of range");
   PFH_CHECK(npts < (1LL << 31), "too many points for one call");
+  PFH_CHECK(!pfh_is_nl(c), "point evaluation is not implemented on the right-diagonal mesh");
   PFH_CUDA(cudaSetDevice(c->cfg.device));
   k_eval_points(c, s_field_ref(c, w + (long long)field * c->n_owned), pts, npts, out);
   if (c->cfg.nranks > 1 && npts > 0) comm_allreduce_sum(c, out, (int)npts);
@@ -397,7 +414,9 @@ int pfh_step_host(pfh_ctx* c, double* w_host, const double* w0_host, double dt, 
   c->dt = dt;
   c->pc_ready = false;
   s_newton(c, c->U, c->U0, o, rep);
-  if (diag) {
+  if (diag && pfh_is_nl(c)) {
+    diag[0] = diag[1] = diag[2] = diag[3] = 0.0;   // no functional is assembled after nl.py's solves
+  } else if (diag) {
     s_exchange_state(c, c->U, c->gU_lo, c->gU_hi);
     k_energy(c, c->U, diag);
   }
@@ -439,6 +458,7 @@ int pfh_jac_apply_host(pfh_ctx* c, const double* w_host, const double* x_host, d
 int pfh_energy_host(pfh_ctx* c, const double* w_host, double out[4]) {
   PFH_API_BEGIN
   PFH_CHECK(c && w_host && out, "null argument");
+  PFH_CHECK(!pfh_is_nl(c), "PFH_PROBLEM_NLDIFF has no energy functional");
   PFH_CUDA(cudaSetDevice(c->cfg.device));
   stage(c);
   const size_t bytes = (size_t)c->nf * c->n_owned * sizeof(double);
@@ -493,6 +513,8 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->use_first2 = value != 0.0;
   } else if (k == "use_tma") {
     c->use_tma = value != 0.0;
+  } else if (k == "nl_tiled") {
+    c->nl_tiled = value != 0.0;
   } else {
     throw PfhError("unknown option: " + k);
   }

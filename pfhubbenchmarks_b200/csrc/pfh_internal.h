@@ -74,6 +74,18 @@ struct Mesh2 {
   const double* kT;    // [9][9]
 };
 
+// 2-D right-diagonal mesh = df.UnitSquareMesh(Nx, Ny) (dolfin/nl.py:20): grid vertices only, x fastest; every square is
+// cut by the diagonal v0-v3.  Used by the steady quasi-linear diffusion problem PFH_PROBLEM_NLDIFF (pfh_nl.cuh), whose
+// coefficients depend on the solution: no stencil tables.
+struct MeshR2 {
+  int nx, ny, nxv, nyv;
+  long long n;       // vertices = nxv * nyv
+  double hx, hy;
+};
+struct NlParams {
+  double src, kc, reac, bc;  // F = int src v - int kc |u| grad u . grad v - int reac u v, u = bc on x = 0 and x = Lx
+};
+
 void pfh_build_tables3(Mesh3& m, std::vector<double>& mT, std::vector<double>& kT);
 void pfh_build_tables2(Mesh2& m, std::vector<double>& mT, std::vector<double>& kT);
 
@@ -131,6 +143,8 @@ struct pfh_ctx {
   ProblemParams prob;
   Mesh2 m2;
   Mesh3 m3;
+  MeshR2 mr;     // cfg.mesh_kind == PFH_MESH_RIGHT2D
+  NlParams nlp;  // cfg.problem == PFH_PROBLEM_NLDIFF
   long long n_owned = 0, n_global = 0;
   long long nplane = 0;  // ghost plane size (3-D) or 0
   double dt = 0.1;
@@ -216,6 +230,7 @@ struct pfh_ctx {
   bool jac_quadrature_fp32 = false;
   bool use_first2 = true;  // 3-D: first two Chebyshev iterates in one pass over r (k_cheb_first2)
   int basis_precision = 0;  // Krylov basis storage: 0 = fp32 when krylov_rtol >= 1e-6 else fp64, 1 = fp64, 2 = fp32
+  bool nl_tiled = true;  // PFH_PROBLEM_NLDIFF: square-centric tiled kernels (false: the vertex-centric gather kernels)
   bool use_tma = true;  // 3-D fast path: staged kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu); false = gather kernels only
   bool use_tma_loader = true;  // stage with TMA when the operands allow it (false: always the cp.async loader; testing)
 };
@@ -268,6 +283,14 @@ void k_dirichlet_fix(pfh_ctx* c, double* w);  // impose Dirichlet values on the 
 void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst);
 // sig_i = max(d g_field / d u_field (u_i), floor_coef) * rowsum(M)_i  (2-D)
 void k_reaction_diag(pfh_ctx* c, const double* u, int field, double floor_coef, double* sig);  // dst = src on the Dirichlet vertices of a scalar field
+
+// ---- steady quasi-linear diffusion on the right-diagonal mesh (pfh_nl.cu; dolfin/nl.py) ----
+inline bool pfh_is_nl(const pfh_ctx* c) { return c->prob.id == PFH_PROBLEM_NLDIFF; }
+void k_nl_residual(pfh_ctx* c, const double* u, double* R);
+void k_nl_jac(pfh_ctx* c, const double* ulin, const double* x, double* y);
+// one Jacobi-Chebyshev sweep on A = K_{kc|ulin|} + reac M (the SPD part of -J) with right-hand side sgn*r:
+// zprev <- z + a (z - zprev) + b D^-1 (sgn r - A z) on the free vertices, zprev <- r on the Dirichlet vertices
+void k_nl_sweep(pfh_ctx* c, const double* ulin, double a, double b, double sgn, const double* r, const double* z, double* zprev);
 
 // ---- staged 3-D kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu) ----
 bool pfh_fast3_ok(const pfh_ctx* c);   // 3-D and the staged kernels are enabled

@@ -428,6 +428,7 @@ LinCoefs pfh_lin_coefs(const pfh_ctx* c, double dt) {
 }
 
 void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
+  if (pfh_is_nl(c)) return k_nl_residual(c, u, R);   // steady: no previous step
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
   int nprev = 0;
   for (int a = 0; a < c->nf; ++a) nprev += L.Mp[a] != 0.0;
@@ -444,6 +445,7 @@ void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
 }
 
 void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
+  if (pfh_is_nl(c)) return k_nl_jac(c, ulin, x, y);
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
   int nin = c->prob.id == PFH_PROBLEM_BENCH2 ? 5 : (c->prob.id == PFH_PROBLEM_BENCH3 ? 2 : 1);
 #ifdef PFH_USER_PROBLEM_HEADER
@@ -515,7 +517,11 @@ void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const do
   PFH_CUDA(cudaGetLastError());
 }
 
-void k_jacobi(pfh_ctx* c, const double* /*ulin*/, const double* r, double* z) {
+void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z) {
+  if (pfh_is_nl(c)) {  // z = -D^-1 r with D = diag(K_{kc|u|} + reac M): one sweep from z = 0
+    v_zero(c, c->S[0], c->n_owned);
+    return k_nl_sweep(c, ulin, 0.0, 1.0, -1.0, r, c->S[0], z);
+  }
   ProfScope ps(c, T_JACOBI, 16.0 * c->nf * c->n_owned);
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
   if (c->dim == 3)

@@ -10,7 +10,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "libpfh_emul.so")
 _SRC = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_tables.cpp")]
 _DEPS = _SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", f)
-                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh")]
+                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh", "pfh_nl.cuh")]
 
 
 def build(user_header=None):
@@ -62,6 +62,23 @@ def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=
     if mode in (5, 6, 7):
         return out
     return out
+
+
+def run_nl(ncell, length, params, mode, U, X=None, square=False):
+    """dolfin/nl.py's operators (csrc/pfh_nl.cuh) on the CPU: mode 0 residual F(U), 1 J(U) X, 2 (A X, diag A) with A the SPD
+    part of -J.  square=True: square-centric scatter (the tiled kernel's order of work).  Returns (values, diagonal)."""
+    lib = ctypes.CDLL(build())
+    nc = (ctypes.c_int * 3)(*(list(ncell) + [1]))
+    ln = (ctypes.c_double * 3)(*(list(length) + [1.0]))
+    pr = np.ascontiguousarray(params, dtype=np.float64)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    X = None if X is None else np.ascontiguousarray(X, dtype=np.float64)
+    n = (ncell[0] + 1) * (ncell[1] + 1)
+    out = np.zeros(2 * n)
+    lib.emul_nl.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _P, ctypes.c_int, ctypes.c_int, _P, _P, _P]
+    rc = lib.emul_nl(nc, ln, _p(pr), mode, int(square), _p(U), _p(X), _p(out))
+    assert rc == 0, rc
+    return out[:n], out[n:]
 
 
 def sample(mesh_kind, ncell, length, u, pts, z0=0, nzl=-1, glo=None, ghi=None):

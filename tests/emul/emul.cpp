@@ -7,6 +7,7 @@
 
 #include "../../pfhubbenchmarks_b200/csrc/pfh_vertex.cuh"
 #include "../../pfhubbenchmarks_b200/csrc/pfh_sample.cuh"
+#include "../../pfhubbenchmarks_b200/csrc/pfh_nl.cuh"
 
 void pfh_set_error(const std::string&) {}
 
@@ -14,6 +15,7 @@ namespace {
 struct Setup {
   Mesh2 m2;
   Mesh3 m3;
+  MeshR2 mr;
   std::vector<double> mT, kT;
   int dim;
 };
@@ -29,6 +31,13 @@ void setup(Setup& S, int mesh_kind, const int* nc, const double* len, int z0, in
     m.detJ = m.hx * m.hy * m.hz;
     pfh_build_tables3(m, S.mT, S.kT);
     m.mT = S.mT.data(); m.kT = S.kT.data();
+  } else if (mesh_kind == PFH_MESH_RIGHT2D) {
+    S.dim = 2;
+    memset(&S.m2, 0, sizeof S.m2);
+    MeshR2& m = S.mr;
+    m.nx = nc[0]; m.ny = nc[1]; m.nxv = nc[0] + 1; m.nyv = nc[1] + 1;
+    m.n = (long long)m.nxv * m.nyv;
+    m.hx = len[0] / nc[0]; m.hy = len[1] / nc[1];
   } else {
     S.dim = 2;
     Mesh2& m = S.m2;
@@ -180,6 +189,55 @@ extern "C" int emul_sample(int mesh_kind, const int* ncell, const double* length
     fprintf(stderr, "emul: %s\n", e.what());
     return -1;
   }
+}
+
+// dolfin/nl.py on the right-diagonal mesh (csrc/pfh_nl.cuh): mode 0 residual, 1 J(U) X, 2 A X and the diagonal of A
+// (out[0..n) values, out[n..2n) diagonal).  square != 0: square-centric scatter (the order of work of the tiled CUDA kernel)
+// instead of the vertex-centric gather.
+extern "C" int emul_nl(const int* ncell, const double* length, const double* params, int mode, int square, const double* U,
+                       const double* X, double* out) {
+  Setup S;
+  setup(S, PFH_MESH_RIGHT2D, ncell, length, 0, -1);
+  const MeshR2& m = S.mr;
+  const NlParams p{params[0], params[1], params[2], params[3]};
+  for (long long i = 0; i < 2 * m.n; ++i) out[i] = 0.0;
+  if (square) {
+    for (int oy = 0; oy < m.ny; ++oy)
+      for (int ox = 0; ox < m.nx; ++ox) {
+        const long long v0 = (long long)oy * m.nxv + ox, idx[4] = {v0, v0 + 1, v0 + m.nxv, v0 + m.nxv + 1};
+        double u[4], x[4] = {0, 0, 0, 0}, o[4] = {0, 0, 0, 0}, d[4] = {0, 0, 0, 0};
+        for (int l = 0; l < 4; ++l) {
+          u[l] = U[idx[l]];
+          if (mode != 0) x[l] = X[idx[l]];
+        }
+        if (mode == 0) nl::square_op<0>(m, p, u, x, o, d);
+        else if (mode == 1) nl::square_op<1>(m, p, u, x, o, d);
+        else nl::square_op<2>(m, p, u, x, o, d);
+        for (int l = 0; l < 4; ++l) {
+          out[idx[l]] += o[l];
+          out[m.n + idx[l]] += d[l];
+        }
+      }
+    for (int iy = 0; iy < m.nyv; ++iy)
+      for (int ix = 0; ix < m.nxv; ++ix)
+        if (nl::is_dirichlet(m, ix)) {
+          const long long i = (long long)iy * m.nxv + ix;
+          out[i] = mode == 0 ? U[i] - p.bc : X[i];
+          out[m.n + i] = 1.0;
+        }
+    return 0;
+  }
+  for (int iy = 0; iy < m.nyv; ++iy)
+    for (int ix = 0; ix < m.nxv; ++ix) {
+      const long long i = (long long)iy * m.nxv + ix;
+      double v, d;
+      if (mode == 0) nl::vertex_op<0>(m, p, U, X, ix, iy, v, d);
+      else if (mode == 1) nl::vertex_op<1>(m, p, U, X, ix, iy, v, d);
+      else nl::vertex_op<2>(m, p, U, X, ix, iy, v, d);
+      out[i] = v;
+      out[m.n + i] = d;
+    }
+  return 0;
 }
 
 extern "C" int emul_run(int mesh_kind, int problem, const int* ncell, const double* length, const double* params, int nparams,

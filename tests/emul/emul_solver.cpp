@@ -137,10 +137,45 @@ void k3_scalar_launch(pfh_ctx*, const ScalarOp&) { throw PfhError("emul: staged 
 bool k_cheb_first2(pfh_ctx*, double, double, double, double, double, FieldRef, double*, double*) { return false; }
 bool k_ch_crow(pfh_ctx*, const double*, FieldRef, double*) { return false; }
 
+// dolfin/nl.py: loops over nl::vertex_op (csrc/pfh_nl.cuh), the function k_nl_gather wraps on the device
+void k_nl_residual(pfh_ctx* c, const double* u, double* R) {
+  const MeshR2& m = c->mr;
+  for (int iy = 0; iy < m.nyv; ++iy)
+    for (int ix = 0; ix < m.nxv; ++ix) {
+      double d;
+      nl::vertex_op<0>(m, c->nlp, u, nullptr, ix, iy, R[(long long)iy * m.nxv + ix], d);
+    }
+}
+void k_nl_jac(pfh_ctx* c, const double* ulin, const double* x, double* y) {
+  const MeshR2& m = c->mr;
+  for (int iy = 0; iy < m.nyv; ++iy)
+    for (int ix = 0; ix < m.nxv; ++ix) {
+      double d;
+      nl::vertex_op<1>(m, c->nlp, ulin, x, ix, iy, y[(long long)iy * m.nxv + ix], d);
+    }
+}
+void k_nl_sweep(pfh_ctx* c, const double* ulin, double a, double b, double sgn, const double* r, const double* z, double* zprev) {
+  const MeshR2& m = c->mr;
+  for (int iy = 0; iy < m.nyv; ++iy)
+    for (int ix = 0; ix < m.nxv; ++ix) {
+      const long long i = (long long)iy * m.nxv + ix;
+      if (nl::is_dirichlet(m, ix)) {
+        zprev[i] = r[i];
+        continue;
+      }
+      double Az, d;
+      nl::vertex_op<2>(m, c->nlp, ulin, z, ix, iy, Az, d);
+      const double zp = a != 0.0 ? zprev[i] : z[i];
+      zprev[i] = z[i] + a * (z[i] - zp) + (b / d) * (sgn * r[i] - Az);
+    }
+}
+
 void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
+  if (pfh_is_nl(c)) return k_nl_residual(c, u, R);
   EMUL_DISPATCH(c, (run<P>(setup_of(c), c->prob, c->dt, 0, u, nullptr, u0, nullptr, nullptr, R, nullptr)));
 }
 void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
+  if (pfh_is_nl(c)) return k_nl_jac(c, ulin, x, y);
   EMUL_DISPATCH(c, (run<P>(setup_of(c), c->prob, c->dt, 1, ulin, x, nullptr, nullptr, nullptr, y, nullptr)));
 }
 void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const double* add, double* out) {
@@ -152,7 +187,11 @@ void k_cheb_first(pfh_ctx* c, double am, double ak, double b, const double* r, d
 void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const double* r, FieldRef z, double* zprev, bool zprev_is_zero, double) {
   scalar_all<2>(c, am, ak, a, b, z, r, zprev, zprev_is_zero);
 }
-void k_jacobi(pfh_ctx* c, const double*, const double* r, double* z) {
+void k_jacobi(pfh_ctx* c, const double* ulin, const double* r, double* z) {
+  if (pfh_is_nl(c)) {
+    memset(c->S[0], 0, c->n_owned * sizeof(double));
+    return k_nl_sweep(c, ulin, 0.0, 1.0, -1.0, r, c->S[0], z);
+  }
   const LinCoefs L = pfh_lin_coefs(c, c->dt);
   const long long n = c->n_owned;
   for (long long i = 0; i < n; ++i)
@@ -285,15 +324,17 @@ extern "C" int emul_newton_step(int mesh_kind, int problem, const int* ncell, co
     c.dim = S.dim;
     c.m2 = S.m2;
     c.m3 = S.m3;
+    c.mr = S.mr;
+    if (problem == PFH_PROBLEM_NLDIFF) c.nlp = NlParams{params[0], params[1], params[2], params[3]};
     memset(&c.prob, 0, sizeof c.prob);
     c.prob.id = problem;
     for (int i = 0; i < nparams; ++i) c.prob.p[i] = params[i];
-    c.nf = problem == PFH_PROBLEM_BENCH2 ? 6 : (problem == PFH_PROBLEM_BENCH6 ? 3 : 2);
+    c.nf = problem == PFH_PROBLEM_BENCH2 ? 6 : (problem == PFH_PROBLEM_BENCH6 ? 3 : (problem == PFH_PROBLEM_NLDIFF ? 1 : 2));
 #ifdef PFH_USER_PROBLEM_HEADER
     if (problem == PFH_PROBLEM_USER) c.nf = ProbUser::NF;
 #endif
     c.prob.nf = c.nf;
-    c.n_owned = c.n_global = S.dim == 3 ? S.m3.n_owned : S.m2.n_owned;
+    c.n_owned = c.n_global = S.dim == 3 ? S.m3.n_owned : (mesh_kind == PFH_MESH_RIGHT2D ? S.mr.n : S.m2.n_owned);
     c.dt = dt;
     c.basis_precision = basis_precision;
     g_setup[&c] = &S;
