@@ -9,8 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpfh_b200.so")
 
-MESH_CROSSED2D, MESH_KUHN3D = 2, 3
-PROBLEM_CH, PROBLEM_BENCH2, PROBLEM_BENCH3, PROBLEM_BENCH6, PROBLEM_USER = 1, 2, 3, 6, 100
+MESH_RIGHT2D, MESH_CROSSED2D, MESH_KUHN3D = 1, 2, 3
+PROBLEM_CH, PROBLEM_BENCH2, PROBLEM_BENCH3, PROBLEM_BENCH6, PROBLEM_NLDIFF, PROBLEM_USER = 1, 2, 3, 6, 7, 100
 MAX_PARAMS, NCCL_ID_BYTES, N_TIMERS = 16, 128, 16
 
 

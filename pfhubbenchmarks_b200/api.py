@@ -62,6 +62,16 @@ def RectangleMesh(p0, p1, nx, ny, diagonal="crossed"):
     return Mesh("crossed2d", (nx, ny), p1.x[:2])
 
 
+def UnitSquareMesh(nx, ny, diagonal="right"):
+    """df.UnitSquareMesh(Nx, Ny[, 'crossed'])  (nl.py:19-20): DOLFIN's default split cuts every square by the diagonal
+    from its lower-left to its upper-right vertex ('right')."""
+    if diagonal == "crossed":
+        return Mesh("crossed2d", (nx, ny), (1.0, 1.0))
+    if diagonal != "right":
+        raise NotImplementedError("UnitSquareMesh diagonal %r (the reference uses the default 'right' and 'crossed')" % (diagonal,))
+    return Mesh("right2d", (nx, ny), (1.0, 1.0))
+
+
 def BoxMesh(p0, p1, nx, ny, nz):
     """df.BoxMesh(Point, Point, Nx, Ny, Nz)  (b13d.py:24-26)."""
     if any(abs(v) > 0 for v in p0.x):
@@ -245,7 +255,8 @@ class NonlinearVariationalSolver:
         self.last_report = None
 
     def _opts(self):
-        p = self.parameters["snes_solver"]
+        # nl.py:66-96 configures and runs both trees; here they are one object (DOLFIN's defaults for them coincide)
+        p = self.parameters["newton_solver" if self.parameters["nonlinear_solver"] == "newton" else "snes_solver"]
         k = p["krylov_solver"]
         ls = p["line_search"]
         if ls not in _LINE_SEARCH:
@@ -270,7 +281,8 @@ class NonlinearVariationalSolver:
         """niters, converged = solver.solve()  (bench1.py:162). In place on problem.w; never raises on non-convergence
         unless error_on_nonconvergence is set (the drivers clear it, bench1.py:86)."""
         pr = self.problem
-        pr.ctx.dt = float(pr.dt)
+        if pr.dt is not None:                      # steady problems (nl.py) have no time step
+            pr.ctx.dt = float(pr.dt)
         rep = pr.ctx.newton_solve(pr.w.tensor, pr.w0.tensor, opts=self._opts())
         self.last_report = rep
         if not rep["converged"] and self.parameters["snes_solver"]["error_on_nonconvergence"]:

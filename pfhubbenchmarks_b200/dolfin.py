@@ -18,7 +18,7 @@ import sympy as sy
 
 from . import engine, forms
 from .api import (DOLFIN_EPS, MPI, BoxMesh, Mesh, NonlinearVariationalSolver as _Solver, Point,  # noqa: F401
-                  RectangleMesh, _IC)
+                  RectangleMesh, UnitSquareMesh, _IC)
 from .forms import diff, dx, grad, inner, variable  # noqa: F401
 from .io import File  # noqa: F401
 
@@ -118,6 +118,7 @@ class FunctionSpace:
         if constrained_domain is not None:
             raise NotImplementedError("periodic constrained_domain (commented out in every reference driver)")
         self.mesh, self.index = mesh, _index
+        self.mixed = isinstance(family, list)          # a MixedElement space is indexed (w_[0]) even with one component
         if isinstance(family, list):
             self.nfields = len(family)
         else:
@@ -155,20 +156,34 @@ class Expression:
 
 
 class DirichletBC:
-    """df.DirichletBC(Wphi, value, boundary_fn)  (bench6.py:87-88).  The boundary is identified by probing
-    `boundary_fn(x, on_boundary)` at the four edge midpoints of the rectangle."""
+    """df.DirichletBC(Wphi, value, boundary_fn)  (bench6.py:87-88; nl.py:35).  The boundary is identified by probing
+    `boundary_fn` at the four edge midpoints of the rectangle: `boundary_fn(x, on_boundary)` as DOLFIN calls it, or a
+    one-argument locator over an array of points (nl.py:34 writes `lambda x: np.logical_or(np.isclose(x[0], 0.0), ...)`).
+    bench6 gives one edge per condition, nl.py the pair x = 0 and x = 1 in one."""
 
     def __init__(self, space, value, where):
-        if space.index is None:
+        if space.index is None and space.nfields != 1:
             raise NotImplementedError("DirichletBC on the whole mixed space")
-        self.field = space.index
+        self.field = space.index or 0
+        if isinstance(value, Function):                # u_bc = Function(V); u_bc.interpolate(Constant(0.9))  (nl.py:31-32)
+            if not isinstance(value._pending, Constant):
+                raise NotImplementedError("Dirichlet data from a Function other than an interpolated Constant")
+            value = value._pending
         self.value_expr = value.expr if isinstance(value, Expression) else sy.Float(float(value)) if float(value) != 0 else sy.Integer(0)
         lx, ly = space.mesh.length[:2]
         probes = {"left": (0.0, 0.5 * ly), "right": (lx, 0.5 * ly), "bottom": (0.5 * lx, 0.0), "top": (0.5 * lx, ly)}
-        hit = [k for k, p in probes.items() if where(np.array(p), True)]
-        if where(np.array((0.5 * lx, 0.5 * ly)), False) or len(hit) != 1:
-            raise NotImplementedError("Dirichlet boundary must be exactly one edge of the rectangle")
-        self.side = hit[0]
+
+        def inside(p, on_boundary):
+            try:
+                return bool(where(np.array(p), on_boundary))
+            except TypeError:                          # one-argument locator
+                return bool(where(np.array(p)))
+
+        hit = [k for k, p in probes.items() if inside(p, True)]
+        if inside((0.5 * lx, 0.5 * ly), False) or not hit:
+            raise NotImplementedError("Dirichlet boundary must consist of edges of the rectangle")
+        self.sides = tuple(hit)
+        self.side = hit[0] if len(hit) == 1 else "+".join(hit)
 
 
 class _FunctionIndex:
@@ -184,6 +199,8 @@ class _FunctionIndex:
 
 
 def TestFunction(W):
+    if not W.mixed:                                    # v = TestFunction(V) on a scalar space is used as is (nl.py:28,37)
+        return forms.Test(0)
     return _FunctionIndex(W, True)
 
 
@@ -191,9 +208,16 @@ def TrialFunction(W):
     return _FunctionIndex(W, False)
 
 
-class Function:
+class Function(_SymArith):
     """df.Function(W): symbols in forms; an fp64 device vector [field0 | field1 | ...] once a problem owns it.
-    interpolate()/assign() before the problem exists are replayed when the storage is created."""
+    interpolate()/assign() before the problem exists are replayed when the storage is created.  On a scalar space the
+    Function itself stands for its one symbol in expressions (`sqrt(u * u)`, `inner(u, v)`, nl.py:37)."""
+
+    @property
+    def sym(self):
+        if self.W.nfields != 1:
+            raise AttributeError("a Function on a mixed space enters forms through split(w) or w[i]")
+        return self.symbols[0]
 
     def __init__(self, W):
         self.W = W
@@ -222,7 +246,9 @@ class Function:
             self._pending = ic
             return
         ctx = self._problem.ctx
-        if isinstance(ic, _IC) and ctx.problem in ic.kernel_problems:
+        if isinstance(ic, Constant):                   # u.interpolate(Constant(0.9))
+            self._tensor.fill_(float(ic))
+        elif isinstance(ic, _IC) and ctx.problem in ic.kernel_problems:
             ctx.initial_condition(ic.args, out=self._tensor)      # the problem's own expression: evaluated by its kernel
         elif isinstance(ic, _IC):
             # another benchmark's expression, or a generated model (whose kernel has no initial condition): the closed
@@ -327,6 +353,9 @@ class NonlinearVariationalProblem:
         launch); the shipped systems have theirs built in."""
         problem, name, params, dt, prev, self.model = self._analyse(F, w, bcs, J, functionals)
         mesh = w.W.mesh
+        if (name == "nl") != (mesh.kind == "right2d"):
+            raise NotImplementedError("the right-diagonal UnitSquareMesh carries the steady problem of nl.py and nothing else does"
+                                      " (the benchmark drivers use RectangleMesh(..., 'crossed') / BoxMesh)")
         if name == "bench1" and mesh.kind == "kuhn3d":
             name = problem = "b13d"
         self.benchmark, self.mesh, self.dt, self.params = name, mesh, dt, params
@@ -334,9 +363,10 @@ class NonlinearVariationalProblem:
                         for s in e.free_symbols if isinstance(s, forms.ConstSymbol) and s.const is not dt]
         self.ctx = engine.Context(problem, mesh.ncell, mesh.length, params=params, device=device, rank=rank, nranks=nranks,
                                   nccl_id=nccl_id, krylov_basis=krylov_basis)
-        self.w, self.w0 = w, prev
+        self.w, self.w0 = w, (prev if prev is not None else w)     # steady: the library ignores w0
         w._bind(self)
-        prev._bind(self)
+        if prev is not None:
+            prev._bind(self)
         self._functionals = {}
 
 
@@ -353,8 +383,9 @@ def _analyse(F, w, bcs, J, functionals):
             for s in sy.sympify(t[2]).free_symbols:
                 if isinstance(s, forms.FieldSymbol) and s.owner is not w:
                     prev = s.owner
-    if prev is None:
-        raise NotImplementedError("no previous-step Function in the form")
+    if prev is None:                                   # no time derivative: the steady problem of nl.py, or nothing we know
+        name, params = forms.compile_steady(F, w.W.nfields, w.symbols, bcs or ())
+        return name, name, params, None, None, None
     try:
         name, params, dt = forms.compile_form(F, w.W.nfields, w.symbols, prev.symbols, bcs or ())
         return name, name, params, dt, prev, None

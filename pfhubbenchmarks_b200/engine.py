@@ -22,6 +22,9 @@ PROBLEMS = {
     "bench6": (_lib.PROBLEM_BENCH6, 3, [0.3, 0.7, 5.0, 2.0, 5.0, 0.09, 90.0], [0.5, 0.04], ("c", "mu", "phi")),
 }
 PROBLEMS["b13d"] = PROBLEMS["bench1"]
+# nl.py:37,31-35: src, kc, reac of F = int src v - int kc |u| grad u . grad v - int reac u v, Dirichlet value on x = 0, Lx.
+# Steady, on the right-diagonal mesh (nl.py:20); no initial-condition expression (nl.py:48 fills the vector with 0.9).
+PROBLEMS["nl"] = (_lib.PROBLEM_NLDIFF, 1, [5.0, 1.0, 1.0, 0.9], [0.0], ("u",))
 
 
 def slab_range(nplanes, rank, nranks):
@@ -59,7 +62,8 @@ class Context:
         if pid == _lib.PROBLEM_BENCH3 and params[4] is None:
             params[4] = float(length[0] * length[1])
         cfg = _lib.Config()
-        cfg.mesh_kind = _lib.MESH_KUHN3D if dim == 3 else _lib.MESH_CROSSED2D
+        cfg.mesh_kind = _lib.MESH_KUHN3D if dim == 3 else (_lib.MESH_RIGHT2D if pid == _lib.PROBLEM_NLDIFF else _lib.MESH_CROSSED2D)
+        self.mesh_kind = cfg.mesh_kind
         cfg.problem = pid
         for d in range(3):
             cfg.ncell[d] = int(ncell[d]) if d < dim else 1
@@ -117,6 +121,8 @@ class Context:
         if self.dim == 2:
             (nx, ny), (lx, ly) = self.ncell, self.length
             x, y = np.meshgrid(np.linspace(0.0, lx, nx + 1), np.linspace(0.0, ly, ny + 1))
+            if getattr(self, "mesh_kind", _lib.MESH_CROSSED2D) == _lib.MESH_RIGHT2D:     # grid vertices only (UnitSquareMesh, nl.py:20)
+                return np.stack([x.ravel(), y.ravel()], 1)
             xc, yc = np.meshgrid((np.arange(nx) + 0.5) * (lx / nx), (np.arange(ny) + 0.5) * (ly / ny))
             return np.concatenate([np.stack([x.ravel(), y.ravel()], 1), np.stack([xc.ravel(), yc.ravel()], 1)])
         (nx, ny, nz), (lx, ly, lz) = self.ncell, self.length

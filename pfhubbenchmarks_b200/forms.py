@@ -231,7 +231,9 @@ def grad(u):
 def inner(a, b):
     if isinstance(a, Grad) and isinstance(b, Grad):
         return GradPair(a.of, b.of, a.coef * b.coef)
-    raise NotImplementedError("inner() of anything but two gradients")
+    if isinstance(a, Grad) or isinstance(b, Grad):
+        raise NotImplementedError("inner() of a gradient and a scalar")
+    return a * b          # inner(u, v) of two scalars (nl.py:37)
 
 
 def variable(x):
@@ -331,6 +333,46 @@ def compile_form(F, nfields, fields, prev, bcs=()):
             return out[0], [_snap(v) for v in out[1]], dt.const
     raise NotImplementedError(
         "this weak form is not one of the compiled operator families (bench1/b13d, bench2, bench3, bench6)")
+
+
+def compile_steady(F, nfields, fields, bcs=()):
+    """A residual form without a time derivative.  The one steady system the reference holds is dolfin/nl.py:37,
+        F = int src v - int kc sqrt(u u) grad u . grad v - int reac u v,   u = g on x = 0 and x = Lx (nl.py:31-35);
+    returns ("nl", [src, kc, reac, g]) for it (PFH_PROBLEM_NLDIFF on the right-diagonal mesh), NotImplementedError for
+    anything else."""
+    no = NotImplementedError("steady form that is not dolfin/nl.py's  src*v - kc*sqrt(u*u)*inner(grad(u), grad(v)) - reac*u*v")
+    if nfields != 1:
+        raise no
+    u = fields[0]
+    src, stiff = sy.Integer(0), sy.Integer(0)
+    for t in F.terms:
+        if t[0] == "src" and t[1] == 0:
+            src += t[2]
+        elif t[0] == "stiff" and t[1] == 0 and t[2] is u:
+            stiff += t[3]
+        else:
+            raise no
+
+    def values(e):
+        e = sy.sympify(e)
+        return e.subs({s: s.const.value for s in e.free_symbols if isinstance(s, ConstSymbol)})
+
+    src, stiff = sy.expand(values(src)), values(stiff)
+    try:
+        p = sy.Poly(src, u)
+    except sy.PolynomialError:
+        raise no
+    if p.degree() > 1 or (src.free_symbols - {u}):
+        raise no
+    reac, s0 = -_num(p.coeff_monomial(u)), _num(p.coeff_monomial(1))
+    kc = sy.simplify(-stiff / sy.Abs(u))
+    if kc.free_symbols or _num(kc) <= 0.0 or reac < 0.0:
+        raise no
+    sides = sorted(s for bc in bcs for s in bc.sides)
+    vals = {float(bc.value_expr) for bc in bcs if not sy.sympify(bc.value_expr).free_symbols}
+    if sides != ["left", "right"] or len(vals) != 1 or any(bc.field != 0 for bc in bcs):
+        raise NotImplementedError("nl.py-type problem needs one constant Dirichlet value on x = 0 and x = Lx (nl.py:31-35)")
+    return "nl", [_snap(s0), _snap(_num(kc)), _snap(reac), _snap(vals.pop())]
 
 
 def _time_row(L, a):

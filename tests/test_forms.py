@@ -109,8 +109,10 @@ def test_dirichlet_boundaries():
     right = df.DirichletBC(sub, df.Expression("sin(x[1]/7)", degree=2), lambda x, on: on and df.near(x[0], 10.0, 1e-12))
     assert (left.side, left.field, left.value_expr) == ("left", 2, 0)
     assert right.side == "right" and str(right.value_expr) == "sin(x1/7)"
+    whole = df.DirichletBC(sub, df.Constant(0.0), lambda x, on: on)     # several edges in one condition (nl.py:34 has two):
+    assert set(whole.sides) == {"left", "right", "bottom", "top"}       # accepted here, refused by the form matchers
     with pytest.raises(NotImplementedError):
-        df.DirichletBC(sub, df.Constant(0.0), lambda x, on: on)          # the whole boundary
+        df.DirichletBC(sub, df.Constant(0.0), lambda x, on: True)        # interior points too
     with pytest.raises(NotImplementedError):
         df.DirichletBC(W, df.Constant(0.0), lambda x, on: on and df.near(x[0], 0.0))
 
