@@ -3,11 +3,12 @@
 // coefficient kc |u| changes with every Newton iterate, nothing could be tabulated).
 //
 // Two mappings of the same arithmetic:
-//  * k_nl_tiled (default): SQUARE-centric, the 2-D form of the cube-centric J.v of pfh_stencil3_tma.cu.  A CTA owns a
-//    32 x 8 tile of vertices, stages the 34 x 10 operand values it touches in shared memory, evaluates each of the 33 x 9
-//    squares around the tile ONCE (two triangles, six quadrature points each) and leaves the four corner contributions
-//    in shared memory; after one barrier every vertex adds up the entries of its four squares.  2.3 triangle
-//    evaluations per vertex instead of the 6 of a vertex-centric gather; operand traffic = one read per array + halo.
+//  * k_nl_tiled (default): SQUARE-centric, the 2-D form of the cube-centric J.v of pfh_stencil3_tma.cu.  A CTA of 32 x 8
+//    threads owns a 31 x 7 tile of vertices: it stages the 33 x 9 operand values around the tile in shared memory, every
+//    thread evaluates ONE of the 32 x 8 squares that touch the tile (two triangles, six quadrature points each; one
+//    pass, no idle second pass) and leaves its four corner contributions in shared memory; after one barrier
+//    every vertex adds up the entries of its four squares.  2.4 triangle evaluations per vertex instead of the 6 of a
+//    vertex-centric gather; operand traffic = one read per array + halo.
 //  * k_nl_gather: thread -> vertex around nl::vertex_op, the mapping tests/emul runs on the CPU (pfh_set_option
 //    "nl_tiled" 0); the tiled kernel is tested against it.
 // Algorithmic bytes per vertex: residual 16 (u, F), J.v 24 (u, x, y), sweep 40 (u, z, zprev, r, out).
@@ -15,7 +16,9 @@
 
 namespace {
 
-constexpr int NTX = 32, NTY = 8, NSX = NTX + 1, NSY = NTY + 1, NVX = NTX + 2, NVY = NTY + 2;
+constexpr int NTX = 32, NTY = 8;                                  // gather kernel: vertices per CTA
+constexpr int NSX = 32, NSY = 8;                                  // tiled kernel: squares per CTA = threads per CTA
+constexpr int NWX = NSX - 1, NWY = NSY - 1, NVX = NSX + 1, NVY = NSY + 1;   // vertices owned / staged per CTA
 
 struct SweepArgs {
   double a, b, sgn;
@@ -45,15 +48,15 @@ __global__ void __launch_bounds__(NTX* NTY) k_nl_gather(MeshR2 m, NlParams p, co
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NTX* NTY) k_nl_tiled(MeshR2 m, NlParams p, const double* __restrict__ U,
+__global__ void __launch_bounds__(NSX* NSY) k_nl_tiled(MeshR2 m, NlParams p, const double* __restrict__ U,
                                                        const double* __restrict__ X, SweepArgs s, double* out) {
   __shared__ double us[NVY][NVX];
   __shared__ double xs[MODE == 0 ? 1 : NVY][MODE == 0 ? 1 : NVX];
   __shared__ double cv[4][NSY][NSX];
   __shared__ double cd[MODE == 2 ? 4 : 1][MODE == 2 ? NSY : 1][MODE == 2 ? NSX : 1];
-  const int tid = threadIdx.y * NTX + threadIdx.x;
-  const int x0 = blockIdx.x * NTX - 1, y0 = blockIdx.y * NTY - 1;  // vertex (and square) origin of the staged window
-  for (int k = tid; k < NVX * NVY; k += NTX * NTY) {
+  const int tid = threadIdx.y * NSX + threadIdx.x;
+  const int x0 = blockIdx.x * NWX - 1, y0 = blockIdx.y * NWY - 1;  // vertex (and square) origin of the staged window
+  for (int k = tid; k < NVX * NVY; k += NSX * NSY) {
     const int lx = k % NVX, ly = k / NVX, gx = x0 + lx, gy = y0 + ly;
     const bool in = gx >= 0 && gx < m.nxv && gy >= 0 && gy < m.nyv;
     const long long g = (long long)gy * m.nxv + gx;
@@ -61,8 +64,8 @@ __global__ void __launch_bounds__(NTX* NTY) k_nl_tiled(MeshR2 m, NlParams p, con
     if (MODE != 0) xs[ly][lx] = in ? X[g] : 0.0;
   }
   __syncthreads();
-  for (int k = tid; k < NSX * NSY; k += NTX * NTY) {
-    const int sx = k % NSX, sy = k / NSX, ox = x0 + sx, oy = y0 + sy;
+  {
+    const int sx = threadIdx.x, sy = threadIdx.y, ox = x0 + sx, oy = y0 + sy;
     double o[4] = {0.0, 0.0, 0.0, 0.0}, d[4] = {0.0, 0.0, 0.0, 0.0};
     if (ox >= 0 && ox <= m.nx - 1 && oy >= 0 && oy <= m.ny - 1) {
       const double u[4] = {us[sy][sx], us[sy][sx + 1], us[sy + 1][sx], us[sy + 1][sx + 1]};
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(NTX* NTY) k_nl_tiled(MeshR2 m, NlParams p, con
   }
   __syncthreads();
   const int lx = threadIdx.x, ly = threadIdx.y, ix = x0 + 1 + lx, iy = y0 + 1 + ly;
-  if (ix >= m.nxv || iy >= m.nyv) return;
+  if (lx >= NWX || ly >= NWY || ix >= m.nxv || iy >= m.nyv) return;
   const long long i = (long long)iy * m.nxv + ix;
   double val, diag = 1.0;
   if (nl::is_dirichlet(m, ix)) {
@@ -97,11 +100,10 @@ __global__ void __launch_bounds__(NTX* NTY) k_nl_tiled(MeshR2 m, NlParams p, con
 template <int MODE>
 void launch(pfh_ctx* c, const double* U, const double* X, const SweepArgs& s, double* out) {
   const MeshR2& m = c->mr;
-  const dim3 grid((m.nxv + NTX - 1) / NTX, (m.nyv + NTY - 1) / NTY), block(NTX, NTY);
   if (c->nl_tiled)
-    k_nl_tiled<MODE><<<grid, block, 0, c->stream>>>(m, c->nlp, U, X, s, out);
+    k_nl_tiled<MODE><<<dim3((m.nxv + NWX - 1) / NWX, (m.nyv + NWY - 1) / NWY), dim3(NSX, NSY), 0, c->stream>>>(m, c->nlp, U, X, s, out);
   else
-    k_nl_gather<MODE><<<grid, block, 0, c->stream>>>(m, c->nlp, U, X, s, out);
+    k_nl_gather<MODE><<<dim3((m.nxv + NTX - 1) / NTX, (m.nyv + NTY - 1) / NTY), dim3(NTX, NTY), 0, c->stream>>>(m, c->nlp, U, X, s, out);
   PFH_CUDA(cudaGetLastError());
 }
 

@@ -7,7 +7,8 @@
 //   bc     u = g on the vertices of x = 0 and x = Lx (nl.py:31-35): rows F_i = u_i - g, (J x)_i = x_i
 //
 // Quadrature degree 3 (nl.py:12) = the 6-point Strang-Fix rule on every triangle; grad u is constant per triangle, so the
-// diffusion term of a triangle is (grad u . grad phi_i) * sum_q w_q kc |u_q|.  Nothing is assembled: one call computes the
+// diffusion term of a triangle is (grad u . grad phi_i) * sum_q w_q kc |u_q|; only a triangle on which u_h changes sign needs
+// the six points for it, and the polynomial terms have closed forms (tri_op).  Nothing is assembled: one call computes the
 // row of one vertex from the (up to) six triangles around it.  The functions are __host__ __device__: the CUDA kernels of
 // pfh_nl.cu are thread -> vertex mappings around them, and tests/emul compiles them for the CPU against the oracle
 // (oracle/nl.py).
@@ -30,23 +31,25 @@ namespace nl {
 template <int MODE>
 PFH_HD void tri_op(const NlParams& p, double w, const double (&u)[3], const double (&x)[3], const double (&g)[3][2],
                    double (&out)[3], double (&dg)[3]) {
-  double kbar = 0.0, sbar = 0.0, acc[3] = {0.0, 0.0, 0.0};
+  // sum_q |u_q| and sum_q sign(u_q) x_q over the six points.  The barycentric coordinates of the points are the six
+  // permutations of (A, B, C), A + B + C = 1, so sum_q u_q = 2 (u0 + u1 + u2): where u_h keeps one sign on the triangle
+  // (everywhere in nl.py's solution, which stays above its boundary value 0.9) the two sums need no quadrature loop.
+  const double Su = u[0] + u[1] + u[2];
+  const double Sx = MODE != 0 ? x[0] + x[1] + x[2] : 0.0;
+  double kbar = 0.0, sbar = 0.0;
+  const bool pos = u[0] > 0.0 && u[1] > 0.0 && u[2] > 0.0, neg = u[0] < 0.0 && u[1] < 0.0 && u[2] < 0.0;
+  if (pos || neg) {
+    const double sg = pos ? 2.0 : -2.0;
+    kbar = sg * Su;
+    if (MODE == 1) sbar = sg * Sx;
+  } else {
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const double l0 = elem::sf(q, 0), l1 = elem::sf(q, 1), l2 = elem::sf(q, 2);
-    const double uq = l0 * u[0] + l1 * u[1] + l2 * u[2];
-    kbar += fabs(uq);
-    double pt;
-    if (MODE == 0) {
-      pt = p.src - p.reac * uq;
-    } else {
-      const double xq = l0 * x[0] + l1 * x[1] + l2 * x[2];
-      pt = MODE == 1 ? -p.reac * xq : p.reac * xq;
-      if (MODE == 1) sbar += (uq > 0.0 ? 1.0 : (uq < 0.0 ? -1.0 : 0.0)) * xq;
+    for (int q = 0; q < 6; ++q) {
+      const double l0 = elem::sf(q, 0), l1 = elem::sf(q, 1), l2 = elem::sf(q, 2);
+      const double uq = l0 * u[0] + l1 * u[1] + l2 * u[2];
+      kbar += fabs(uq);
+      if (MODE == 1) sbar += (uq > 0.0 ? 1.0 : (uq < 0.0 ? -1.0 : 0.0)) * (l0 * x[0] + l1 * x[1] + l2 * x[2]);
     }
-    acc[0] += l0 * pt;
-    acc[1] += l1 * pt;
-    acc[2] += l2 * pt;
   }
   kbar *= w * p.kc;
   sbar *= w * p.kc;
@@ -56,15 +59,17 @@ PFH_HD void tri_op(const NlParams& p, double w, const double (&u)[3], const doub
     gx[0] = x[0] * g[0][0] + x[1] * g[1][0] + x[2] * g[2][0];
     gx[1] = x[0] * g[0][1] + x[1] * g[1][1] + x[2] * g[2][1];
   }
+  // the source / reaction terms are polynomials of degree <= 2, which the rule integrates exactly: closed forms
+  // int phi_l = |T|/3 = 2w, int v phi_l = |T|/12 (v0 + v1 + v2 + v_l) = (w/2)(S + v_l), int phi_l^2 = |T|/6 = w
+  const double hm = 0.5 * w * p.reac;
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
     const double gul = gu[0] * g[l][0] + gu[1] * g[l][1];
     const double gxl = gx[0] * g[l][0] + gx[1] * g[l][1];
-    if (MODE == 0) out[l] += w * acc[l] - kbar * gul;
-    if (MODE == 1) out[l] += w * acc[l] - sbar * gul - kbar * gxl;
+    if (MODE == 0) out[l] += (2.0 * w * p.src - hm * (Su + u[l])) - kbar * gul;
+    if (MODE == 1) out[l] += -hm * (Sx + x[l]) - sbar * gul - kbar * gxl;
     if (MODE == 2) {
-      out[l] += w * acc[l] + kbar * gxl;
-      // int phi_l^2 = |T| / 6 = w (the 6-point rule integrates it exactly)
+      out[l] += hm * (Sx + x[l]) + kbar * gxl;
       dg[l] += p.reac * w + kbar * (g[l][0] * g[l][0] + g[l][1] * g[l][1]);
     }
   }

@@ -94,6 +94,14 @@ def test_other_parameters():
     u = 1.2 + 0.3 * rng.random(P.nv)
     R, _ = emul.run_nl((6, 4), (2.0, 1.0), [3.0, 0.5, 2.0, 1.2], 0, u)
     assert np.abs(R - P.residual(u)).max() <= 1e-14
+    # one-signed triangles take the closed forms of tri_op (no quadrature loop): all positive above, all negative here
+    x = rng.standard_normal(P.nv)
+    for sq in (False, True):
+        Jx, _ = emul.run_nl((6, 4), (2.0, 1.0), [3.0, 0.5, 2.0, 1.2], 1, -u, x, square=sq)
+        Ax, d = emul.run_nl((6, 4), (2.0, 1.0), [3.0, 0.5, 2.0, 1.2], 2, -u, x, square=sq)
+        assert np.abs(Jx - P.jacobian(-u) @ x).max() <= 1e-13 * np.abs(Jx).max()
+        A = P.sym_operator(-u)
+        assert np.abs(Ax - A @ x).max() <= 1e-13 * np.abs(Ax).max() and np.abs(d - A.diagonal()).max() <= 1e-13 * d.max()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
