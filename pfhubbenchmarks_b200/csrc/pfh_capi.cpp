@@ -513,6 +513,8 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->use_first2 = value != 0.0;
   } else if (k == "use_tma") {
     c->use_tma = value != 0.0;
+  } else if (k == "op2_tiled") {
+    c->op2_tiled = value != 0.0;
   } else if (k == "nl_tiled") {
     c->nl_tiled = value != 0.0;
   } else {

@@ -230,6 +230,7 @@ struct pfh_ctx {
   bool jac_quadrature_fp32 = false;
   bool use_first2 = true;  // 3-D: first two Chebyshev iterates in one pass over r (k_cheb_first2)
   int basis_precision = 0;  // Krylov basis storage: 0 = fp32 when krylov_rtol >= 1e-6 else fp64, 1 = fp64, 2 = fp32
+  bool op2_tiled = true;  // 2-D crossed mesh: square-centric residual / J.v (pfh_op2_tiled.cuh); false: the vertex-centric gather k2_op
   bool nl_tiled = true;  // PFH_PROBLEM_NLDIFF: square-centric tiled kernels (false: the vertex-centric gather kernels)
   bool use_tma = true;  // 3-D fast path: staged kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu); false = gather kernels only
   bool use_tma_loader = true;  // stage with TMA when the operands allow it (false: always the cp.async loader; testing)

@@ -12,6 +12,7 @@
 // Thread mapping: 3-D kernels use (BX x BY) tiles of an x-y plane and march along z so the three planes a vertex
 // reads stay in L1; 2-D kernels use 64 x 4 tiles with one corner vertex and one cell centre per thread.
 #include "pfh_vertex.cuh"
+#include "pfh_op2_tiled.cuh"
 
 namespace {
 
@@ -135,6 +136,30 @@ __global__ void __launch_bounds__(TPB) k2_op(P prob, Mesh2 m, LinCoefs L, const 
     const long long i = m.ncorner + (long long)iy * m.nx + ix;
 #pragma unroll
     for (int a = 0; a < P::NF; ++a) out[a * m.n_owned + i] = o[a];
+  }
+}
+
+// square-centric form of k2_op (pfh_op2_tiled.cuh): every crossed square is evaluated once per launch
+template <class P, bool JAC>
+__global__ void __launch_bounds__(op2t::SX* op2t::SY) k2_op_tiled(P prob, Mesh2 m, LinCoefs L, const double* __restrict__ OP,
+                                                                   const double* __restrict__ EX, double* __restrict__ out) {
+  __shared__ op2t::Tile<P, JAC> s;
+  const int x0 = blockIdx.x * op2t::WX - 1, y0 = blockIdx.y * op2t::WY - 1;
+  op2t::stage<P, JAC>(s, m, L, OP, EX, x0, y0, threadIdx.y * op2t::SX + threadIdx.x, op2t::SX * op2t::SY);
+  __syncthreads();
+  op2t::square_phase<P, JAC>(s, prob, m, L, x0, y0, threadIdx.x, threadIdx.y, out);
+  __syncthreads();
+  op2t::vertex_phase<P, JAC>(s, prob, m, L, x0, y0, threadIdx.x, threadIdx.y, out);
+}
+template <class P, bool JAC>
+bool launch_op2_tiled(pfh_ctx* c, const LinCoefs& L, const double* op, const double* ex, double* out) {
+  if constexpr (op2t::fits<P, JAC>()) {
+    const Mesh2& m = c->m2;
+    k2_op_tiled<P, JAC><<<dim3((m.nxv + op2t::WX - 1) / op2t::WX, (m.nyv + op2t::WY - 1) / op2t::WY), dim3(op2t::SX, op2t::SY), 0,
+                          c->stream>>>(P(c->prob), m, L, op, ex, out);
+    return true;
+  } else {
+    return false;   // the staged tile of this problem (bench2: six fields) exceeds the static shared memory: gather kernel
   }
 }
 
@@ -439,7 +464,10 @@ void k_residual(pfh_ctx* c, const double* u, const double* u0, double* R) {
                          P(c->prob), c->m3, L, state_fields<P>(c, u, c->gU_lo, c->gU_hi), state_fields<P>(c, nullptr, nullptr, nullptr),
                          state_fields<P>(c, u0, c->gU0_lo, c->gU0_hi), R)));
   } else {
-    PFH_DISPATCH2(c, (k2_op<P, false><<<dim3((c->m2.nxv + 63) / 64, (c->m2.nyv + 3) / 4), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, u, nullptr, u0, R)));
+    bool done = false;
+    if (c->op2_tiled) PFH_DISPATCH2(c, (done = launch_op2_tiled<P, false>(c, L, u, u0, R)));
+    if (!done)
+      PFH_DISPATCH2(c, (k2_op<P, false><<<dim3((c->m2.nxv + 63) / 64, (c->m2.nyv + 3) / 4), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, u, nullptr, u0, R)));
   }
   PFH_CUDA(cudaGetLastError());
 }
@@ -458,7 +486,10 @@ void k_jac_apply(pfh_ctx* c, const double* ulin, const double* x, double* y) {
                          P(c->prob), c->m3, L, state_fields<P>(c, ulin, c->gU_lo, c->gU_hi), state_fields<P>(c, x, c->gX_lo, c->gX_hi),
                          state_fields<P>(c, nullptr, nullptr, nullptr), y)));
   } else {
-    PFH_DISPATCH2(c, (k2_op<P, true><<<dim3((c->m2.nxv + 63) / 64, (c->m2.nyv + 3) / 4), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, ulin, x, nullptr, y)));
+    bool done = false;
+    if (c->op2_tiled) PFH_DISPATCH2(c, (done = launch_op2_tiled<P, true>(c, L, x, ulin, y)));
+    if (!done)
+      PFH_DISPATCH2(c, (k2_op<P, true><<<dim3((c->m2.nxv + 63) / 64, (c->m2.nyv + 3) / 4), TPB, 0, c->stream>>>(P(c->prob), c->m2, L, ulin, x, nullptr, y)));
   }
   PFH_CUDA(cudaGetLastError());
 }

@@ -10,7 +10,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "libpfh_emul.so")
 _SRC = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_tables.cpp")]
 _DEPS = _SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", f)
-                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh", "pfh_nl.cuh")]
+                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh", "pfh_nl.cuh", "pfh_op2_tiled.cuh")]
 
 
 def build(user_header=None):
@@ -39,7 +39,8 @@ def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=
         z0=0, nzl=-1, glo=None, ghi=None, user_header=None):
     """mode: 0 residual, 1 jac_apply, 2 energy -> [E, M], 3 scalar op -> [Av, diag], 4 initial condition,
     5 nonlinear Jacobian block via the low-flop cube routine (3-D quartic problems), 6 its residual counterpart,
-    7 the single-precision variant of 5."""
+    7 the single-precision variant of 5, 8 / 9 residual / jac_apply through the phases of the square-centric 2-D kernel
+    (csrc/pfh_op2_tiled.cuh; returns None when the problem's tile does not fit and the product keeps the gather kernel)."""
     lib = ctypes.CDLL(build(user_header))
     nc = (ctypes.c_int * 3)(*(list(ncell) + [1] * (3 - len(ncell))))
     ln = (ctypes.c_double * 3)(*(list(length) + [1.0] * (3 - len(length))))
@@ -50,12 +51,14 @@ def run(mesh_kind, problem, ncell, length, params, dt, mode, U=None, X=None, U0=
     else:
         n = (ncell[0] + 1) * (ncell[1] + 1) + ncell[0] * ncell[1]
     arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (U, X, U0, glo, ghi)]
-    out = np.zeros({0: nf * n, 1: nf * n, 2: 2, 3: 2 * n, 4: nf * n, 5: n, 6: n, 7: n}[mode])
+    out = np.zeros({0: nf * n, 1: nf * n, 2: 2, 3: 2 * n, 4: nf * n, 5: n, 6: n, 7: n, 8: nf * n, 9: nf * n}[mode])
     icp = np.ascontiguousarray(icp if icp is not None else [0.0], dtype=np.float64)
     rc = lib.emul_run(mesh_kind, problem, nc, ln, _p(pr), len(pr), ctypes.c_double(dt), mode, z0, nzl,
                       _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(out), _p(icp))
+    if mode in (8, 9) and rc == -3:
+        return None
     assert rc == 0, rc
-    if mode in (0, 1, 4):
+    if mode in (0, 1, 4, 8, 9):
         return out.reshape(nf, n)
     if mode == 3:
         return out.reshape(2, n)

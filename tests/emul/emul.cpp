@@ -8,6 +8,7 @@
 #include "../../pfhubbenchmarks_b200/csrc/pfh_vertex.cuh"
 #include "../../pfhubbenchmarks_b200/csrc/pfh_sample.cuh"
 #include "../../pfhubbenchmarks_b200/csrc/pfh_nl.cuh"
+#include "../../pfhubbenchmarks_b200/csrc/pfh_op2_tiled.cuh"
 
 void pfh_set_error(const std::string&) {}
 
@@ -46,6 +47,29 @@ void setup(Setup& S, int mesh_kind, const int* nc, const double* len, int z0, in
     m.hx = len[0] / nc[0]; m.hy = len[1] / nc[1]; m.detJ = 0.5 * m.hx * m.hy;
     pfh_build_tables2(m, S.mT, S.kT);
     m.mT = S.mT.data(); m.kT = S.kT.data();
+  }
+}
+
+// the square-centric 2-D kernel k2_op_tiled (csrc/pfh_stencil.cu) block by block: all threads of a CTA run a phase before
+// the next one starts, as between the kernel's barriers
+template <class P, bool JAC>
+int run_tiled(const Mesh2& m, const P& prob, const LinCoefs& L, const double* OP, const double* EX, double* out) {
+  if constexpr (op2t::fits<P, JAC>()) {
+    using namespace op2t;
+    std::vector<Tile<P, JAC>> tile(1);
+    for (int by = 0; by < (m.nyv + WY - 1) / WY; ++by)
+      for (int bx = 0; bx < (m.nxv + WX - 1) / WX; ++bx) {
+        const int x0 = bx * WX - 1, y0 = by * WY - 1;
+        memset(&tile[0], 0xff, sizeof tile[0]);   // NaN fill: a read of an entry no phase wrote would show
+        for (int t = 0; t < SX * SY; ++t) stage<P, JAC>(tile[0], m, L, OP, EX, x0, y0, t, SX * SY);
+        for (int ty = 0; ty < SY; ++ty)
+          for (int tx = 0; tx < SX; ++tx) square_phase<P, JAC>(tile[0], prob, m, L, x0, y0, tx, ty, out);
+        for (int ty = 0; ty < SY; ++ty)
+          for (int tx = 0; tx < SX; ++tx) vertex_phase<P, JAC>(tile[0], prob, m, L, x0, y0, tx, ty, out);
+      }
+    return 0;
+  } else {
+    return -3;   // tile does not fit the static shared memory: the product uses the gather kernel for this problem
   }
 }
 
@@ -137,6 +161,10 @@ int run(const Setup& S, const ProblemParams& pp, double dt, int mode, const doub
   } else {
     const Mesh2& m = S.m2;
     const long long n = m.n_owned;
+    if (mode == 8 || mode == 9) {
+      for (long long i = 0; i < P::NF * n; ++i) out[i] = NAN;   // every entry must be written exactly by its owner
+      return mode == 8 ? run_tiled<P, false>(m, prob, L, U, U0, out) : run_tiled<P, true>(m, prob, L, X, U, out);
+    }
     double E = 0, Mm = 0;
 #pragma omp parallel for reduction(+ : E, Mm)
     for (long long i = 0; i < n; ++i) {

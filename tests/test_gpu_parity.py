@@ -72,6 +72,39 @@ def test_operators_match_oracle(name, ncell, length):
     ctx.close()
 
 
+@pytest.mark.parametrize("name,ncell,length", [("bench1", (30, 6), (60.0, 12.0)), ("bench1", (31, 7), (62.0, 21.0)),
+                                               ("bench1", (61, 13), (61.0, 26.0)), ("bench1", (70, 9), (140.0, 18.0)),
+                                               ("bench1", (1, 1), (2.0, 2.0)), ("bench1", (257, 130), (514.0, 260.0)),
+                                               ("bench3", (33, 9), (66.0, 18.0)), ("bench6", (33, 16), (33.0, 16.0)),
+                                               ("bench2", (12, 9), (24.0, 18.0))])
+def test_square_centric_2d_operators(name, ncell, length):
+    """k2_op_tiled (every crossed square evaluated once per launch, csrc/pfh_op2_tiled.cuh; sizes around its 31 x 7 vertex
+    tile) against the oracle and against the vertex-centric gather kernel ("op2_tiled" 0).  bench2's tile does not fit the
+    static shared memory: both settings run the gather kernel there."""
+    eng = _engine()
+    rng = np.random.default_rng(9)
+    D = discretization(name, ncell, length)
+    nf, nv = D.nf, D.nv
+    ic_o = D.prob.ic(D.mesh)
+    U = ic_o + 0.1 * rng.standard_normal((nf, nv))
+    U0 = ic_o + 0.1 * rng.standard_normal((nf, nv))
+    X = rng.standard_normal((nf, nv))
+    got = {}
+    for tiled in (1, 0):
+        ctx = eng.Context(name, ncell, length)
+        ctx.set_option("op2_tiled", tiled)
+        ctx.dt = 0.37
+        R = to_np(ctx.residual(to_dev(U), to_dev(U0)), nf)
+        Ud = to_dev(U)
+        ctx.jac_setup(Ud)
+        Y = to_np(ctx.jac_apply(to_dev(X)), nf)
+        assert rel_max(R, D.residual(U, U0, 0.37)) < 1e-13
+        assert rel_max(Y, (D.jacobian(U, 0.37) @ X.ravel()).reshape(nf, -1)) < 1e-13
+        got[tiled] = (R, Y)
+        ctx.close()
+    assert rel_max(got[1][0], got[0][0]) < 1e-14 and rel_max(got[1][1], got[0][1]) < 1e-14
+
+
 @pytest.mark.parametrize("name,ncell,length", [("bench1", (20, 14), (40.0, 28.0)), ("b13d", (9, 8, 7), (18.0, 16.0, 14.0))])
 def test_preconditioner_matches_cpu_statement(name, ncell, length):
     """P^-1 r of the CUDA Schur/Chebyshev preconditioner == oracle/krylov.SchurChebPC (same sweeps)."""
