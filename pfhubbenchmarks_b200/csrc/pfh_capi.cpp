@@ -187,6 +187,23 @@ int pfh_create(const pfh_config* cfg, pfh_ctx** out) {
     PFH_CUDA(cudaMemcpy(c->d_tables + mT.size(), kT.data(), kT.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (c->dim == 3) { c->m3.mT = c->d_tables; c->m3.kT = c->d_tables + mT.size(); }
     else { c->m2.mT = c->d_tables; c->m2.kT = c->d_tables + mT.size(); }
+    if (cfg->mesh_kind == PFH_MESH_CROSSED2D && cfg->problem == PFH_PROBLEM_BENCH6) {
+      // coarse levels of the multigrid cycle for the Poisson block (pfh_solver.cpp): meshes, their stencil tables, work vectors
+      std::vector<Mesh2> meshes;
+      std::vector<std::vector<double>> tabs;
+      pfh_mg_build_levels(c->m2, meshes, tabs);
+      for (size_t l = 0; l < meshes.size(); ++l) {
+        MgLevel L;
+        L.m = meshes[l];
+        double* d = pfh_alloc(c, tabs[l].size());
+        PFH_CUDA(cudaMemcpy(d, tabs[l].data(), tabs[l].size() * sizeof(double), cudaMemcpyHostToDevice));
+        L.m.mT = d;
+        L.m.kT = d + tabs[l].size() / 2;
+        L.x = pfh_alloc(c, L.m.n_owned + 32); L.b = pfh_alloc(c, L.m.n_owned + 32);
+        L.t = pfh_alloc(c, L.m.n_owned + 32); L.tmp = pfh_alloc(c, L.m.n_owned + 32);
+        c->mg.push_back(L);
+      }
+    }
 
     if (c->cfg.krylov_basis <= 0) c->cfg.krylov_basis = 30;
     PFH_CHECK(c->cfg.krylov_basis + 2 <= PFH_RED_MAXVALS, "krylov_basis too large");
@@ -513,6 +530,10 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     c->use_first2 = value != 0.0;
   } else if (k == "use_tma") {
     c->use_tma = value != 0.0;
+  } else if (k == "mg_cycles") {
+    PFH_CHECK(value >= 0.0 && value <= 8.0, "mg_cycles: 0 (Chebyshev solve) .. 8 V-cycles per application");
+    c->mg_cycles = (int)value;
+    c->pc_ready = false;
   } else if (k == "op2_tiled") {
     c->op2_tiled = value != 0.0;
   } else if (k == "nl_tiled") {

@@ -88,6 +88,16 @@ struct NlParams {
 
 void pfh_build_tables3(Mesh3& m, std::vector<double>& mT, std::vector<double>& kT);
 void pfh_build_tables2(Mesh2& m, std::vector<double>& mT, std::vector<double>& kT);
+// Coarse levels 1, 2, .. of the crossed mesh `fine` for the geometric multigrid (pfh_mg2.cuh): cells per direction halved
+// while both counts are even and the coarse mesh keeps at least 2 x 2 cells.  meshes[l].mT / kT point into tables[l] (host;
+// layout mT then kT, 81 doubles each).
+void pfh_mg_build_levels(const Mesh2& fine, std::vector<Mesh2>& meshes, std::vector<std::vector<double>>& tables);
+
+// one coarse level: its mesh (device table pointers in the product) and work vectors of n_owned doubles
+struct MgLevel {
+  Mesh2 m;
+  double *x = nullptr, *b = nullptr, *t = nullptr, *tmp = nullptr;
+};
 
 // Block structure the Schur/Chebyshev preconditioner works on (pfh_solver.cpp): fields (0, 1) as a Cahn-Hilliard
 // (c, mu) pair, up to four further fields with an SPD parabolic diagonal block am M + ak K, or plain Jacobi.
@@ -230,6 +240,9 @@ struct pfh_ctx {
   bool jac_quadrature_fp32 = false;
   bool use_first2 = true;  // 3-D: first two Chebyshev iterates in one pass over r (k_cheb_first2)
   int basis_precision = 0;  // Krylov basis storage: 0 = fp32 when krylov_rtol >= 1e-6 else fp64, 1 = fp64, 2 = fp32
+  // bench6 Poisson block: geometric multigrid V-cycles instead of a long Chebyshev solve (pfh_solver.cpp)
+  std::vector<MgLevel> mg;  // coarse levels 1.. of the crossed mesh (empty: no hierarchy)
+  int mg_cycles = 1;        // V-cycles per preconditioner application; 0 = the 240-sweep Chebyshev solve of round 1
   bool op2_tiled = true;  // 2-D crossed mesh: square-centric residual / J.v (pfh_op2_tiled.cuh); false: the vertex-centric gather k2_op
   bool nl_tiled = true;  // PFH_PROBLEM_NLDIFF: square-centric tiled kernels (false: the vertex-centric gather kernels)
   bool use_tma = true;  // 3-D fast path: staged kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu); false = gather kernels only
@@ -292,6 +305,12 @@ void k_nl_jac(pfh_ctx* c, const double* ulin, const double* x, double* y);
 // one Jacobi-Chebyshev sweep on A = K_{kc|ulin|} + reac M (the SPD part of -J) with right-hand side sgn*r:
 // zprev <- z + a (z - zprev) + b D^-1 (sgn r - A z) on the free vertices, zprev <- r on the Dirichlet vertices
 void k_nl_sweep(pfh_ctx* c, const double* ulin, double a, double b, double sgn, const double* r, const double* z, double* zprev);
+
+// ---- multigrid transfers on the crossed mesh (pfh_stencil.cu; arithmetic in pfh_mg2.cuh) ----
+// bc_ = scale * P^T tf on the coarse mesh mc, zero on its Dirichlet vertices when bc != 0
+void k2_mg_restrict(pfh_ctx* c, const Mesh2& mf, const Mesh2& mc, const double* tf, double scale, double* bc_, int bc);
+// xf += P xc (Dirichlet vertices of the fine mesh untouched when bc != 0)
+void k2_mg_prolong_add(pfh_ctx* c, const Mesh2& mf, const Mesh2& mc, const double* xc, double* xf, int bc);
 
 // ---- staged 3-D kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu) ----
 bool pfh_fast3_ok(const pfh_ctx* c);   // 3-D and the staged kernels are enabled

@@ -13,6 +13,7 @@
 // reads stay in L1; 2-D kernels use 64 x 4 tiles with one corner vertex and one cell centre per thread.
 #include "pfh_vertex.cuh"
 #include "pfh_op2_tiled.cuh"
+#include "pfh_mg2.cuh"
 
 namespace {
 
@@ -249,6 +250,20 @@ __global__ void __launch_bounds__(T2X* T2Y) k2_scalar_tiled(Mesh2 m, double am, 
     if (MODE == 0) out[ci] = a * ri + Av;
     else out[ci] = self + a * (self - (out_is_zero ? 0.0 : out[ci])) + (b / (cf.zc[0] + sg)) * (ri - Av);
   }
+}
+
+// multigrid transfers on the crossed mesh (pfh_mg2.cuh): one coarse / fine node per thread, gathers only
+__global__ void __launch_bounds__(TPB) k2_mg_restrict_kernel(Mesh2 mf, Mesh2 mc, const double* __restrict__ t, double scale,
+                                                             double* __restrict__ b, int bc) {
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= mc.n_owned) return;
+  b[i] = (bc && mg2::is_dirichlet(mc, i)) ? 0.0 : scale * mg2::restrict_node(mf, mc, t, i);
+}
+__global__ void __launch_bounds__(TPB) k2_mg_prolong_kernel(Mesh2 mf, Mesh2 mc, const double* __restrict__ xc, double* __restrict__ xf,
+                                                            int bc) {
+  const long long i = blockIdx.x * (long long)TPB + threadIdx.x;
+  if (i >= mf.n_owned || (bc && mg2::is_dirichlet(mf, i))) return;
+  xf[i] += mg2::prolong_node(mf, mc, xc, i);
 }
 
 template <class P>
@@ -606,6 +621,17 @@ void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst) {
   if (c->dim != 2) return;
   ProfScope ps(c, T_OTHER);
   k2_dirichlet_copy<<<grid1(c->m2.ncorner), TPB, 0, c->stream>>>(c->m2, src, dst);
+  PFH_CUDA(cudaGetLastError());
+}
+
+void k2_mg_restrict(pfh_ctx* c, const Mesh2& mf, const Mesh2& mc, const double* tf, double scale, double* b, int bc) {
+  ProfScope ps(c, T_OTHER, 8.0 * (mf.n_owned + mc.n_owned));
+  k2_mg_restrict_kernel<<<grid1(mc.n_owned), TPB, 0, c->stream>>>(mf, mc, tf, scale, b, bc);
+  PFH_CUDA(cudaGetLastError());
+}
+void k2_mg_prolong_add(pfh_ctx* c, const Mesh2& mf, const Mesh2& mc, const double* xc, double* xf, int bc) {
+  ProfScope ps(c, T_OTHER, 8.0 * (2 * mf.n_owned + mc.n_owned));
+  k2_mg_prolong_kernel<<<grid1(mf.n_owned), TPB, 0, c->stream>>>(mf, mc, xc, xf, bc);
   PFH_CUDA(cudaGetLastError());
 }
 

@@ -117,6 +117,29 @@ void pfh_build_tables3(Mesh3& m, std::vector<double>& mT, std::vector<double>& k
   for (int o = 0; o < PFH_NKOFF3; ++o) m.kI[o] = kT[13 * PFH_NKOFF3 + o];
 }
 
+void pfh_mg_build_levels(const Mesh2& fine, std::vector<Mesh2>& meshes, std::vector<std::vector<double>>& tables) {
+  meshes.clear();
+  tables.clear();
+  Mesh2 cur = fine;
+  while (cur.nx % 2 == 0 && cur.ny % 2 == 0 && cur.nx >= 4 && cur.ny >= 4) {
+    Mesh2 m = cur;
+    m.nx = cur.nx / 2; m.ny = cur.ny / 2; m.nxv = m.nx + 1; m.nyv = m.ny + 1;
+    m.ncorner = (long long)m.nxv * m.nyv; m.ncentre = (long long)m.nx * m.ny; m.n_owned = m.ncorner + m.ncentre;
+    m.hx = 2.0 * cur.hx; m.hy = 2.0 * cur.hy; m.detJ = 0.5 * m.hx * m.hy;
+    std::vector<double> mT, kT;
+    pfh_build_tables2(m, mT, kT);
+    tables.emplace_back(mT);
+    tables.back().insert(tables.back().end(), kT.begin(), kT.end());
+    meshes.push_back(m);
+    cur = m;
+  }
+  // the vectors no longer move: fix the table pointers
+  for (size_t l = 0; l < meshes.size(); ++l) {
+    meshes[l].mT = tables[l].data();
+    meshes[l].kT = tables[l].data() + tables[l].size() / 2;
+  }
+}
+
 void pfh_build_tables2(Mesh2& m, std::vector<double>& mT, std::vector<double>& kT) {
   mT.assign(9 * PFH_NOFF2, 0.0);
   kT.assign(9 * PFH_NOFF2, 0.0);

@@ -10,7 +10,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "libpfh_emul.so")
 _SRC = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_tables.cpp")]
 _DEPS = _SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", f)
-                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh", "pfh_nl.cuh", "pfh_op2_tiled.cuh")]
+                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh", "pfh_nl.cuh", "pfh_op2_tiled.cuh", "pfh_mg2.cuh", "pfh_tables.cpp")]
 
 
 def build(user_header=None):
@@ -84,6 +84,22 @@ def run_nl(ncell, length, params, mode, U, X=None, square=False):
     return out[:n], out[n:]
 
 
+def mg_transfer(ncell, length, mode, v):
+    """csrc/pfh_mg2.cuh on the CPU: mode 0 restriction P^T v (v on the crossed mesh `ncell`, result on ncell / 2), mode 1
+    prolongation P v (v on ncell / 2).  Also returns the number of coarse levels pfh_mg_build_levels finds for `ncell`."""
+    lib = ctypes.CDLL(build())
+    nc = (ctypes.c_int * 3)(*(list(ncell) + [1]))
+    ln = (ctypes.c_double * 3)(*(list(length) + [1.0]))
+    nf = (ncell[0] + 1) * (ncell[1] + 1) + ncell[0] * ncell[1]
+    ncs = (ncell[0] // 2 + 1) * (ncell[1] // 2 + 1) + (ncell[0] // 2) * (ncell[1] // 2)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros(ncs if mode == 0 else nf)
+    lib.emul_mg_transfer.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _P, _P]
+    nlev = lib.emul_mg_transfer(nc, ln, mode, _p(v), _p(out))
+    assert nlev > 0, nlev
+    return out, nlev
+
+
 def sample(mesh_kind, ncell, length, u, pts, z0=0, nzl=-1, glo=None, ghi=None):
     """csrc/pfh_sample.cuh on the CPU: values at pts ((npts, dim)); +inf outside the mesh, NaN where a slab does not own the cube."""
     lib = ctypes.CDLL(build())
@@ -118,7 +134,21 @@ def build_solver(user_header=None):
     return lib
 
 
-def newton_step(mesh_kind, problem, ncell, length, params, dt, w, w0, basis_precision=0, user_header=None, **opts):
+def mg_solve(ncell, length, cycles, rhs):
+    """x ~ K_D^-1 rhs on the crossed mesh by `cycles` V-cycles of the product's multigrid (mg_solve in csrc/pfh_solver.cpp),
+    K_D = stiffness matrix with identity rows on the corner vertices of x = 0 and x = Lx."""
+    lib = ctypes.CDLL(build_solver())
+    nc = (ctypes.c_int * 3)(*(list(ncell) + [1]))
+    ln = (ctypes.c_double * 3)(*(list(length) + [1.0]))
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    x = np.zeros_like(rhs)
+    lib.emul_mg_solve.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _P, _P]
+    rc = lib.emul_mg_solve(nc, ln, int(cycles), _p(rhs), _p(x))
+    assert rc > 0, rc
+    return x
+
+
+def newton_step(mesh_kind, problem, ncell, length, params, dt, w, w0, basis_precision=0, user_header=None, mg_cycles=1, **opts):
     """One backward-Euler step with the product's Newton-Krylov solver on the CPU.  Returns (w_new (nf, n), report dict);
     `opts` are pfh_solver_opts fields (pfhubbenchmarks_b200._lib.default_opts)."""
     from pfhubbenchmarks_b200 import _lib
@@ -131,9 +161,9 @@ def newton_step(mesh_kind, problem, ncell, length, params, dt, w, w0, basis_prec
     w0 = np.ascontiguousarray(w0, dtype=np.float64)
     rep = np.zeros(8)
     lib.emul_newton_step.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _P, ctypes.c_int, ctypes.c_double,
-                                     ctypes.c_void_p, ctypes.c_int, _P, _P, _P]
+                                     ctypes.c_void_p, ctypes.c_int, _P, _P, _P, ctypes.c_int]
     rc = lib.emul_newton_step(mesh_kind, problem, nc, ln, _p(pr), len(params), float(dt), ctypes.byref(o), int(basis_precision),
-                              _p(w.reshape(-1)), _p(w0.reshape(-1)), _p(rep))
+                              _p(w.reshape(-1)), _p(w0.reshape(-1)), _p(rep), int(mg_cycles))
     assert rc == 0, rc
     keys = ("niters", "converged", "reason", "fnorm0", "fnorm", "krylov_its", "residual_evals", "pc_applies")
     return w, dict(zip(keys, rep))

@@ -9,6 +9,7 @@
 #include "../../pfhubbenchmarks_b200/csrc/pfh_sample.cuh"
 #include "../../pfhubbenchmarks_b200/csrc/pfh_nl.cuh"
 #include "../../pfhubbenchmarks_b200/csrc/pfh_op2_tiled.cuh"
+#include "../../pfhubbenchmarks_b200/csrc/pfh_mg2.cuh"
 
 void pfh_set_error(const std::string&) {}
 
@@ -266,6 +267,23 @@ extern "C" int emul_nl(const int* ncell, const double* length, const double* par
       out[m.n + i] = d;
     }
   return 0;
+}
+
+// multigrid transfers on the crossed mesh (csrc/pfh_mg2.cuh): fine mesh = ncell, coarse = ncell / 2.  mode 0: out (coarse) =
+// P^T in (fine); mode 1: out (fine) = P in (coarse)
+extern "C" int emul_mg_transfer(const int* ncell, const double* length, int mode, const double* in, double* out) {
+  Setup S;
+  setup(S, PFH_MESH_CROSSED2D, ncell, length, 0, -1);
+  std::vector<Mesh2> meshes;
+  std::vector<std::vector<double>> tabs;
+  pfh_mg_build_levels(S.m2, meshes, tabs);
+  if (meshes.empty()) return -2;
+  const Mesh2 &mf = S.m2, &mc = meshes[0];
+  if (mode == 0)
+    for (long long i = 0; i < mc.n_owned; ++i) out[i] = mg2::restrict_node(mf, mc, in, i);
+  else
+    for (long long i = 0; i < mf.n_owned; ++i) out[i] = mg2::prolong_node(mf, mc, in, i);
+  return (int)meshes.size();
 }
 
 extern "C" int emul_run(int mesh_kind, int problem, const int* ncell, const double* length, const double* params, int nparams,

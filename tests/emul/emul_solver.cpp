@@ -226,6 +226,13 @@ void k_dirichlet_copy(pfh_ctx* c, const double* src, double* dst) {
     if (ix == 0 || ix == m.nxv - 1) dst[i] = src[i];
   }
 }
+void k2_mg_restrict(pfh_ctx*, const Mesh2& mf, const Mesh2& mc, const double* tf, double scale, double* b, int bc) {
+  for (long long i = 0; i < mc.n_owned; ++i) b[i] = (bc && mg2::is_dirichlet(mc, i)) ? 0.0 : scale * mg2::restrict_node(mf, mc, tf, i);
+}
+void k2_mg_prolong_add(pfh_ctx*, const Mesh2& mf, const Mesh2& mc, const double* xc, double* xf, int bc) {
+  for (long long i = 0; i < mf.n_owned; ++i)
+    if (!(bc && mg2::is_dirichlet(mf, i))) xf[i] += mg2::prolong_node(mf, mc, xc, i);
+}
 void k_reaction_diag(pfh_ctx* c, const double* u, int field, double floor_coef, double* sig) {
   PFH_CHECK(c->dim == 2, "reaction diagonal is only used by the 2-D multi-field problems");
   EMUL_DISPATCH(c, (reaction_diag<P>(c, u, field, floor_coef, sig)));
@@ -311,9 +318,51 @@ void comm_halo_n(pfh_ctx*, const double*, int, double*, double*, cudaStream_t) {
 // entry point: one backward-Euler step  w0 -> w  (w in: initial guess) with the product's solver on host arrays
 // report[8] = niters, converged (reason > 0), reason, fnorm0, fnorm, krylov_its, residual_evals, pc_applies
 // ---------------------------------------------------------------------------------------------------------------------
+// the multigrid solve of the bench6 Poisson block alone: x ~ K_D^-1 rhs by `cycles` V-cycles (mg_solve, csrc/pfh_solver.cpp)
+extern "C" int emul_mg_solve(const int* ncell, const double* length, int cycles, const double* rhs, double* x) {
+  try {
+    Setup S;
+    setup(S, PFH_MESH_CROSSED2D, ncell, length, 0, -1);
+    pfh_ctx c;
+    memset(&c.cfg, 0, sizeof c.cfg);
+    c.cfg.nranks = 1;
+    c.dim = 2;
+    c.m2 = S.m2;
+    memset(&c.prob, 0, sizeof c.prob);
+    c.prob.id = PFH_PROBLEM_BENCH6;
+    c.nf = c.prob.nf = 3;
+    c.n_owned = c.n_global = S.m2.n_owned;
+    g_setup[&c] = &S;
+    std::vector<std::vector<double>> store;
+    auto alloc = [&](size_t n) {
+      store.emplace_back(n, 0.0);
+      return store.back().data();
+    };
+    for (int i = 0; i < 5; ++i) c.S[i] = alloc(c.n_owned + 32);
+    std::vector<Mesh2> meshes;
+    std::vector<std::vector<double>> tabs;
+    pfh_mg_build_levels(c.m2, meshes, tabs);
+    for (const Mesh2& m : meshes) {
+      MgLevel L;
+      L.m = m;
+      L.x = alloc(m.n_owned + 32); L.b = alloc(m.n_owned + 32); L.t = alloc(m.n_owned + 32); L.tmp = alloc(m.n_owned + 32);
+      c.mg.push_back(L);
+    }
+    if (c.mg.empty()) return -2;
+    c.mg_cycles = cycles;
+    c.scalar_bc = 1;
+    mg_solve(&c, rhs, x);
+    g_setup.erase(&c);
+    return (int)c.mg.size();
+  } catch (const std::exception& e) {
+    fprintf(stderr, "emul_solver: %s\n", e.what());
+    return -1;
+  }
+}
+
 extern "C" int emul_newton_step(int mesh_kind, int problem, const int* ncell, const double* length, const double* params, int nparams,
                                 double dt, const pfh_solver_opts* opts, int basis_precision, double* w, const double* w0,
-                                double* report) {
+                                double* report, int mg_cycles) {
   try {
     Setup S;
     setup(S, mesh_kind, ncell, length, 0, -1);
@@ -349,6 +398,18 @@ extern "C" int emul_newton_step(int mesh_kind, int problem, const int* ncell, co
     for (int i = 0; i < 5; ++i) c.S[i] = alloc(c.n_owned + 32);
     if (c.dim == 2 && (problem == PFH_PROBLEM_BENCH2 || problem == PFH_PROBLEM_BENCH3 || problem == PFH_PROBLEM_USER))
       for (int i = 0; i < 4; ++i) c.SIG[i] = alloc(c.n_owned + 32);
+    std::vector<Mesh2> mg_meshes;
+    std::vector<std::vector<double>> mg_tabs;
+    c.mg_cycles = mg_cycles;
+    if (mesh_kind == PFH_MESH_CROSSED2D && problem == PFH_PROBLEM_BENCH6) {   // as pfh_create: the Poisson block's hierarchy
+      pfh_mg_build_levels(c.m2, mg_meshes, mg_tabs);
+      for (const Mesh2& m : mg_meshes) {
+        MgLevel L;
+        L.m = m;
+        L.x = alloc(m.n_owned + 32); L.b = alloc(m.n_owned + 32); L.t = alloc(m.n_owned + 32); L.tmp = alloc(m.n_owned + 32);
+        c.mg.push_back(L);
+      }
+    }
     pfh_solve_report rep;
     s_newton(&c, w, w0, opts, &rep);
     g_setup.erase(&c);

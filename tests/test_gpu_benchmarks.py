@@ -72,6 +72,31 @@ def test_bench6_golden_step_kats(golden):
     ctx.close()
 
 
+@pytest.mark.parametrize("n", [64, 100, 512])
+def test_bench6_multigrid_poisson_block(n):
+    """The preconditioner's Poisson block by one geometric-multigrid V-cycle (default) against the 240 Chebyshev sweeps it
+    replaces ("mg_cycles" 0): same Newton iterate, no more Krylov iterations -- and fewer where 240 sweeps stop resolving the
+    smooth modes (512^2).  The CPU leg (tests/test_emul_solver.py) pins the cycle itself: transfers = P1 interpolation and its
+    transpose, contraction <= 0.06 per cycle; here the device launch layer (level meshes, tables, work vectors) is what is new."""
+    from pfhubbenchmarks_b200 import engine
+    out = {}
+    for cycles in (1, 0, 2):
+        ctx = engine.Context("bench6", (n, n), (float(n), float(n)))
+        ctx.set_option("mg_cycles", cycles)
+        w0 = ctx.initial_condition(); w = w0.clone()
+        ctx.dt = 0.01
+        rep = ctx.newton_solve(w, w0, absolute_tolerance=1e-9, maximum_iterations=10, krylov_rtol=1e-8, line_search=1,
+                               krylov_maximum_iterations=5000)
+        assert rep["converged"], (cycles, rep)
+        out[cycles] = (w.cpu().numpy().reshape(3, -1), rep)
+        ctx.close()
+    for cycles in (1, 2):
+        for f in range(3):
+            assert rel_l2(out[cycles][0][f], out[0][0][f]) < 1e-6 or np.abs(out[0][0][f]).max() < 1e-12, (cycles, f)
+        assert out[cycles][1]["niters"] == out[0][1]["niters"]
+        assert out[cycles][1]["krylov_its"] <= 1.1 * out[0][1]["krylov_its"], (n, cycles, out[cycles][1], out[0][1])
+
+
 def test_bench3_first_csv_rows(golden):
     """bench3 has no committed fields; the CSV pins energy and solid fraction of the first steps."""
     csv = golden["csv"]["bench3"]
