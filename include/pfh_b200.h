@@ -173,8 +173,7 @@ long long pfh_launch_count(const pfh_ctx* ctx);
  * of the GMRES basis: 0 = fp32 when krylov_rtol >= 1e-6 else fp64 (default), 1 = fp64, 2 = fp32 (arithmetic is fp64
  * in all cases); "jac_quadrature_fp32" 0/1 (default 0): the quadrature block of the Krylov J.v of the 3-D fast path in
  * single precision (Newton's residual stays fp64); "op2_tiled" 0/1 (default 1): square-centric residual / J.v kernels on the
- * 2-D crossed mesh (0 = vertex-centric gather kernels); "scalar2_staged" 0/1: shared-memory staged form of the 2-D scalar
- * operators (sweeps, lin_apply) instead of the L1-staged one; "mg_cycles" (default 1): geometric-multigrid V-cycles per application
+ * 2-D crossed mesh (0 = vertex-centric gather kernels); "mg_cycles" (default 1): geometric-multigrid V-cycles per application
  * of the preconditioner's Poisson block (bench6), 0 = a 240-sweep Chebyshev solve instead; "nl_tiled" 0/1 (default 1): the same choice for PFH_PROBLEM_NLDIFF.
  * Unknown keys are an error. */
 int pfh_set_option(pfh_ctx* ctx, const char* key, double value);

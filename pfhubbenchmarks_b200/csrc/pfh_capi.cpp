@@ -534,8 +534,6 @@ int pfh_set_option(pfh_ctx* c, const char* key, double value) {
     PFH_CHECK(value >= 0.0 && value <= 8.0, "mg_cycles: 0 (Chebyshev solve) .. 8 V-cycles per application");
     c->mg_cycles = (int)value;
     c->pc_ready = false;
-  } else if (k == "scalar2_staged") {
-    c->scalar2_staged = value != 0.0;
   } else if (k == "op2_tiled") {
     c->op2_tiled = value != 0.0;
   } else if (k == "nl_tiled") {

@@ -243,7 +243,6 @@ struct pfh_ctx {
   // bench6 Poisson block: geometric multigrid V-cycles instead of a long Chebyshev solve (pfh_solver.cpp)
   std::vector<MgLevel> mg;  // coarse levels 1.. of the crossed mesh (empty: no hierarchy)
   int mg_cycles = 1;        // V-cycles per preconditioner application; 0 = the 240-sweep Chebyshev solve of round 1
-  bool scalar2_staged = false;  // 2-D scalar operators: shared-memory staged kernel (pfh_scalar2_staged.cuh) instead of the L1-staged one
   bool op2_tiled = true;  // 2-D crossed mesh: square-centric residual / J.v (pfh_op2_tiled.cuh); false: the vertex-centric gather k2_op
   bool nl_tiled = true;  // PFH_PROBLEM_NLDIFF: square-centric tiled kernels (false: the vertex-centric gather kernels)
   bool use_tma = true;  // 3-D fast path: staged kernels (pfh_scalar3_tma.cu, pfh_stencil3_tma.cu); false = gather kernels only

@@ -14,7 +14,6 @@
 #include "pfh_vertex.cuh"
 #include "pfh_op2_tiled.cuh"
 #include "pfh_mg2.cuh"
-#include "pfh_scalar2_staged.cuh"
 
 namespace {
 
@@ -267,19 +266,6 @@ __global__ void __launch_bounds__(TPB) k2_mg_prolong_kernel(Mesh2 mf, Mesh2 mc, 
   xf[i] += mg2::prolong_node(mf, mc, xc, i);
 }
 
-// shared-memory staged form of k2_scalar_tiled (pfh_scalar2_staged.cuh)
-template <int MODE>
-__global__ void __launch_bounds__(sc2::TX* sc2::TY, 6) k2_scalar_staged(Mesh2 m, double am, double ak, sc2::Coefs cf, double a, double b,
-                                                                       const double* __restrict__ in, const double* __restrict__ r,
-                                                                       double* __restrict__ out, int out_is_zero, int bc,
-                                                                       const double* __restrict__ sig) {
-  __shared__ sc2::Tile s;
-  const int x0 = blockIdx.x * sc2::TX, y0 = blockIdx.y * sc2::TY;
-  sc2::stage(s, m, in, x0, y0, threadIdx.y * sc2::TX + threadIdx.x, sc2::TX * sc2::TY);
-  __syncthreads();
-  sc2::compute<MODE>(s, m, am, ak, cf, a, b, r, out, out_is_zero, bc, sig, x0, y0, threadIdx.x, threadIdx.y);
-}
-
 template <class P>
 __global__ void __launch_bounds__(TPB) k2_energy(P prob, Mesh2 m, const double* __restrict__ U, double* __restrict__ partial) {
   double acc[2] = {0.0, 0.0};
@@ -416,13 +402,6 @@ Coef2 coef2(const Mesh2& m, double am, double ak) {
   return cf;
 }
 dim3 grid2_tiled(const Mesh2& m) { return dim3((m.nxv + T2X - 1) / T2X, (m.nyv + T2Y - 1) / T2Y); }
-sc2::Coefs coefs_staged(const Mesh2& m, double am, double ak) {
-  sc2::Coefs cf;
-  for (int o = 0; o < PFH_NOFF2; ++o) cf.cc[o] = am * m.mI[o] + ak * m.kI[o];
-  for (int o = 0; o < 5; ++o) cf.zc[o] = am * m.mC[o] + ak * m.kC[o];
-  return cf;
-}
-dim3 grid2_staged(const Mesh2& m) { return dim3((m.nxv + sc2::TX - 1) / sc2::TX, (m.nyv + sc2::TY - 1) / sc2::TY); }
 
 dim3 grid3(const Mesh3& m) { return dim3((m.nxv + BX - 1) / BX, (m.nyv + BY - 1) / BY, (m.nzl + ZCHUNK - 1) / ZCHUNK); }
 int grid1(long long n) { return (int)((n + TPB - 1) / TPB); }
@@ -546,9 +525,6 @@ void k_lin_apply(pfh_ctx* c, double am, double ak, FieldRef in, double s, const 
   }
   if (c->dim == 3)
     k3_scalar<0><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, s, 0.0, in, add, out, false);
-  else if (c->scalar2_staged)
-    k2_scalar_staged<0><<<grid2_staged(c->m2), dim3(sc2::TX, sc2::TY), 0, c->stream>>>(c->m2, am, ak, coefs_staged(c->m2, am, ak), s, 0.0, in.p,
-                                                                                          add, out, 0, c->scalar_bc, c->scalar_sig);
   else
     k2_scalar_tiled<0><<<grid2_tiled(c->m2), dim3(T2X, T2Y), 0, c->stream>>>(c->m2, am, ak, coef2(c->m2, am, ak), s, 0.0, in.p, add, out, 0,
                                                                                   c->scalar_bc, c->scalar_sig);
@@ -581,9 +557,6 @@ void k_cheb_sweep(pfh_ctx* c, double am, double ak, double a, double b, const do
   PFH_CHECK(zprev_b0 == 0.0, "internal: recomputed first iterate needs the staged 3-D kernel");
   if (c->dim == 3)
     k3_scalar<2><<<grid3(c->m3), dim3(BX, BY), 0, c->stream>>>(c->m3, am, ak, a, b, z, r, zprev, zprev_is_zero);
-  else if (c->scalar2_staged)
-    k2_scalar_staged<2><<<grid2_staged(c->m2), dim3(sc2::TX, sc2::TY), 0, c->stream>>>(c->m2, am, ak, coefs_staged(c->m2, am, ak), a, b, z.p, r,
-                                                                                          zprev, zprev_is_zero ? 1 : 0, c->scalar_bc, c->scalar_sig);
   else
     k2_scalar_tiled<2><<<grid2_tiled(c->m2), dim3(T2X, T2Y), 0, c->stream>>>(c->m2, am, ak, coef2(c->m2, am, ak), a, b, z.p, r, zprev,
                                                                                   zprev_is_zero ? 1 : 0, c->scalar_bc, c->scalar_sig);

@@ -10,7 +10,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "libpfh_emul.so")
 _SRC = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", "pfh_tables.cpp")]
 _DEPS = _SRC + [os.path.join(_ROOT, "pfhubbenchmarks_b200", "csrc", f)
-                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh", "pfh_nl.cuh", "pfh_op2_tiled.cuh", "pfh_mg2.cuh", "pfh_scalar2_staged.cuh", "pfh_tables.cpp")]
+                for f in ("pfh_vertex.cuh", "pfh_elem.cuh", "pfh_problems.cuh", "pfh_internal.h", "pfh_sample.cuh", "pfh_nl.cuh", "pfh_op2_tiled.cuh", "pfh_mg2.cuh", "pfh_tables.cpp")]
 
 
 def build(user_header=None):
@@ -82,20 +82,6 @@ def run_nl(ncell, length, params, mode, U, X=None, square=False):
     rc = lib.emul_nl(nc, ln, _p(pr), mode, int(square), _p(U), _p(X), _p(out))
     assert rc == 0, rc
     return out[:n], out[n:]
-
-
-def scalar2_staged(ncell, length, am, ak, mode, a, b, vin, r, out, out_is_zero=False, bc=False, sig=None):
-    """csrc/pfh_scalar2_staged.cuh on the CPU (see emul_scalar2_staged in emul.cpp); `out` is read (mode 2) and returned."""
-    lib = ctypes.CDLL(build())
-    nc = (ctypes.c_int * 3)(*(list(ncell) + [1]))
-    ln = (ctypes.c_double * 3)(*(list(length) + [1.0]))
-    arrs = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in (vin, r, sig)]
-    out = np.ascontiguousarray(out, dtype=np.float64).copy()
-    lib.emul_scalar2_staged.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double,
-                                        ctypes.c_double, _P, _P, _P, ctypes.c_int, ctypes.c_int, _P]
-    rc = lib.emul_scalar2_staged(nc, ln, am, ak, mode, a, b, _p(arrs[0]), _p(arrs[1]), _p(out), int(out_is_zero), int(bc), _p(arrs[2]))
-    assert rc == 0, rc
-    return out
 
 
 def mg_transfer(ncell, length, mode, v):

@@ -10,7 +10,6 @@
 #include "../../pfhubbenchmarks_b200/csrc/pfh_nl.cuh"
 #include "../../pfhubbenchmarks_b200/csrc/pfh_op2_tiled.cuh"
 #include "../../pfhubbenchmarks_b200/csrc/pfh_mg2.cuh"
-#include "../../pfhubbenchmarks_b200/csrc/pfh_scalar2_staged.cuh"
 
 void pfh_set_error(const std::string&) {}
 
@@ -266,31 +265,6 @@ extern "C" int emul_nl(const int* ncell, const double* length, const double* par
       else nl::vertex_op<2>(m, p, U, X, ix, iy, v, d);
       out[i] = v;
       out[m.n + i] = d;
-    }
-  return 0;
-}
-
-// k2_scalar_staged (csrc/pfh_scalar2_staged.cuh) block by block: mode 0: out = a r + A in; mode 2: out <- in + a (in - out)
-// + b D^-1 (r - A in), A = am M + ak K on the crossed mesh; bc: Dirichlet identity rows on x = 0, Lx; sig: optional diagonal
-extern "C" int emul_scalar2_staged(const int* ncell, const double* length, double am, double ak, int mode, double a, double b,
-                                   const double* in, const double* r, double* out, int out_is_zero, int bc, const double* sig) {
-  Setup S;
-  setup(S, PFH_MESH_CROSSED2D, ncell, length, 0, -1);
-  const Mesh2& m = S.m2;
-  sc2::Coefs cf;
-  for (int o = 0; o < PFH_NOFF2; ++o) cf.cc[o] = am * m.mI[o] + ak * m.kI[o];
-  for (int o = 0; o < 5; ++o) cf.zc[o] = am * m.mC[o] + ak * m.kC[o];
-  std::vector<sc2::Tile> tile(1);
-  for (int by = 0; by < (m.nyv + sc2::TY - 1) / sc2::TY; ++by)
-    for (int bx = 0; bx < (m.nxv + sc2::TX - 1) / sc2::TX; ++bx) {
-      const int x0 = bx * sc2::TX, y0 = by * sc2::TY;
-      memset(&tile[0], 0xff, sizeof tile[0]);
-      for (int t = 0; t < sc2::TX * sc2::TY; ++t) sc2::stage(tile[0], m, in, x0, y0, t, sc2::TX * sc2::TY);
-      for (int ty = 0; ty < sc2::TY; ++ty)
-        for (int tx = 0; tx < sc2::TX; ++tx) {
-          if (mode == 0) sc2::compute<0>(tile[0], m, am, ak, cf, a, b, r, out, out_is_zero, bc, sig, x0, y0, tx, ty);
-          else sc2::compute<2>(tile[0], m, am, ak, cf, a, b, r, out, out_is_zero, bc, sig, x0, y0, tx, ty);
-        }
     }
   return 0;
 }

@@ -195,33 +195,3 @@ def test_square_centric_2d_kernel_phases(name, pid, ncell, length):
     # and against the vertex-centric code the gather kernel runs: same arithmetic, sums in the same order
     assert np.abs(R - emul.run(*args, 0, U=U, U0=U0, nf=nf)).max() <= 1e-14 * np.abs(R).max()
     assert np.abs(Jx - emul.run(*args, 1, U=U, X=X, nf=nf)).max() <= 1e-14 * np.abs(Jx).max()
-
-
-@pytest.mark.parametrize("ncell,length", [((7, 5), (14.0, 10.0)), ((31, 7), (31.0, 14.0)), ((32, 8), (64.0, 8.0)), ((33, 9), (33.0, 9.0)),
-                                          ((70, 21), (70.0, 42.0)), ((1, 1), (2.0, 3.0))])
-def test_staged_2d_scalar_operator_phases(ncell, length):
-    """k2_scalar_staged (csrc/pfh_scalar2_staged.cuh; sizes around its 32 x 8 tile): lin_apply and Chebyshev-sweep modes,
-    with and without Dirichlet rows and the lumped reaction diagonal, against the assembled operator."""
-    import scipy.sparse as sp
-    rng = np.random.default_rng(6)
-    D = discretization("bench1", ncell, length)
-    n = D.nv
-    am, ak = 1.3, 0.7
-    A = (am * D.V.M + ak * D.V.K).tocsr()
-    vin, r, zprev = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
-    got = emul.scalar2_staged(ncell, length, am, ak, 0, 0.6, 0.0, vin, r, np.full(n, np.nan))
-    assert rel_max(got, 0.6 * r + A @ vin) < 1e-13
-    got = emul.scalar2_staged(ncell, length, am, ak, 2, 0.4, 0.9, vin, r, zprev)
-    assert rel_max(got, vin + 0.4 * (vin - zprev) + 0.9 / A.diagonal() * (r - A @ vin)) < 1e-13
-    got = emul.scalar2_staged(ncell, length, am, ak, 2, 0.4, 0.9, vin, r, np.full(n, np.nan), out_is_zero=True)
-    assert rel_max(got, vin + 0.4 * vin + 0.9 / A.diagonal() * (r - A @ vin)) < 1e-13
-    # Dirichlet identity rows on the corner vertices of x = 0, Lx and a diagonal shift
-    nx = ncell[0]
-    ix = np.arange((nx + 1) * (ncell[1] + 1)) % (nx + 1)
-    Dv = np.where((ix == 0) | (ix == nx))[0]
-    sig = rng.random(n)
-    As = (A + sp.diags(sig)).tocsr()
-    want = vin + 0.4 * (vin - zprev) + 0.9 / As.diagonal() * (r - As @ vin)
-    want[Dv] = r[Dv]
-    got = emul.scalar2_staged(ncell, length, am, ak, 2, 0.4, 0.9, vin, r, zprev, bc=True, sig=sig)
-    assert rel_max(got, want) < 1e-13

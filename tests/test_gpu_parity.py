@@ -105,37 +105,6 @@ def test_square_centric_2d_operators(name, ncell, length):
     assert rel_max(got[1][0], got[0][0]) < 1e-14 and rel_max(got[1][1], got[0][1]) < 1e-14
 
 
-@pytest.mark.parametrize("name,ncell,length", [("bench1", (70, 21), (140.0, 42.0)), ("bench1", (33, 9), (66.0, 18.0)),
-                                               ("bench1", (256, 64), (512.0, 128.0)), ("bench2", (31, 7), (62.0, 14.0)),
-                                               ("bench3", (40, 24), (80.0, 48.0)), ("bench6", (64, 32), (64.0, 32.0))])
-def test_staged_2d_scalar_operators(name, ncell, length):
-    """k2_scalar_staged (shared-memory staged sweeps / lin_apply, "scalar2_staged" 1) == k2_scalar_tiled (L1-staged, 0): the
-    whole preconditioner application (mass and shifted Chebyshev solves; bench2 / bench3: lumped reaction diagonal; bench6:
-    Dirichlet rows and every multigrid level) and the assembled-functional pieces agree to round-off."""
-    eng = _engine()
-    rng = np.random.default_rng(12)
-    D = discretization(name, ncell, length)
-    nf, nv = D.nf, D.nv
-    U = D.prob.ic(D.mesh) + 0.05 * rng.standard_normal((nf, nv))
-    r = rng.standard_normal(nf * nv)
-    got = {}
-    for staged in (1, 0):
-        ctx = eng.Context(name, ncell, length)
-        ctx.set_option("scalar2_staged", staged)
-        ctx.dt = 0.05
-        Ud = to_dev(U)
-        ctx.jac_setup(Ud)
-        ctx.precond_setup()
-        z = ctx.precond_apply(to_dev(r)).cpu().numpy()
-        quad = ctx.bilinear(Ud, 0, nf - 1, 1.3, 0.7)
-        got[staged] = (z, quad)
-        ctx.close()
-    assert rel_max(got[1][0], got[0][0]) < 1e-12
-    assert abs(got[1][1] - got[0][1]) <= 1e-13 * abs(got[0][1])
-    M, K = D.V.M, D.V.K
-    assert abs(got[1][1] - U[0] @ ((1.3 * M + 0.7 * K) @ U[nf - 1])) <= 1e-12 * abs(got[0][1])
-
-
 @pytest.mark.parametrize("name,ncell,length", [("bench1", (20, 14), (40.0, 28.0)), ("b13d", (9, 8, 7), (18.0, 16.0, 14.0))])
 def test_preconditioner_matches_cpu_statement(name, ncell, length):
     """P^-1 r of the CUDA Schur/Chebyshev preconditioner == oracle/krylov.SchurChebPC (same sweeps)."""
