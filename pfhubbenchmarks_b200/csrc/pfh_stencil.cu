@@ -200,7 +200,7 @@ struct Coef2 {
   double zc[5];          // am*M + ak*K, centre row
 };
 template <int MODE>
-__global__ void __launch_bounds__(T2X* T2Y) k2_scalar_tiled(Mesh2 m, double am, double ak, Coef2 cf, double a, double b,
+__global__ void __launch_bounds__(T2X* T2Y, 8) k2_scalar_tiled(Mesh2 m, double am, double ak, Coef2 cf, double a, double b,
                                                              const double* __restrict__ in, const double* __restrict__ r,
                                                              double* __restrict__ out, int out_is_zero, int bc,
                                                              const double* __restrict__ sig) {
