@@ -46,7 +46,10 @@ class Constant:
 
 
 class Mesh:
-    def __init__(self, kind, ncell, length):
+    """A structured DOLFIN mesh by kind and size; `Mesh()` is the empty mesh a stored series is read into
+    (`mesh = Mesh(); hdf.read(mesh, "mesh", True)`, process_bench1.py:14-15)."""
+
+    def __init__(self, kind=None, ncell=(), length=()):
         self.kind, self.ncell, self.length = kind, tuple(int(n) for n in ncell), tuple(float(v) for v in length)
 
     def mpi_comm(self):

@@ -224,6 +224,7 @@ class Function(_SymArith):
         k = next(forms._counter)
         self.symbols = [forms.FieldSymbol("w%d_%d" % (k, i), owner=self, index=i) for i in range(W.nfields)]
         self._tensor, self._pending, self._problem = None, None, None
+        self._host = None          # vertex values of a Function read back from a stored series (HDF5File.read), host numpy
 
     def __getitem__(self, i):
         return self.symbols[i]
@@ -456,13 +457,43 @@ def assemble(form):
 class HDF5File:
     """`outfile = HDF5File(MPI.comm_world, filename + ".h5", "w")`; `outfile.write(mesh, "mesh")`;
     `outfile.write(c, "c", float(t))`  (bench1.py:116-118,191).  HDF5 is not available in this image: the same time
-    series is written as <filename>.pvd + one VTU per step (what b13d.py / bench2.py write), with a warning."""
+    series is written as <filename>.pvd + one VTU per step (what b13d.py / bench2.py write), with a warning.
+    Mode "r" reads that series back the way the reference's post-processing reads its container
+    (`hdf.read(mesh, "mesh", True)`, `hdf.read(c, f"c/vector_{i}")`, process_bench1.py:8-27, b1_read.py:9-30)."""
 
     def __init__(self, comm, path, mode="w"):
+        base = path[:-3] if path.endswith(".h5") else path
+        self._mode = mode
+        if mode == "r":
+            from . import io
+            self._entries = io.read_pvd(base + ".pvd")
+            if not self._entries:
+                raise RuntimeError("%s.pvd holds no time steps" % base)
+            self._geom = None
+            return
         if mode != "w":
-            raise NotImplementedError("reading HDF5 checkpoints")
-        self._pvd = File((path[:-3] if path.endswith(".h5") else path) + ".pvd", "compressed")
+            raise NotImplementedError("HDF5File mode %r" % (mode,))
+        self._pvd = File(base + ".pvd", "compressed")
         warnings.warn("HDF5 is not available: writing %s (VTU series) instead of %s" % (self._pvd.path, path))
+
+    def read(self, obj, name, *args):
+        from . import io
+        if self._mode != "r":
+            raise RuntimeError("HDF5File opened for writing")
+        if isinstance(obj, Mesh):                      # hdf.read(mesh, "mesh", True)
+            pts, cells, _ = io.read_vtu(self._entries[0][1])
+            obj.kind, obj.ncell, obj.length = io.identify_mesh(pts, cells)
+            return
+        field, _, vec = name.partition("/vector_")      # "c/vector_12": step 12 of field c
+        if not vec.isdigit() or int(vec) >= len(self._entries):
+            raise RuntimeError("no dataset %r in the series (%d steps)" % (name, len(self._entries)))
+        data = io.read_vtu(self._entries[int(vec)][1])[2]
+        if field not in data and len(data) == 1:
+            field = next(iter(data))
+        obj._host = np.array(data[field], dtype=np.float64)
+
+    def attributes(self, name):                        # hdf.attributes("c")["count"]: number of stored steps
+        return {"count": len(self._entries)}
 
     def write(self, obj, name, t=None):
         if isinstance(obj, Mesh):                      # outfile.write(mesh, "mesh"): every VTU carries the mesh

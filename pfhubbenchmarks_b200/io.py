@@ -43,11 +43,52 @@ def box_mesh(nx, ny, nz, Lx, Ly, Lz):
     return pts, cells
 
 
+def right_mesh(nx, ny, Lx, Ly):
+    """(points, cells (m,3)) of df.UnitSquareMesh-style right-diagonal meshes (dolfin/nl.py:20)."""
+    hx, hy = Lx / nx, Ly / ny
+    jx, jy = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")
+    pts = np.stack([jx.ravel() * hx, jy.ravel() * hy, np.zeros(jx.size)], axis=1)
+    cx, cy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    v0 = (cy * (nx + 1) + cx).ravel()
+    tri = np.stack([v0, v0 + 1, v0 + nx + 2, v0, v0 + nx + 1, v0 + nx + 2], axis=1)
+    return pts, tri.reshape(-1, 3)
+
+
 def mesh_of(mesh):
     """Points / cells of a pfhubbenchmarks_b200.api.Mesh."""
     if mesh.kind == "crossed2d":
         return crossed_mesh(mesh.ncell[0], mesh.ncell[1], mesh.length[0], mesh.length[1])
+    if mesh.kind == "right2d":
+        return right_mesh(mesh.ncell[0], mesh.ncell[1], mesh.length[0], mesh.length[1])
     return box_mesh(*mesh.ncell, *mesh.length)
+
+
+def identify_mesh(points, cells):
+    """(kind, ncell, length) of a stored structured mesh -- the inverse of mesh_of, from the vertex coordinates alone
+    (corners are stored x-fastest): what `hdf.read(mesh, "mesh", True)` recovers (process_bench1.py:14-15).  Every candidate
+    size is checked by regenerating the mesh and comparing points and connectivity."""
+    from .api import Mesh
+    pts = np.asarray(points, dtype=float)
+    cells = np.asarray(cells)
+    n = len(pts)
+    nxv = int(np.argmax(pts[:, 1] > 0)) if np.any(pts[:, 1] > 0) else n           # first vertex of the second row
+    cands = []
+    if cells.shape[1] == 4 and np.any(pts[:, 2] > 0):
+        nxy = int(np.argmax(pts[:, 2] > 0))
+        if nxv >= 2 and nxy % nxv == 0 and n % nxy == 0:
+            cands.append(("kuhn3d", (nxv - 1, nxy // nxv - 1, n // nxy - 1), tuple(float(v) for v in pts.max(axis=0))))
+    elif cells.shape[1] == 3 and nxv >= 2:
+        length = tuple(float(v) for v in pts[:, :2].max(axis=0))
+        for nyv in range(2, n // nxv + 1):                                          # corners only, or corners + centres
+            if nxv * nyv == n:
+                cands.append(("right2d", (nxv - 1, nyv - 1), length))
+            if nxv * nyv + (nxv - 1) * (nyv - 1) == n:
+                cands.append(("crossed2d", (nxv - 1, nyv - 1), length))
+    for kind, ncell, length in cands:
+        gp, gc = mesh_of(Mesh(kind, ncell, length))
+        if gp.shape == pts.shape and gc.shape == cells.shape and np.allclose(gp, pts, atol=1e-9 * max(length)) and np.array_equal(gc, cells):
+            return kind, ncell, length
+    raise ValueError("the stored mesh is not one of the structured DOLFIN meshes (crossed / right-diagonal rectangle, box)")
 
 
 def _b64_zlib(arr, block=32768):
@@ -119,7 +160,14 @@ class File:
     def __lshift__(self, pair):
         """`file << (c, t)` with c a component of a Function (`c, _ = w.split()`, bench2.py:269-274), a device tensor or
         a numpy array; the mesh is taken from the Function when the File was opened without one, as in the reference."""
-        values, t = pair
+        if hasattr(pair, "kind") and hasattr(pair, "ncell"):       # `file << mesh` (process_bench1.py:39): every VTU carries it
+            self.mesh = pair
+            return self
+        values, t = pair if isinstance(pair, tuple) else (pair, len(self.entries))   # `file << c` numbers the steps itself
+        if hasattr(values, "_host") and values._host is not None:  # a Function read back from a stored series
+            if self.mesh is None:
+                self.mesh = values.W.mesh
+            values = values._host
         if hasattr(values, "owner"):                      # dolfin.SubFunction
             if self.mesh is None:
                 self.mesh = values.owner.W.mesh

@@ -77,3 +77,46 @@ def test_product_reader_on_the_committed_reference_series(golden):
     assert v2.shape == (29, 20201)
     for k, idx in enumerate(g2["index"]):
         assert t2[int(idx)] == g2["times"][k] and np.array_equal(v2[int(idx)], g2["fields"][k, 0])
+
+
+@pytest.mark.parametrize("kind,ncell,length", [("crossed2d", (6, 4), (12.0, 8.0)), ("crossed2d", (1, 3), (2.0, 6.0)),
+                                               ("right2d", (5, 7), (1.0, 1.0)), ("kuhn3d", (3, 4, 2), (6.0, 8.0, 4.0))])
+def test_stored_series_is_read_back_like_the_reference_post_processing(tmp_path, kind, ncell, length):
+    """process_bench1.py:8-43 / b1_read.py:9-30 on the container the HDF5File stand-in writes: open "r", read the mesh into
+    an empty Mesh(), read every `c/vector_{i}` into a Function of a P1 space on it, re-emit the series with `File << c`."""
+    import pfhubbenchmarks_b200.dolfin as df
+    from pfhubbenchmarks_b200 import io
+    from pfhubbenchmarks_b200.api import Mesh
+    mesh = Mesh(kind, ncell, length)
+    pts, cells = io.mesh_of(mesh)
+    assert io.identify_mesh(pts, cells) == (kind, ncell, length)
+    rng = np.random.default_rng(0)
+    series = rng.standard_normal((3, len(pts)))
+    with pytest.warns(UserWarning, match="HDF5 is not available"):
+        out = df.HDF5File(df.MPI.comm_world, str(tmp_path / "conc.h5"), "w")
+    out.write(mesh, "mesh")
+    for i, v in enumerate(series):
+        out.write(v, "c", 0.1 * i)
+    out.close()
+    # the reader's side, in the reference's words
+    hdf = df.HDF5File(df.MPI.comm_world, str(tmp_path / "conc.h5"), "r")
+    back = df.Mesh()
+    hdf.read(back, "mesh", True)
+    assert (back.kind, back.ncell, back.length) == (kind, ncell, length)
+    V = df.FunctionSpace(back, "P", 1)
+    cs = []
+    for i in range(hdf.attributes("c")["count"]):
+        c = df.Function(V)
+        hdf.read(c, "c/vector_%d" % i)
+        cs.append(c)
+    assert len(cs) == 3 and all(np.array_equal(c._host, v) for c, v in zip(cs, series))
+    with pytest.raises(RuntimeError):
+        hdf.read(df.Function(V), "c/vector_3")
+    pvd = df.File(str(tmp_path / "again" / "c.pvd"), "compressed")
+    pvd << back
+    for c in cs:
+        pvd << c
+    times, vals = io.read_series(str(tmp_path / "again" / "c.pvd"))
+    assert np.array_equal(times, [0.0, 1.0, 2.0]) and np.array_equal(vals, series)
+    p2, c2, _ = io.read_vtu(str(tmp_path / "again" / "c000000.vtu"))
+    assert np.allclose(p2, pts) and np.array_equal(c2, cells)
