@@ -159,8 +159,10 @@ def test_function_storage_is_deferred():
     with pytest.raises(NotImplementedError):
         df.Constant((1.0, 0.0))
     assert isinstance(df.Constant((0.0, 0.0)), forms.VectorZero)
+    with pytest.raises(FileNotFoundError):
+        df.HDF5File(None, "no_such_series.h5", "r")      # mode "r" reads the stand-in's own series (tests/test_io.py)
     with pytest.raises(NotImplementedError):
-        df.HDF5File(None, "x.h5", "r")
+        df.HDF5File(None, "x.h5", "a")
     with pytest.warns(UserWarning, match="HDF5 is not available"):
         h5 = df.HDF5File(None, "results/conc.h5", "w")          # stands in with a VTU series next to the requested file
     assert h5._pvd.path == "results/conc.pvd"
